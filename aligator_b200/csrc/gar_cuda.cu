@@ -1,0 +1,413 @@
+// gar_cuda.cu -- sm_100a kernels + C-ABI implementation (include/aligator_b200/gar.h).
+//
+// The arithmetic lives in riccati_group.cuh (one group of G lanes per problem
+// instance).  This file supplies the device execution context -- TMA bulk copies
+// (cp.async.bulk, SASS UBLKCP) completing on per-group mbarriers, or cp.async
+// (LDGSTS) staging -- the persistent-sweep kernel, the shape dispatch and the
+// host-side handle.  No CPU fallback: every entry point fails loudly without a
+// CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aligator_b200/gar.h"
+#include "riccati_configs.h"
+#include "riccati_launch.cuh"
+
+namespace ab2 {
+
+// cycleAppend support: shift the per-knot records of every instance one knot left.
+__global__ void shift_left_kernel(double *base, long inst_stride, int nrec, int rec, int last_zero) {
+  double *b = base + (size_t)blockIdx.x * inst_stride;
+  for (int t = 0; t + 1 < nrec; ++t) {
+    for (int i = threadIdx.x; i < rec; i += blockDim.x)
+      b[(size_t)t * rec + i] = b[(size_t)(t + 1) * rec + i];
+    __syncthreads();
+  }
+  if (last_zero && nrec > 0)
+    for (int i = threadIdx.x; i < rec; i += blockDim.x)
+      b[(size_t)(nrec - 1) * rec + i] = 0.0;
+}
+
+// one KernelEntry per compile-time shape, each defined in its own object file
+// (kernel_inst.cu compiled with -DAB2_NX=.. -DAB2_NU=.. -DAB2_NC=.. -DAB2_G=..)
+#define X(NX, NU, NC, G) extern const KernelEntry kEntry_##NX##_##NU##_##NC;
+AB2_FOR_EACH_CONFIG(X)
+#undef X
+static const KernelEntry *const kTable[] = {
+#define X(NX, NU, NC, G) &kEntry_##NX##_##NU##_##NC,
+    AB2_FOR_EACH_CONFIG(X)
+#undef X
+};
+
+static const KernelEntry *find_kernel(int nx, int nu, int nc) {
+  for (const KernelEntry *e : kTable)
+    if (e->nx == nx && e->nu == nu && e->nc == nc)
+      return e;
+  return nullptr;
+}
+
+} // namespace ab2
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(AB2_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+  } while (0)
+} // namespace
+
+struct ab2_gar_solver {
+  ab2_gar_dims d;
+  const ab2::KernelEntry *k;
+  int srec, trec, nr;
+  ab2::SweepParams p;
+  // owned device storage
+  double *own_stage = nullptr, *own_term = nullptr, *own_G0 = nullptr, *own_g0 = nullptr;
+  double *out[AB2_OUT_COUNT] = {};
+  size_t out_doubles[AB2_OUT_COUNT] = {};
+  size_t out_rec[AB2_OUT_COUNT] = {};  // doubles per knot (or per instance)
+  int out_knots[AB2_OUT_COUNT] = {};   // knots per instance (1 for per-instance arrays)
+  int *status = nullptr;
+  bool have_problem = false, have_backward = false;
+  long launches = 0;
+  int variant = 0;
+  int group_doubles[2] = {0, 0};
+};
+
+static size_t stage_total(const ab2_gar_solver *s) {
+  return (size_t)s->d.batch * s->d.horizon * s->srec;
+}
+
+extern "C" {
+
+const char *ab2_gar_last_error(void) { return g_err.c_str(); }
+const char *ab2_gar_version(void) { return "aligator_b200 gar 0.1 (sm_100a)"; }
+
+size_t ab2_gar_stage_record_doubles(int nx, int nu, int nc) {
+  size_t n = 2 * (size_t)nx * nx + 2 * (size_t)nx * nu + (size_t)nu * nu + 2 * (size_t)nx + nu +
+             (size_t)nc * (nx + nu + 1);
+  return (n + 1) & ~(size_t)1;
+}
+size_t ab2_gar_term_record_doubles(int nx, int nct) {
+  return (size_t)nx * nx + nx + (size_t)nct * nx + nct;
+}
+int ab2_gar_supported(int nx, int nu, int nc, int nc0) {
+  const ab2::KernelEntry *k = ab2::find_kernel(nx, nu, nc);
+  return (k && nx + nc0 <= k->G) ? 1 : 0;
+}
+
+int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
+  if (!dims || !out)
+    return fail(AB2_ERR_INVALID, "null argument");
+  const ab2_gar_dims &d = *dims;
+  if (d.nx < 1 || d.nu < 1 || d.nc < 0 || d.nct < 0 || d.nc0 < 0 || d.horizon < 0 || d.batch < 1)
+    return fail(AB2_ERR_INVALID, "bad dimensions");
+  const ab2::KernelEntry *k = ab2::find_kernel(d.nx, d.nu, d.nc);
+  if (!k)
+    return fail(AB2_ERR_UNSUPPORTED, "no kernel instantiation for (nx,nu,nc) = (" + std::to_string(d.nx) +
+                                         "," + std::to_string(d.nu) + "," + std::to_string(d.nc) + ")");
+  if (d.nx + d.nc0 > k->G)
+    return fail(AB2_ERR_UNSUPPORTED, "nx + nc0 exceeds the group size of this kernel");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (d.device < 0 || d.device >= ndev)
+    return fail(AB2_ERR_CUDA, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(d.device));
+  auto *s = new ab2_gar_solver();
+  s->d = d;
+  s->k = k;
+  s->srec = k->srec_pad;
+  s->trec = (int)ab2_gar_term_record_doubles(d.nx, d.nct);
+  s->nr = d.nu + d.nc + d.nx;
+  k->group_doubles(d.nc0, s->group_doubles);
+  const int N = d.horizon, B = d.batch, nx = d.nx;
+  auto setup = [&](int what, size_t rec, int knots) {
+    s->out_rec[what] = rec;
+    s->out_knots[what] = knots;
+    s->out_doubles[what] = (size_t)B * knots * rec;
+  };
+  setup(AB2_OUT_FF, s->nr, N);
+  setup(AB2_OUT_FB, (size_t)s->nr * nx, N);
+  setup(AB2_OUT_VXX, (size_t)nx * nx, N + 1);
+  setup(AB2_OUT_VX, nx, N + 1);
+  setup(AB2_OUT_FFT, d.nct, 1);
+  setup(AB2_OUT_FBT, (size_t)d.nct * nx, 1);
+  setup(AB2_OUT_KKT0, nx + d.nc0, 1);
+  setup(AB2_OUT_XS, nx, N + 1);
+  setup(AB2_OUT_US, d.nu, N);
+  setup(AB2_OUT_VS, d.nc, N);
+  setup(AB2_OUT_VST, d.nct, 1);
+  setup(AB2_OUT_LBD0, d.nc0, 1);
+  setup(AB2_OUT_LBDAS, nx, N);
+  for (int w = 0; w < AB2_OUT_COUNT; ++w) {
+    const size_t bytes = (s->out_doubles[w] > 0 ? s->out_doubles[w] : 1) * sizeof(double);
+    cudaError_t e = cudaMalloc(&s->out[w], bytes);
+    if (e == cudaSuccess)
+      e = cudaMemset(s->out[w], 0, bytes);
+    if (e != cudaSuccess) {
+      ab2_gar_destroy(s);
+      return fail(AB2_ERR_CUDA, std::string("cudaMalloc outputs: ") + cudaGetErrorString(e));
+    }
+  }
+  {
+    cudaError_t e = cudaMalloc(&s->status, sizeof(int) * B);
+    if (e == cudaSuccess)
+      e = cudaMemset(s->status, 0, sizeof(int) * B);
+    if (e != cudaSuccess) {
+      ab2_gar_destroy(s);
+      return fail(AB2_ERR_CUDA, std::string("cudaMalloc status: ") + cudaGetErrorString(e));
+    }
+  }
+  ab2::SweepParams &p = s->p;
+  std::memset(&p, 0, sizeof(p));
+  p.N = N;
+  p.nct = d.nct;
+  p.nc0 = d.nc0;
+  p.batch = B;
+  p.ff = s->out[AB2_OUT_FF];
+  p.fb = s->out[AB2_OUT_FB];
+  p.Vxx = s->out[AB2_OUT_VXX];
+  p.vx = s->out[AB2_OUT_VX];
+  p.ffT = s->out[AB2_OUT_FFT];
+  p.fbT = s->out[AB2_OUT_FBT];
+  p.kkt0 = s->out[AB2_OUT_KKT0];
+  p.xs = s->out[AB2_OUT_XS];
+  p.us = s->out[AB2_OUT_US];
+  p.vs = s->out[AB2_OUT_VS];
+  p.vsT = s->out[AB2_OUT_VST];
+  p.lbd0 = s->out[AB2_OUT_LBD0];
+  p.lbdas = s->out[AB2_OUT_LBDAS];
+  p.status = s->status;
+  *out = s;
+  return AB2_OK;
+}
+
+int ab2_gar_destroy(ab2_gar_solver *s) {
+  if (!s)
+    return AB2_OK;
+  cudaSetDevice(s->d.device);
+  for (int w = 0; w < AB2_OUT_COUNT; ++w)
+    if (s->out[w])
+      cudaFree(s->out[w]);
+  if (s->status)
+    cudaFree(s->status);
+  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0})
+    if (q)
+      cudaFree(q);
+  delete s;
+  return AB2_OK;
+}
+
+int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t) {
+  if (!s || !t)
+    return fail(AB2_ERR_INVALID, "null argument");
+  if (t->variant < -1 || t->variant > 3)
+    return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..3");
+  s->variant = t->variant < 0 ? 0 : t->variant;
+  return AB2_OK;
+}
+
+int ab2_gar_set_problem(ab2_gar_solver *s, const double *stage, const double *term, const double *G0,
+                        const double *g0, int memspace, void *stream) {
+  if (!s)
+    return fail(AB2_ERR_INVALID, "null solver");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_stage = stage_total(s), n_term = (size_t)s->d.batch * s->trec,
+               n_G0 = (size_t)s->d.batch * s->d.nc0 * s->d.nx, n_g0 = (size_t)s->d.batch * s->d.nc0;
+  if (memspace == AB2_DEVICE) {
+    if (stage)
+      s->p.stage = stage;
+    if (term)
+      s->p.term = term;
+    if (G0)
+      s->p.G0 = G0;
+    if (g0)
+      s->p.g0 = g0;
+  } else if (memspace == AB2_HOST) {
+    auto up = [&](double *&own, const double *src, size_t n, const double *&dst) -> int {
+      if (!src)
+        return AB2_OK;
+      if (!own)
+        CUDA_TRY(cudaMalloc(&own, (n > 0 ? n : 1) * sizeof(double)));
+      if (n)
+        CUDA_TRY(cudaMemcpyAsync(own, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
+      dst = own;
+      return AB2_OK;
+    };
+    int rc;
+    if ((rc = up(s->own_stage, stage, n_stage, s->p.stage)) != AB2_OK)
+      return rc;
+    if ((rc = up(s->own_term, term, n_term, s->p.term)) != AB2_OK)
+      return rc;
+    if ((rc = up(s->own_G0, G0, n_G0, s->p.G0)) != AB2_OK)
+      return rc;
+    if ((rc = up(s->own_g0, g0, n_g0, s->p.g0)) != AB2_OK)
+      return rc;
+  } else {
+    return fail(AB2_ERR_INVALID, "memspace must be AB2_HOST or AB2_DEVICE");
+  }
+  s->have_problem = s->p.stage && s->p.term && (s->p.G0 || s->d.nc0 == 0) && (s->p.g0 || s->d.nc0 == 0);
+  if (s->d.horizon == 0 && s->p.term)
+    s->have_problem = true;
+  return AB2_OK;
+}
+
+static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream) {
+  if (!s)
+    return fail(AB2_ERR_INVALID, "null solver");
+  if (!s->have_problem)
+    return fail(AB2_ERR_STATE, "set_problem has not been called with all four buffers");
+  if (fwd && !bwd && !s->have_backward)
+    return fail(AB2_ERR_STATE, "forward() before backward()");
+  if (bwd && !(mueq > 0.0) && (s->d.nc > 0 || s->d.nct > 0))
+    return fail(AB2_ERR_INVALID, "mueq must be > 0 when constraints are present");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  s->p.mueq = mueq;
+  s->p.do_bwd = bwd;
+  s->p.do_fwd = fwd;
+  CUDA_TRY(s->k->launch(s->p, s->variant, s->group_doubles, (cudaStream_t)stream, nullptr));
+  s->launches += 1;
+  if (bwd)
+    s->have_backward = true;
+  return AB2_OK;
+}
+
+int ab2_gar_backward(ab2_gar_solver *s, double mueq, void *stream) { return launch(s, mueq, 1, 0, stream); }
+int ab2_gar_forward(ab2_gar_solver *s, void *stream) { return launch(s, s ? s->p.mueq : 0.0, 0, 1, stream); }
+int ab2_gar_sweep(ab2_gar_solver *s, double mueq, void *stream) { return launch(s, mueq, 1, 1, stream); }
+
+size_t ab2_gar_output_doubles(const ab2_gar_solver *s, int what) {
+  if (!s || what < 0 || what >= AB2_OUT_COUNT)
+    return 0;
+  return s->out_doubles[what];
+}
+
+int ab2_gar_get(ab2_gar_solver *s, int what, double *dst, int memspace, void *stream) {
+  if (!s || !dst || what < 0 || what >= AB2_OUT_COUNT)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  if (s->out_doubles[what] == 0)
+    return AB2_OK;
+  CUDA_TRY(cudaMemcpyAsync(dst, s->out[what], s->out_doubles[what] * sizeof(double),
+                           memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+  return AB2_OK;
+}
+
+int ab2_gar_get_range(ab2_gar_solver *s, int what, int b0, int nb, int t0, int nt, double *dst,
+                      int memspace, void *stream) {
+  if (!s || !dst || what < 0 || what >= AB2_OUT_COUNT)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  const int knots = s->out_knots[what];
+  if (b0 < 0 || nb < 0 || b0 + nb > s->d.batch || t0 < 0 || nt < 0 || t0 + nt > knots)
+    return fail(AB2_ERR_INVALID, "range out of bounds");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  const size_t rec = s->out_rec[what];
+  if (rec == 0 || nb == 0 || nt == 0)
+    return AB2_OK;
+  const double *src = s->out[what] + ((size_t)b0 * knots + t0) * rec;
+  CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)nt * rec * sizeof(double), src, (size_t)knots * rec * sizeof(double),
+                             (size_t)nt * rec * sizeof(double), (size_t)nb,
+                             memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+  return AB2_OK;
+}
+
+int ab2_gar_device_ptr(ab2_gar_solver *s, int what, double **out) {
+  if (!s || !out || what < 0 || what >= AB2_OUT_COUNT)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  *out = s->out[what];
+  return AB2_OK;
+}
+
+int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream) {
+  if (!s || !dst)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  CUDA_TRY(cudaMemcpyAsync(dst, s->status, sizeof(int) * s->d.batch,
+                           memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+  return AB2_OK;
+}
+
+int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace, void *stream) {
+  if (!s || !new_last)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  const int N = s->d.horizon, B = s->d.batch;
+  if (N < 1)
+    return fail(AB2_ERR_INVALID, "cycle_append needs horizon >= 1");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  // factors: datas[0..N-1] rotate left, datas[N-1] re-created (zeros), terminal kept
+  // (proximal-riccati.hxx:79-83).  Vxx/vx have N+1 entries; the last is the terminal's.
+  const int whats[4] = {AB2_OUT_FF, AB2_OUT_FB, AB2_OUT_VXX, AB2_OUT_VX};
+  for (int w : whats) {
+    const int rec = (int)s->out_rec[w];
+    if (rec == 0)
+      continue;
+    ab2::shift_left_kernel<<<B, 128, 0, st>>>(s->out[w], (long)s->out_knots[w] * rec, N, rec, 1);
+    s->launches += 1;
+  }
+  // kkt0 zeroed (:84-86)
+  if (s->out_doubles[AB2_OUT_KKT0])
+    CUDA_TRY(cudaMemsetAsync(s->out[AB2_OUT_KKT0], 0, s->out_doubles[AB2_OUT_KKT0] * sizeof(double), st));
+  // the problem itself: rotate our own device copy (host-fed problems); a device-resident
+  // caller rotates its own buffers, like cycleProblem does for the reference's problem.
+  if (s->own_stage && s->p.stage == s->own_stage) {
+    ab2::shift_left_kernel<<<B, 128, 0, st>>>(s->own_stage, (long)N * s->srec, N, s->srec, 0);
+    s->launches += 1;
+    CUDA_TRY(cudaMemcpy2DAsync(s->own_stage + (size_t)(N - 1) * s->srec, (size_t)N * s->srec * sizeof(double),
+                               new_last, (size_t)s->srec * sizeof(double), (size_t)s->srec * sizeof(double),
+                               (size_t)B,
+                               memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaGetLastError());
+  s->have_backward = false;
+  return AB2_OK;
+}
+
+int ab2_gar_synchronize(ab2_gar_solver *s, void *stream) {
+  if (!s)
+    return fail(AB2_ERR_INVALID, "null solver");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return AB2_OK;
+}
+
+long ab2_gar_launch_count(const ab2_gar_solver *s) { return s ? s->launches : 0; }
+
+int ab2_gar_kernel_info(const ab2_gar_solver *s, int *group_lanes, int *smem_bytes_per_cta,
+                        int *threads_per_cta, int *grid, int *regs_per_thread) {
+  if (!s)
+    return fail(AB2_ERR_INVALID, "null solver");
+  int info[5] = {0, 0, 0, 0, 0};
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  CUDA_TRY(s->k->launch(s->p, s->variant, s->group_doubles, 0, info));
+  if (group_lanes)
+    *group_lanes = info[0];
+  if (smem_bytes_per_cta)
+    *smem_bytes_per_cta = info[1];
+  if (threads_per_cta)
+    *threads_per_cta = info[2];
+  if (grid)
+    *grid = info[3];
+  if (regs_per_thread)
+    *regs_per_thread = info[4];
+  return AB2_OK;
+}
+
+} // extern "C"

@@ -2,6 +2,9 @@
 // used in tests).  X(NX, NU, NC, G): G lanes per instance (sub-warp or warp);
 // requires nx+nu+1 <= G, nu+nc <= G and nx+nc0 <= G at run time.
 #pragma once
+#ifdef AB2_ONLY_C2
+#define AB2_FOR_EACH_CONFIG(X) X(12, 6, 0, 32)
+#else
 #define AB2_FOR_EACH_CONFIG(X)                                                  \
   X(2, 2, 0, 8)   /* tests/gar/riccati.cpp short-horizon shape            */    \
   X(2, 2, 2, 8)   /* ... with the control-constrained knot                */    \
@@ -15,3 +18,5 @@
   X(12, 6, 0, 32) /* BASELINE config 2 (headline)                         */    \
   X(12, 6, 6, 32)                                                               \
   X(14, 7, 0, 32) /* BASELINE config 4: Talos arm                         */
+
+#endif

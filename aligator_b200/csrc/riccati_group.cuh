@@ -31,12 +31,15 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <utility>
 
 #if defined(__CUDACC__)
 #define AB2_HD __host__ __device__ __forceinline__
+#define AB2_D __device__ __forceinline__ // group-program code: device only under nvcc
 #define AB2_UNROLL _Pragma("unroll")
 #else
 #define AB2_HD inline
+#define AB2_D inline
 #define AB2_UNROLL
 #endif
 
@@ -78,13 +81,17 @@ struct SweepParams {
 // ---------------------------------------------------------------------------
 // Compile-time shape of one kernel instantiation.
 // ---------------------------------------------------------------------------
-template <int NX_, int NU_, int NC_, int G_> struct Cfg {
+template <int NX_, int NU_, int NC_, int G_, bool DB_ = false> struct Cfg {
   static constexpr int NX = NX_, NU = NU_, NC = NC_, G = G_;
+  static constexpr bool DB = DB_;          // double-buffered knot records
   static constexpr int NCOL = NX + NU + 1; // columns of M = [A | B | f]
   static constexpr int NXU = NX + NU;      // rows of H
   static constexpr int NK = NU + NC;       // reduced KKT size
   static constexpr int NR = NU + NC + NX;  // rows of ff / fb
   static constexpr int FCOL = NX + NU;     // the lane that owns f / q,r / ff
+  static constexpr bool EVEN = (NX % 2) == 0; // 16-byte aligned rows -> 128-bit LDS
+  static constexpr bool REGBK = NK <= 8;   // Bunch-Kaufman entirely in registers
+  static constexpr int ev(int x) { return (x + 1) & ~1; }
   // stage record offsets (doubles) -- the reference's 11 buffers, concatenated
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + NX * NX;
@@ -98,20 +105,21 @@ template <int NX_, int NU_, int NC_, int G_> struct Cfg {
   static constexpr int OFF_D = OFF_C + NC * NX;
   static constexpr int OFF_DV = OFF_D + NC * NU;
   static constexpr int SREC = OFF_DV + NC;
-  static constexpr int SREC_PAD = (SREC + 1) & ~1; // 16-byte granularity for TMA
-  static constexpr int M_DBL = OFF_Q;              // [A|B|f]
-  static constexpr int SPLIT = (M_DBL + 1) & ~1;   // part 0 = [0,SPLIT), part 1 = rest
-  // shared-memory layout of one group (doubles)
+  static constexpr int SREC_PAD = ev(SREC);  // 16-byte granularity for bulk copies
+  static constexpr int M_DBL = OFF_Q;        // [A|B|f]
+  static constexpr int SPLIT = ev(M_DBL);    // part 0 = [0,SPLIT), part 1 = rest
+  static constexpr int RS = ev(NX + 1);      // row stride of rhs0 / sol
+  // shared-memory layout of one group (doubles); every region starts 16-byte aligned
   static constexpr int S_REC = 0;
-  static constexpr int S_VN = S_REC + SREC_PAD;  // V' (symmetric, full) NX*NX
-  static constexpr int S_VXN = S_VN + NX * NX;   // vx'
-  static constexpr int S_KKT = S_VXN + NX;       // NK*NK column-major
-  static constexpr int S_RHS = S_KKT + NK * NK;  // NK x (NX+1) row-major, unsolved
-  static constexpr int S_SOL = S_RHS + NK * (NX + 1);
-  static constexpr int S_DD = S_SOL + NK * (NX + 1);
-  static constexpr int S_SD = S_DD + NK;
-  static constexpr int S_X = S_SD + NK;    // forward state x_t (NX) + x_{t+1} (NX)
-  static constexpr int S_INT = S_X + 2 * NX; // perm[NK], kind[NK] (ints)
+  static constexpr int S_VN = S_REC + (DB ? 2 : 1) * SREC_PAD; // V' (symmetric, full)
+  static constexpr int S_VXN = S_VN + ev(NX * NX);             // vx'
+  static constexpr int S_KKT = S_VXN + ev(NX);                 // NK*NK column-major
+  static constexpr int S_RHS = S_KKT + ev(NK * NK);            // NK x RS, unsolved rhs
+  static constexpr int S_SOL = S_RHS + NK * RS;
+  static constexpr int S_DD = S_SOL + NK * RS;
+  static constexpr int S_SD = S_DD + ev(NK);
+  static constexpr int S_X = S_SD + ev(NK);    // forward state x_t (NX) + x_{t+1} (NX)
+  static constexpr int S_INT = S_X + 2 * ev(NX); // perm[NK], kind[NK] (ints)
   static constexpr int S_STAGE_END = S_INT + NK + 1;
 
   static_assert(NU >= 1, "stage knots need nu >= 1");
@@ -129,6 +137,38 @@ template <int NX_, int NU_, int NC_, int G_> struct Cfg {
   static AB2_HD int term_rec(int nct) { return NX * NX + NX + nct * NX + nct; }
 };
 
+// 128-bit shared-memory load of two consecutive doubles (p 16-byte aligned).
+struct D2 {
+  double x, y;
+};
+AB2_D D2 lds2(const double *p) {
+#if defined(__CUDA_ARCH__)
+  const double2 v = *reinterpret_cast<const double2 *>(p);
+  return D2{v.x, v.y};
+#else
+  return D2{p[0], p[1]};
+#endif
+}
+// acc + sum_k row[k] * v[k]; `row` is read by the whole group at the same address
+// (broadcast).  ALIGNED: row is 16-byte aligned -> LDS.128.
+template <int N, bool ALIGNED> AB2_D double dot_bcast(const double *row, const double (&v)[N], double acc) {
+  if constexpr (ALIGNED) {
+    AB2_UNROLL
+    for (int k = 0; k + 1 < N; k += 2) {
+      const D2 a = lds2(row + k);
+      acc += a.x * v[k];
+      acc += a.y * v[k + 1];
+    }
+    if constexpr (N % 2)
+      acc += row[N - 1] * v[N - 1];
+  } else {
+    AB2_UNROLL
+    for (int k = 0; k < N; ++k)
+      acc += row[k] * v[k];
+  }
+  return acc;
+}
+
 // ---------------------------------------------------------------------------
 // Cooperative Bunch-Kaufman (lower), n <= G, matrix in shared memory.
 // Same pivot logic and arithmetic as bunch_kaufman_in_place_unblocked
@@ -140,7 +180,7 @@ template <int NX_, int NU_, int NC_, int G_> struct Cfg {
 // Returns false where the reference reports NumericalIssue (:58-59).
 // ---------------------------------------------------------------------------
 template <class Ctx>
-AB2_HD bool bk_factor_group(Ctx &ctx, double *a, const int lda, const int n,
+AB2_D bool bk_factor_group(Ctx &ctx, double *a, const int lda, const int n,
                             double *dd, double *sd, int *perm, int *kind) {
   const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
   const int lane = ctx.lane;
@@ -285,55 +325,242 @@ AB2_HD bool bk_factor_group(Ctx &ctx, double *a, const int lda, const int n,
   return ok;
 }
 
-// Per-lane solve of one right-hand-side column with the factor above (n = NK
-// compile-time; everything in registers, factor read by broadcast).
-// Same sequence as bunch_kaufman_solve_in_place (core/bunchkaufman.hpp:451-518):
-// interchanges, unit-lower solve, D^-1, unit-upper solve, inverse interchanges.
-template <int NK>
-AB2_HD void bk_solve_column(const double *a, const double *dd, const double *sd,
-                            const int *perm, const int *kind, const double *rhs,
-                            double *sol, const int stride, double (&x)[NK > 0 ? NK : 1]) {
+// Per-lane solve of one right-hand-side column (n = NK compile-time, x in
+// registers).  Same sequence as bunch_kaufman_solve_in_place
+// (core/bunchkaufman.hpp:451-518): interchanges, unit-lower solve, D^-1,
+// unit-upper solve, inverse interchanges.  F supplies the factor: F.L(i,c),
+// F.dd(k), F.sd(k), F.kind(k), F.perm(i) -- from shared memory (broadcast reads)
+// or from registers.
+template <int NK, class F>
+AB2_D void bk_solve_column(const F &f, const double *rhs, double *sol, const int stride,
+                           double (&x)[NK]) {
   AB2_UNROLL
   for (int i = 0; i < NK; ++i)
-    x[i] = rhs[perm[i] * stride];
+    x[i] = rhs[f.perm(i) * stride];
   AB2_UNROLL
   for (int c = 0; c < NK; ++c) {
     AB2_UNROLL
     for (int i = c + 1; i < NK; ++i)
-      x[i] -= a[i + c * NK] * x[c];
+      x[i] -= f.L(i, c) * x[c];
   }
   AB2_UNROLL
   for (int k = 0; k < NK; ++k) {
-    const int kd = kind[k];
+    const int kd = f.kind(k);
+    const int k1 = (k + 1 < NK) ? k + 1 : k;
     if (kd == 0) {
-      x[k] *= dd[k];
-    } else if (kd == 1) {
-      if (k + 1 < NK) {
-        const double xk = x[k], xk1 = x[k + 1 < NK ? k + 1 : k];
-        const double s = sd[k];
-        x[k] = xk * dd[k] + xk1 * s;
-        x[k + 1 < NK ? k + 1 : k] = xk1 * dd[k + 1 < NK ? k + 1 : k] + xk * s;
-      }
+      x[k] *= f.dd(k);
+    } else if (kd == 1 && k + 1 < NK) {
+      const double xk = x[k], xk1 = x[k1];
+      const double sdk = f.sd(k);
+      x[k] = xk * f.dd(k) + xk1 * sdk;
+      x[k1] = xk1 * f.dd(k1) + xk * sdk;
     }
   }
   AB2_UNROLL
   for (int c = NK - 1; c >= 0; --c) {
     AB2_UNROLL
     for (int i = c + 1; i < NK; ++i)
-      x[c] -= a[i + c * NK] * x[i];
+      x[c] -= f.L(i, c) * x[i];
   }
   AB2_UNROLL
   for (int i = 0; i < NK; ++i)
-    sol[perm[i] * stride] = x[i];
+    sol[f.perm(i) * stride] = x[i];
   AB2_UNROLL
   for (int i = 0; i < NK; ++i)
     x[i] = sol[i * stride];
 }
 
+template <int NK> struct SmemFactor { // factor left in shared memory by bk_factor_group
+  const double *a, *d, *s;
+  const int *pm, *kd;
+  AB2_D double L(int i, int c) const { return a[i + c * NK]; }
+  AB2_D double dd(int k) const { return d[k]; }
+  AB2_D double sd(int k) const { return s[k]; }
+  AB2_D int kind(int k) const { return kd[k]; }
+  AB2_D int perm(int i) const { return pm[i]; }
+};
+
+// Bunch-Kaufman of an N x N matrix held in registers by EVERY lane of the group:
+// all lanes run the same scalar algorithm on the same data, so there is no shared
+// memory traffic, no synchronisation and no divergence inside a group.  Identical
+// pivot logic / arithmetic to bunch_kaufman_in_place_unblocked
+// (core/bunchkaufman.hpp:46-151); the dynamic pivot row is resolved by fully
+// unrolled compare chains so every register index is static.
+template <int N> struct RegFactor {
+  double a[N][N]; // lower triangle: L below the diagonal after factor()
+  double d[N], s[N];
+  int pm[N], kd[N];
+  AB2_D double L(int i, int c) const { return a[i][c]; }
+  AB2_D double dd(int k) const { return d[k]; }
+  AB2_D double sd(int k) const { return s[k]; }
+  AB2_D int kind(int k) const { return kd[k]; }
+  AB2_D int perm(int i) const { return pm[i]; }
+
+  // symmetric interchange KK <-> C (static), rows swapped across ALL columns
+  // K0 = first column of the current pivot block.
+  AB2_D void swap_sym(const int KK, const int C, const int K0, const bool two) {
+    AB2_UNROLL
+    for (int i = 0; i < N; ++i) {
+      if (i > C) {
+        const double t = a[i][KK];
+        a[i][KK] = a[i][C];
+        a[i][C] = t;
+      } else if (i > KK && i < C) {
+        const double t = a[i][KK];
+        a[i][KK] = a[C][i];
+        a[C][i] = t;
+      } else if (i < K0) {
+        const double t = a[KK][i];
+        a[KK][i] = a[C][i];
+        a[C][i] = t;
+      }
+    }
+    {
+      const double t = a[KK][KK];
+      a[KK][KK] = a[C][C];
+      a[C][C] = t;
+      const int tp = pm[KK];
+      pm[KK] = pm[C];
+      pm[C] = tp;
+    }
+    if (two) { // column K0 of the 2x2 block: rows K0+1 (= KK) <-> C
+      const double t = a[KK][K0];
+      a[KK][K0] = a[C][K0];
+      a[C][K0] = t;
+    }
+  }
+
+  // one elimination step with a COMPILE-TIME column index (so that every register
+  // index stays static even if the compiler declines to unroll a large loop body)
+  template <int K> AB2_D void step(bool &ok, bool &skip, bool &dead) {
+    constexpr int k = K;
+    const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
+    if (skip || dead) {
+      skip = false;
+      return;
+    }
+    const double akk = a[k][k];
+    const double abs_akk = fabs(akk);
+    int imax = k + 1;
+    double colmax = 0.0;
+    AB2_UNROLL
+    for (int i = k + 1; i < N; ++i) {
+      const double v = fabs(a[i][k]);
+      if (v > colmax) {
+        colmax = v;
+        imax = i;
+      }
+    }
+    if (fmax(abs_akk, colmax) == 0.0) {
+      ok = false;
+      dead = true;
+      AB2_UNROLL
+      for (int i = k; i < N; ++i) {
+        AB2_UNROLL
+        for (int j = k; j < i; ++j)
+          a[i][j] = 0.0;
+      }
+      return;
+    }
+    int kp = k, kstep = 1;
+    if (!(abs_akk >= colmax * alpha)) {
+      double rowmax = 0.0, aii = akk;
+      AB2_UNROLL
+      for (int c = k + 1; c < N; ++c)
+        if (imax == c) {
+          AB2_UNROLL
+          for (int j = k; j < c; ++j)
+            rowmax = fmax(rowmax, fabs(a[c][j]));
+          AB2_UNROLL
+          for (int i = c + 1; i < N; ++i)
+            rowmax = fmax(rowmax, fabs(a[i][c]));
+          aii = a[c][c];
+        }
+      if (abs_akk >= (alpha * colmax) * (colmax / rowmax)) {
+        kp = k;
+      } else if (fabs(aii) >= alpha * rowmax) {
+        kp = imax;
+      } else {
+        kp = imax;
+        kstep = 2;
+      }
+    }
+    constexpr int k1 = (k + 1 < N) ? k + 1 : k;
+    if (kstep == 1) {
+      if (kp != k) {
+        AB2_UNROLL
+        for (int c = k + 1; c < N; ++c)
+          if (kp == c)
+            swap_sym(k, c, k, false);
+      }
+      const double d11 = 1.0 / a[k][k];
+      d[k] = d11;
+      AB2_UNROLL
+      for (int j = k + 1; j < N; ++j) {
+        const double d11xj = a[j][k] * d11;
+        AB2_UNROLL
+        for (int i = j; i < N; ++i)
+          a[i][j] -= d11xj * a[i][k];
+      }
+      AB2_UNROLL
+      for (int i = k + 1; i < N; ++i)
+        a[i][k] *= d11;
+    } else if (k + 1 < N) {
+      if (kp != k1) {
+        AB2_UNROLL
+        for (int c = k + 2; c < N; ++c)
+          if (kp == c)
+            swap_sym(k1, c, k, true);
+      }
+      const double d21v = a[k1][k];
+      const double d21_abs = fabs(d21v);
+      const double d21_inv = 1.0 / d21_abs;
+      const double d11 = d21_inv * a[k1][k1];
+      const double d22 = d21_inv * a[k][k];
+      const double t = 1.0 / ((d11 * d22) - 1.0);
+      const double dm = t * d21_inv;
+      const double d21 = d21v * d21_inv;
+      d[k] = d11 * dm;
+      s[k] = -d21 * dm;
+      d[k1] = d22 * dm;
+      kd[k] = 1;
+      kd[k1] = 2;
+      AB2_UNROLL
+      for (int j = k + 2; j < N; ++j) {
+        const double wk = ((a[j][k] * d11) - (a[j][k1] * d21)) * dm;
+        const double wkp1 = ((a[j][k1] * d22) - (a[j][k] * d21)) * dm;
+        AB2_UNROLL
+        for (int i = j; i < N; ++i)
+          a[i][j] -= a[i][k] * wk + a[i][k1] * wkp1;
+        a[j][k] = wk;
+        a[j][k1] = wkp1;
+      }
+      a[k1][k] = 0.0;
+      skip = true;
+    }
+  }
+  template <int... Ks> AB2_D void steps(bool &ok, bool &skip, bool &dead, std::integer_sequence<int, Ks...>) {
+    (step<Ks>(ok, skip, dead), ...);
+  }
+
+  AB2_D bool factor() {
+    bool ok = true, skip = false, dead = false;
+    AB2_UNROLL
+    for (int i = 0; i < N; ++i) {
+      pm[i] = i;
+      kd[i] = 0;
+      d[i] = 0.0;
+      s[i] = 0.0;
+    }
+    steps(ok, skip, dead, std::make_integer_sequence<int, N>{});
+    return ok;
+  }
+};
+
 // Group-cooperative solve of ONE vector (runtime n <= G): lane i owns x[i].
 // b: input (n), x: work/output in permuted order, out: un-permuted result.
 template <class Ctx>
-AB2_HD void bk_solve_vec_group(Ctx &ctx, const double *a, const int lda, const int n,
+AB2_D void bk_solve_vec_group(Ctx &ctx, const double *a, const int lda, const int n,
                                const double *dd, const double *sd, const int *perm,
                                const int *kind, const double *b, double *x, double *out) {
   const int lane = ctx.lane;
@@ -373,7 +600,7 @@ AB2_HD void bk_solve_vec_group(Ctx &ctx, const double *a, const int lda, const i
 // The sweep of one instance by one group.
 // ---------------------------------------------------------------------------
 template <class C, class Ctx>
-AB2_HD void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
+AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
                                 double *__restrict__ sm) {
   constexpr int NX = C::NX, NU = C::NU, NC = C::NC, NK = C::NK, NR = C::NR;
   constexpr int NXU = C::NXU, NCOL = C::NCOL, FCOL = C::FCOL;
@@ -382,7 +609,7 @@ AB2_HD void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
   const int nct = p.nct, nc0 = p.nc0;
   const double mueq = p.mueq;
 
-  double *rec = sm + C::S_REC;
+  double *rec = sm + C::S_REC; // current knot record (buffer 0 / alternating when DB)
   double *Vn = sm + C::S_VN;
   double *vxn = sm + C::S_VXN;
   double *kkt = sm + C::S_KKT;
@@ -412,8 +639,12 @@ AB2_HD void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     // prefetch the last stage knot while the terminal knot is processed
     if (N > 0) {
       const double *src = stage_b + (size_t)(N - 1) * C::SREC_PAD;
-      ctx.issue_copy(0, rec, src, C::SPLIT);
-      ctx.issue_copy(1, rec + C::SPLIT, src + C::SPLIT, C::SREC_PAD - C::SPLIT);
+      if (C::DB) {
+        ctx.issue_copy(0, rec, src, C::SREC_PAD);
+      } else {
+        ctx.issue_copy(0, rec, src, C::SPLIT);
+        ctx.issue_copy(1, rec + C::SPLIT, src + C::SPLIT, C::SREC_PAD - C::SPLIT);
+      }
     }
     // ---------------- terminal knot (nu = 0): riccati-kernel.hxx:146-149,175-183
     {
@@ -423,112 +654,118 @@ AB2_HD void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       const double *Ct = qt + NX;            // nct x NX column-major
       const double *dt = Ct + (size_t)nct * NX;
       double *VN = Vxx_b + (size_t)N * NX * NX;
-      double tv[NX];
-      if (colA) {
-        const int j = lane;
-        for (int m = 0; m < nct; ++m) // Z = C / mu  (row-major nct x NX)
-          p.fbT[(size_t)inst * nct * NX + (size_t)m * NX + j] = Ct[m + (size_t)j * nct] / mueq;
+      if (colA || colF) {
+        // column j of Z = C/mu (or z = d/mu), then column j of Q + C^T Z (q + C^T z)
+        double acc[NX];
+        AB2_UNROLL
+        for (int i = 0; i < NX; ++i)
+          acc[i] = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+        for (int m = 0; m < nct; ++m) {
+          const double zm = (colF ? dt[m] : Ct[m + (size_t)lane * nct]) / mueq;
+          if (colF)
+            p.ffT[(size_t)inst * nct + m] = zm;
+          else
+            p.fbT[(size_t)inst * nct * NX + (size_t)m * NX + lane] = zm;
+          AB2_UNROLL
+          for (int i = 0; i < NX; ++i)
+            acc[i] += Ct[m + (size_t)i * nct] * zm;
+        }
         AB2_UNROLL
         for (int i = 0; i < NX; ++i) {
-          double s = Qt[i + j * NX];
-          double acc = 0.0;
-          for (int m = 0; m < nct; ++m)
-            acc += Ct[m + (size_t)i * nct] * (Ct[m + (size_t)j * nct] / mueq);
-          s += acc;
-          tv[i] = s;
-          if (i >= j) { // V' for the next step = lower triangle mirrored (:216)
-            Vn[i * NX + j] = s;
-            Vn[j * NX + i] = s;
+          const double s = (colF ? qt[i] : Qt[i + lane * NX]) + acc[i];
+          if (colF) {
+            vx_b[(size_t)N * NX + i] = s;
+            vxn[i] = s;
+          } else {
+            VN[i + lane * NX] = s; // as computed; re-written symmetric below when N > 0
+            if (i >= lane) {       // V' for the next step = lower triangle mirrored (:216)
+              Vn[i * NX + lane] = s;
+              Vn[lane * NX + i] = s;
+            }
           }
         }
       }
-      if (colF) {
-        for (int m = 0; m < nct; ++m)
-          p.ffT[(size_t)inst * nct + m] = dt[m] / mueq;
-        AB2_UNROLL
-        for (int i = 0; i < NX; ++i) {
-          double acc = 0.0;
-          for (int m = 0; m < nct; ++m)
-            acc += Ct[m + (size_t)i * nct] * (dt[m] / mueq);
-          const double s = qt[i] + acc;
-          vx_b[(size_t)N * NX + i] = s;
-          vxn[i] = s;
-        }
-      }
       ctx.sync();
-      if (colA) { // the step N-1 of the reference symmetrises datas[N].Vxx in place (A1)
+      if (colA && N > 0) { // step N-1 of the reference symmetrises datas[N].Vxx in place (A1)
         AB2_UNROLL
         for (int i = 0; i < NX; ++i)
-          VN[i + lane * NX] = (N > 0) ? Vn[lane * NX + i] : tv[i];
+          VN[i + lane * NX] = Vn[lane * NX + i];
       }
     }
 
     // ---------------- stage knots N-1 .. 0: riccati-kernel.hxx:210-277
+    constexpr int RS = C::RS;
+    constexpr bool EV = C::EVEN;
+    int cur = 0; // record buffer in use (DB)
     for (int t = N - 1; t >= 0; --t) {
-      ctx.wait_copy(0);
-      ctx.wait_copy(1);
+      if (C::DB) {
+        ctx.wait_copy(cur);
+        rec = sm + C::S_REC + cur * C::SREC_PAD;
+        if (t > 0) // stream the next knot into the other buffer during this step
+          ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::SREC_PAD,
+                         stage_b + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
+        cur ^= 1;
+      } else {
+        ctx.wait_copy(0);
+        ctx.wait_copy(1);
+      }
       // own column of M = [A|B|f]
       double mcol[NX];
-      AB2_UNROLL
-      for (int k = 0; k < NX; ++k)
-        mcol[k] = active ? rec[lane * NX + k] : 0.0;
+      if (EV) {
+        AB2_UNROLL
+        for (int k = 0; k < NX; k += 2) {
+          const D2 v = lds2(rec + (active ? lane : 0) * NX + k);
+          mcol[k] = v.x;
+          mcol[k + 1 < NX ? k + 1 : k] = v.y;
+        }
+      } else {
+        AB2_UNROLL
+        for (int k = 0; k < NX; ++k)
+          mcol[k] = rec[(active ? lane : 0) * NX + k];
+      }
       // (A) w = V' m_j  (+ vx' on the affine column: vplus = vx' + V' f, :217-218)
       double w[NX];
       AB2_UNROLL
-      for (int i = 0; i < NX; ++i) {
-        double s = 0.0;
-        AB2_UNROLL
-        for (int k = 0; k < NX; ++k)
-          s += Vn[i * NX + k] * mcol[k];
-        w[i] = s;
-      }
+      for (int i = 0; i < NX; ++i)
+        w[i] = dot_bcast<NX, EV>(Vn + i * NX, mcol, 0.0);
       if (colF) {
         AB2_UNROLL
         for (int i = 0; i < NX; ++i)
           w[i] += vxn[i];
       }
-      // (B) h = H0[:,j] + [A B]^T w      (:220-228 in one product)
-      double h[NXU];
-      {
-        // H0 = [[Q S q],[S^T R r]]; per-lane base/stride so the code is uniform
-        int base1, base2, stride2;
-        if (colA) {
-          base1 = C::OFF_Q + lane * NX;
-          base2 = C::OFF_S + lane;
-          stride2 = NX;
-        } else if (colB) {
-          base1 = C::OFF_S + (lane - NX) * NX;
-          base2 = C::OFF_R + (lane - NX) * NU;
-          stride2 = 1;
-        } else {
-          base1 = C::OFF_QV;
-          base2 = C::OFF_RV;
-          stride2 = 1;
-        }
-        AB2_UNROLL
-        for (int i = 0; i < NX; ++i)
-          h[i] = active ? rec[base1 + i] : 0.0;
-        AB2_UNROLL
-        for (int i = 0; i < NU; ++i)
-          h[NX + i] = active ? rec[base2 + i * stride2] : 0.0;
+      // (B) H[:,j] = H0[:,j] + [A B]^T w      (:220-228 in one product)
+      // H0 = [[Q S q],[S^T R r]]; per-lane base/stride so the code is uniform
+      int base1, base2, stride2;
+      if (colA) {
+        base1 = C::OFF_Q + lane * NX;
+        base2 = C::OFF_S + lane;
+        stride2 = NX;
+      } else if (colB) {
+        base1 = C::OFF_S + (lane - NX) * NX;
+        base2 = C::OFF_R + (lane - NX) * NU;
+        stride2 = 1;
+      } else {
+        base1 = C::OFF_QV;
+        base2 = C::OFF_RV;
+        stride2 = 1;
       }
+      // control rows first: they go straight to the KKT matrix / right-hand sides
+      // (:232-257) and never occupy registers afterwards
       AB2_UNROLL
-      for (int i = 0; i < NXU; ++i) {
-        double s = 0.0;
-        AB2_UNROLL
-        for (int k = 0; k < NX; ++k)
-          s += rec[i * NX + k] * w[k];
-        h[i] += s;
+      for (int r = 0; r < NU; ++r) {
+        const double hr = dot_bcast<NX, EV>(rec + (NX + r) * NX, w, rec[base2 + r * stride2]);
+        if (colB)
+          kkt[r + (lane - NX) * NK] = hr; // Rhat[r][c]; only r >= c is read
+        else if (colA || colF)
+          rhs0[r * RS + jj] = -hr; // -Shat^T[:,j] / -rhat
       }
-      // (C) reduced KKT matrix (lower triangle) and right-hand sides (:232-257)
       if (colB) {
-        const int c = lane - NX;
-        AB2_UNROLL
-        for (int r = 0; r < NU; ++r)
-          kkt[r + c * NK] = h[NX + r]; // Rhat[r][c]; only r >= c is read
         AB2_UNROLL
         for (int m = 0; m < NC; ++m)
-          kkt[NU + m + c * NK] = rec[C::OFF_D + c * NC + m];
+          kkt[NU + m + (lane - NX) * NK] = rec[C::OFF_D + (lane - NX) * NC + m];
       }
       if (lane < NC) { // (1,1) block: -mu on the diagonal, zeros below
         AB2_UNROLL
@@ -537,55 +774,64 @@ AB2_HD void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       }
       if (colA || colF) {
         AB2_UNROLL
-        for (int r = 0; r < NU; ++r)
-          rhs0[r * (NX + 1) + jj] = -h[NX + r]; // -Shat^T[:,j] / -rhat
-        AB2_UNROLL
         for (int m = 0; m < NC; ++m)
-          rhs0[(NU + m) * (NX + 1) + jj] =
-              colF ? -rec[C::OFF_DV + m] : -rec[C::OFF_C + lane * NC + m];
+          rhs0[(NU + m) * RS + jj] = colF ? -rec[C::OFF_DV + m] : -rec[C::OFF_C + lane * NC + m];
       }
+      // state rows: Qhat[:,j] / Shat[:,c] / qhat stay in registers for step (E)
+      double h[NX];
+      AB2_UNROLL
+      for (int i = 0; i < NX; ++i)
+        h[i] = dot_bcast<NX, EV>(rec + i * NX, w, rec[base1 + i]);
       ctx.sync();
-      // part 1 of the record (Q..d) is consumed: fetch the next knot's
-      if (t > 0)
-        ctx.issue_copy(1, rec + C::SPLIT,
-                       stage_b + (size_t)(t - 1) * C::SREC_PAD + C::SPLIT,
+      if (!C::DB && t > 0) // part 1 of the record (Q..d) is consumed: fetch the next knot's
+        ctx.issue_copy(1, rec + C::SPLIT, stage_b + (size_t)(t - 1) * C::SREC_PAD + C::SPLIT,
                        C::SREC_PAD - C::SPLIT);
-      if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind))
-        st |= ST_STAGE_FACTOR_FAILED;
-      // (D) solve, closed loop, cost-to-go (:259-277)
-      double kz[NK > 0 ? NK : 1];
-      double ahat[NX], vnew[NX];
-      if (colA || colF) {
-        bk_solve_column<NK>(kkt, dd, sd, perm, kind, rhs0 + jj, sol + jj, NX + 1, kz);
+      // (C) Bunch-Kaufman of the reduced KKT matrix, (D) solve + closed loop (:259-267)
+      double kz[NK];
+      double *fbt = fb_b + (size_t)t * NR * NX;
+      double *fft = ff_b + (size_t)t * NR;
+      if constexpr (C::REGBK) {
+        RegFactor<NK> F;
         AB2_UNROLL
-        for (int i = 0; i < NX; ++i) { // [Ahat a] = [A f] + B [K k]
-          double s = 0.0;
+        for (int c = 0; c < NK; ++c) {
           AB2_UNROLL
-          for (int c = 0; c < NU; ++c)
-            s += rec[C::OFF_B + c * NX + i] * kz[c];
-          ahat[i] = mcol[i] + s;
+          for (int i = c; i < NK; ++i)
+            F.a[i][c] = kkt[i + c * NK];
+        }
+        if (!F.factor())
+          st |= ST_STAGE_FACTOR_FAILED;
+        if (colA || colF)
+          bk_solve_column<NK>(F, rhs0 + jj, sol + jj, RS, kz);
+      } else {
+        if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind))
+          st |= ST_STAGE_FACTOR_FAILED;
+        if (colA || colF) {
+          const SmemFactor<NK> F{kkt, dd, sd, perm, kind};
+          bk_solve_column<NK>(F, rhs0 + jj, sol + jj, RS, kz);
         }
       }
-      ctx.sync();
-      // part 0 ([A|B|f]) is consumed
-      if (t > 0)
-        ctx.issue_copy(0, rec, stage_b + (size_t)(t - 1) * C::SREC_PAD, C::SPLIT);
       if (colA || colF) {
+        // [Ahat a] = [A f] + B [K k]
+        double ahat[NX];
         AB2_UNROLL
-        for (int i = 0; i < NX; ++i) { // [Vxx vx] = [Qhat qhat] + [Shat C^T][K k; Z z]
-          double s1 = 0.0;
-          AB2_UNROLL
-          for (int r = 0; r < NU; ++r)
-            s1 -= rhs0[r * (NX + 1) + i] * kz[r]; // rhs0 holds -Shat^T
-          double s2 = 0.0;
-          AB2_UNROLL
-          for (int m = 0; m < NC; ++m)
-            s2 -= rhs0[(NU + m) * (NX + 1) + i] * kz[NU + m]; // and -C
-          vnew[i] = (h[i] + s1) + s2;
+        for (int i = 0; i < NX; ++i)
+          ahat[i] = mcol[i];
+        AB2_UNROLL
+        for (int c = 0; c < NU; ++c) {
+          const double kc = kz[c];
+          if (EV) {
+            AB2_UNROLL
+            for (int i = 0; i < NX; i += 2) {
+              const D2 b = lds2(rec + C::OFF_B + c * NX + i);
+              ahat[i] += b.x * kc;
+              ahat[i + 1 < NX ? i + 1 : i] += b.y * kc;
+            }
+          } else {
+            AB2_UNROLL
+            for (int i = 0; i < NX; ++i)
+              ahat[i] += rec[C::OFF_B + c * NX + i] * kc;
+          }
         }
-        // ---- outputs of knot t ----
-        double *fbt = fb_b + (size_t)t * NR * NX;
-        double *fft = ff_b + (size_t)t * NR;
         if (colA) {
           AB2_UNROLL
           for (int r = 0; r < NK; ++r)
@@ -593,18 +839,6 @@ AB2_HD void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           AB2_UNROLL
           for (int i = 0; i < NX; ++i)
             fbt[(NK + i) * NX + lane] = ahat[i];
-          double *Vt = Vxx_b + (size_t)t * NX * NX;
-          if (t == 0) { // datas[0].Vxx is left unsymmetrised (A1)
-            AB2_UNROLL
-            for (int i = 0; i < NX; ++i)
-              Vt[i + lane * NX] = vnew[i];
-          }
-          AB2_UNROLL
-          for (int i = 0; i < NX; ++i)
-            if (i >= lane) { // V' = lower triangle mirrored (:216 of the next step)
-              Vn[i * NX + lane] = vnew[i];
-              Vn[lane * NX + i] = vnew[i];
-            }
         } else {
           AB2_UNROLL
           for (int r = 0; r < NK; ++r)
@@ -612,10 +846,66 @@ AB2_HD void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           AB2_UNROLL
           for (int i = 0; i < NX; ++i)
             fft[NK + i] = ahat[i];
+        }
+      }
+      if (!C::DB) {
+        ctx.sync();
+        if (t > 0) // part 0 ([A|B|f]) is consumed
+          ctx.issue_copy(0, rec, stage_b + (size_t)(t - 1) * C::SREC_PAD, C::SPLIT);
+      }
+      // (E) cost-to-go: [Vxx vx] = [Qhat qhat] + [Shat C^T][K k; Z z]   (:270-277)
+      if (colA || colF) {
+        // rhs0 still holds -Shat^T (rows 0..NU-1) and -C (rows NU..NK-1)
+        AB2_UNROLL
+        for (int r = 0; r < NU; ++r) {
+          const double kr = kz[r];
+          if (EV) {
+            AB2_UNROLL
+            for (int i = 0; i < NX; i += 2) {
+              const D2 sv = lds2(rhs0 + r * RS + i);
+              h[i] -= sv.x * kr;
+              h[i + 1 < NX ? i + 1 : i] -= sv.y * kr;
+            }
+          } else {
+            AB2_UNROLL
+            for (int i = 0; i < NX; ++i)
+              h[i] -= rhs0[r * RS + i] * kr;
+          }
+        }
+        if (NC > 0) {
+          double s2[NX];
+          AB2_UNROLL
+          for (int i = 0; i < NX; ++i)
+            s2[i] = 0.0;
+          AB2_UNROLL
+          for (int m = 0; m < NC; ++m) {
+            const double zr = kz[NU + m < NK ? NU + m : 0];
+            AB2_UNROLL
+            for (int i = 0; i < NX; ++i)
+              s2[i] -= rhs0[(NU + m) * RS + i] * zr;
+          }
+          AB2_UNROLL
+          for (int i = 0; i < NX; ++i)
+            h[i] += s2[i];
+        }
+        if (colA) {
+          if (t == 0) { // datas[0].Vxx is left unsymmetrised (A1)
+            double *Vt = Vxx_b;
+            AB2_UNROLL
+            for (int i = 0; i < NX; ++i)
+              Vt[i + lane * NX] = h[i];
+          }
+          AB2_UNROLL
+          for (int i = 0; i < NX; ++i)
+            if (i >= lane) { // V' = lower triangle mirrored (:216 of the next step)
+              Vn[i * NX + lane] = h[i];
+              Vn[lane * NX + i] = h[i];
+            }
+        } else {
           AB2_UNROLL
           for (int i = 0; i < NX; ++i) {
-            vx_b[(size_t)t * NX + i] = vnew[i];
-            vxn[i] = vnew[i];
+            vx_b[(size_t)t * NX + i] = h[i];
+            vxn[i] = h[i];
           }
         }
       }

@@ -1,0 +1,171 @@
+// riccati_launch.cuh -- device execution context, the persistent sweep kernel and
+// its launch variants.  Included by kernel_inst.cu (one translation unit per
+// compile-time shape, built in parallel) and by gar_cuda.cu (the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "riccati_group.cuh"
+
+namespace ab2 {
+
+// ---------------------------------------------------------------------------
+// Device execution context of one group.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+template <int G, bool TMA> struct DevCtx {
+  int lane;
+  unsigned mask;
+  uint32_t bar0; // shared address of this group's two mbarriers
+  uint32_t phase; // bit p = parity to wait for on barrier p
+
+  __device__ __forceinline__ void sync() { __syncwarp(mask); }
+
+  __device__ __forceinline__ void init(uint64_t *bars) {
+    bar0 = smem_u32(bars);
+    phase = 0;
+    if (TMA) {
+      if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+    }
+    __syncwarp(mask);
+  }
+
+  // Stage `nd` doubles (nd even, 16-byte aligned both sides) global -> shared.
+  __device__ __forceinline__ void issue_copy(int part, double *dst, const double *src, int nd) {
+    if (TMA) {
+      if (lane == 0) {
+        const uint32_t bar = bar0 + 8 * part;
+        const uint32_t bytes = (uint32_t)nd * 8u;
+        // order this group's earlier generic-proxy reads of the buffer before the
+        // async-proxy writes of the bulk copy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(dst)),
+            "l"(src), "r"(bytes), "r"(bar)
+            : "memory");
+      }
+    } else {
+      const uint32_t d = smem_u32(dst);
+      for (int c = lane; c < nd / 2; c += G)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * c), "l"(src + 2 * c)
+                     : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+
+  __device__ __forceinline__ void wait_copy(int part) {
+    if (TMA) {
+      const uint32_t bar = bar0 + 8 * part;
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"((phase >> part) & 1u)
+                     : "memory");
+      }
+      phase ^= (1u << part);
+    } else {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncwarp(mask);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// The persistent sweep kernel: every group walks the whole horizon of its
+// instance (backward, initial stage, forward) inside one launch.
+// ---------------------------------------------------------------------------
+template <class C, int WARPS, int MINB, bool TMA>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+    riccati_sweep_kernel(const SweepParams p, const int group_doubles) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int IPW = 32 / C::G; // instances per warp
+  const int warp = threadIdx.x >> 5;
+  const int lane32 = threadIdx.x & 31;
+  const int gsub = lane32 / C::G;
+  const int group_in_cta = warp * IPW + gsub;
+  const int inst = blockIdx.x * (WARPS * IPW) + group_in_cta;
+  if (inst >= p.batch)
+    return; // whole group leaves together
+  double *sm = smem + (size_t)group_in_cta * group_doubles;
+  uint64_t *bars =
+      reinterpret_cast<uint64_t *>(smem + (size_t)(WARPS * IPW) * group_doubles) + 2 * group_in_cta;
+  DevCtx<C::G, TMA> ctx;
+  ctx.lane = lane32 % C::G;
+  ctx.mask = (C::G == 32) ? 0xffffffffu : (((1u << C::G) - 1u) << (gsub * C::G));
+  ctx.init(bars);
+  riccati_group_sweep<C>(ctx, p, inst, sm);
+}
+
+// ---------------------------------------------------------------------------
+// Shape dispatch.
+// ---------------------------------------------------------------------------
+struct KernelEntry {
+  int nx, nu, nc, G;
+  int srec_pad;
+  void (*group_doubles)(int nc0, int gd[2]);
+  cudaError_t (*launch)(const SweepParams &, int variant, const int gd[2], cudaStream_t, int *info);
+};
+
+template <class C, int WARPS, int MINB, bool TMA>
+inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int *info) {
+  constexpr int IPW = 32 / C::G;
+  const int groups = WARPS * IPW;
+  const size_t smem = (size_t)groups * gd * sizeof(double) + (size_t)groups * 16;
+  auto kern = riccati_sweep_kernel<C, WARPS, MINB, TMA>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return e;
+  const int grid = (p.batch + groups - 1) / groups;
+  if (info) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    info[0] = C::G;
+    info[1] = (int)smem;
+    info[2] = WARPS * 32;
+    info[3] = grid;
+    info[4] = fa.numRegs;
+    return cudaSuccess;
+  }
+  kern<<<grid, WARPS * 32, smem, st>>>(p, gd);
+  return cudaGetLastError();
+}
+
+// Launch variants per shape (ab2_gar_tuning.variant):
+//   0: 2 warps/CTA x 7 CTAs/SM (14 warp-groups per SM, <= 144 registers), knot
+//      records double-buffered, one TMA bulk copy per knot          [default]
+//   1: 4 warps/CTA x 7 CTAs/SM (28 per SM: one wave at batch 4096 on 148 SMs,
+//      <= 72 registers), single record buffer refilled in two TMA parts
+//   2: as 0 with cp.async (LDGSTS) staging instead of TMA
+//   3: as 1 with cp.async staging
+template <int NX, int NU, int NC, int G>
+inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[2], cudaStream_t st, int *info) {
+  using CS = Cfg<NX, NU, NC, G, false>;
+  using CD = Cfg<NX, NU, NC, G, true>;
+#ifndef AB2_SINGLE_VARIANT
+  if (variant == 1)
+    return launch_one<CS, 4, 7, true>(p, gd[0], st, info);
+  if (variant == 2)
+    return launch_one<CD, 2, 7, false>(p, gd[1], st, info);
+  if (variant == 3)
+    return launch_one<CS, 4, 7, false>(p, gd[0], st, info);
+#endif
+  return launch_one<CD, 2, 7, true>(p, gd[1], st, info);
+}
+template <int NX, int NU, int NC, int G> inline void group_doubles_cfg(int nc0, int gd[2]) {
+  gd[0] = Cfg<NX, NU, NC, G, false>::group_doubles(nc0);
+  gd[1] = Cfg<NX, NU, NC, G, true>::group_doubles(nc0);
+}
+
+} // namespace ab2

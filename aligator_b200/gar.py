@@ -1,0 +1,382 @@
+"""Python host side of the B200 batched Riccati sweep: a ctypes binding of the C ABI
+(include/aligator_b200/gar.h) plus classes that mirror the reference's operator
+interface for this path -- ``gar::RiccatiSolverBase`` (gar/riccati-base.hpp:13-37) as
+implemented by ``gar::ProximalRiccatiSolver`` (gar/proximal-riccati.hpp:12-47).
+
+There is NO CPU fallback: loading fails loudly when the CUDA library has not been
+built, and every call fails loudly without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .lqr import LqrProblem, lqr_initialize_solution
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libaligator_b200_gar.so")
+
+AB2_HOST, AB2_DEVICE = 0, 1
+(OUT_FF, OUT_FB, OUT_VXX, OUT_VX, OUT_FFT, OUT_FBT, OUT_KKT0, OUT_XS, OUT_US, OUT_VS, OUT_VST,
+ OUT_LBD0, OUT_LBDAS) = range(13)
+
+_dp = C.POINTER(C.c_double)
+
+
+class GarDims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nx", "nu", "nc", "nct", "nc0", "horizon", "batch", "device")]
+
+
+class GarTuning(C.Structure):
+    _fields_ = [("variant", C.c_int)]
+
+
+class GarError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The C-ABI library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GarError("%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for this path)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.ab2_gar_last_error.restype = C.c_char_p
+        L.ab2_gar_version.restype = C.c_char_p
+        L.ab2_gar_stage_record_doubles.restype = C.c_size_t
+        L.ab2_gar_term_record_doubles.restype = C.c_size_t
+        L.ab2_gar_output_doubles.restype = C.c_size_t
+        L.ab2_gar_output_doubles.argtypes = [C.c_void_p, C.c_int]
+        L.ab2_gar_launch_count.restype = C.c_long
+        L.ab2_gar_launch_count.argtypes = [C.c_void_p]
+        L.ab2_gar_create.argtypes = [C.POINTER(GarDims), C.POINTER(C.c_void_p)]
+        L.ab2_gar_destroy.argtypes = [C.c_void_p]
+        L.ab2_gar_set_tuning.argtypes = [C.c_void_p, C.POINTER(GarTuning)]
+        L.ab2_gar_set_problem.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_void_p]
+        L.ab2_gar_backward.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.ab2_gar_forward.argtypes = [C.c_void_p, C.c_void_p]
+        L.ab2_gar_sweep.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.ab2_gar_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_get_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.ab2_gar_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_cycle_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_synchronize.argtypes = [C.c_void_p, C.c_void_p]
+        L.ab2_gar_kernel_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise GarError("aligator_b200 gar error %d: %s" % (rc, lib().ab2_gar_last_error().decode()))
+
+
+def stage_record_doubles(nx, nu, nc):
+    return int(lib().ab2_gar_stage_record_doubles(nx, nu, nc))
+
+
+def term_record_doubles(nx, nct):
+    return int(lib().ab2_gar_term_record_doubles(nx, nct))
+
+
+def supported(nx, nu, nc, nc0):
+    return bool(lib().ab2_gar_supported(nx, nu, nc, nc0))
+
+
+def _ptr(a):
+    """Raw address of a numpy array / torch tensor / int."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class CudaRiccatiBatch:
+    """Thin owner of an ``ab2_gar_solver`` handle: `batch` independent LQ problems of
+    identical dimensions (stage knots (nx,nu,nc), terminal knot (nx,0,nct))."""
+
+    def __init__(self, nx, nu, nc, nct, nc0, horizon, batch, device=0, variant=-1):
+        self.dims = GarDims(nx, nu, nc, nct, nc0, horizon, batch, device)
+        self.h = C.c_void_p()
+        _check(lib().ab2_gar_create(C.byref(self.dims), C.byref(self.h)))
+        if variant >= 0:
+            _check(lib().ab2_gar_set_tuning(self.h, C.byref(GarTuning(variant))))
+        self.srec = stage_record_doubles(nx, nu, nc)
+        self.trec = term_record_doubles(nx, nct)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib().ab2_gar_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    # ---- problem data -------------------------------------------------------
+    def set_problem(self, stage=None, term=None, G0=None, g0=None, memspace=AB2_HOST, stream=0):
+        """stage [batch][N][srec], term [batch][trec], G0 [batch][nc0*nx] (col-major
+        blocks), g0 [batch][nc0]; host numpy arrays or device pointers/tensors."""
+        if memspace == AB2_HOST:
+            conv = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+            stage, term, G0, g0 = conv(stage), conv(term), conv(G0), conv(g0)
+            d = self.dims
+            if stage is not None:
+                assert stage.size == d.batch * d.horizon * self.srec, "stage size"
+            if term is not None:
+                assert term.size == d.batch * self.trec, "term size"
+        self._keep = (stage, term, G0, g0)
+        _check(lib().ab2_gar_set_problem(self.h, _ptr(stage), _ptr(term), _ptr(G0), _ptr(g0),
+                                         memspace, C.c_void_p(stream)))
+
+    # ---- the hot calls ------------------------------------------------------
+    def backward(self, mueq, stream=0):
+        _check(lib().ab2_gar_backward(self.h, float(mueq), C.c_void_p(stream)))
+
+    def forward(self, stream=0):
+        _check(lib().ab2_gar_forward(self.h, C.c_void_p(stream)))
+
+    def sweep(self, mueq, stream=0):
+        _check(lib().ab2_gar_sweep(self.h, float(mueq), C.c_void_p(stream)))
+
+    def synchronize(self, stream=0):
+        _check(lib().ab2_gar_synchronize(self.h, C.c_void_p(stream)))
+
+    # ---- results ------------------------------------------------------------
+    def out_shape(self, what):
+        d = self.dims
+        nr = d.nu + d.nc + d.nx
+        return {
+            OUT_FF: (d.batch, d.horizon, nr), OUT_FB: (d.batch, d.horizon, nr, d.nx),
+            OUT_VXX: (d.batch, d.horizon + 1, d.nx, d.nx), OUT_VX: (d.batch, d.horizon + 1, d.nx),
+            OUT_FFT: (d.batch, d.nct), OUT_FBT: (d.batch, d.nct, d.nx),
+            OUT_KKT0: (d.batch, d.nx + d.nc0), OUT_XS: (d.batch, d.horizon + 1, d.nx),
+            OUT_US: (d.batch, d.horizon, d.nu), OUT_VS: (d.batch, d.horizon, d.nc),
+            OUT_VST: (d.batch, d.nct), OUT_LBD0: (d.batch, d.nc0),
+            OUT_LBDAS: (d.batch, d.horizon, d.nx)}[what]
+
+    def get(self, what, out=None, stream=0, sync=True):
+        """Copy an output array to the host.  VXX blocks are column-major in memory; the
+        returned array is indexed [b, t, i, j]."""
+        shape = self.out_shape(what)
+        n = int(np.prod(shape))
+        assert n == lib().ab2_gar_output_doubles(self.h, what)
+        buf = out if out is not None else np.empty(max(n, 1), dtype=np.float64)
+        if n:
+            _check(lib().ab2_gar_get(self.h, what, _ptr(buf), AB2_HOST, C.c_void_p(stream)))
+            if sync:
+                self.synchronize(stream)
+        a = buf[:n].reshape(shape)
+        if what == OUT_VXX:
+            a = a.transpose(0, 1, 3, 2)
+        return a
+
+    def get_into(self, what, dst, memspace, stream=0):
+        _check(lib().ab2_gar_get(self.h, what, _ptr(dst), memspace, C.c_void_p(stream)))
+
+    def get_range_into(self, what, b0, nb, t0, nt, dst, memspace, stream=0):
+        _check(lib().ab2_gar_get_range(self.h, what, b0, nb, t0, nt, _ptr(dst), memspace,
+                                       C.c_void_p(stream)))
+
+    def device_ptr(self, what):
+        p = C.c_void_p()
+        _check(lib().ab2_gar_device_ptr(self.h, what, C.byref(p)))
+        return p.value
+
+    def status(self, stream=0):
+        st = np.empty(self.dims.batch, dtype=np.int32)
+        _check(lib().ab2_gar_status(self.h, _ptr(st), AB2_HOST, C.c_void_p(stream)))
+        self.synchronize(stream)
+        return st
+
+    def cycle_append(self, new_last, memspace=AB2_HOST, stream=0):
+        if memspace == AB2_HOST:
+            new_last = np.ascontiguousarray(new_last, dtype=np.float64)
+            assert new_last.size == self.dims.batch * self.srec
+        _check(lib().ab2_gar_cycle_append(self.h, _ptr(new_last), memspace, C.c_void_p(stream)))
+        self.synchronize(stream)
+
+    def launch_count(self):
+        return int(lib().ab2_gar_launch_count(self.h))
+
+    def kernel_info(self):
+        v = [C.c_int() for _ in range(5)]
+        _check(lib().ab2_gar_kernel_info(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("group_lanes", "smem_bytes_per_cta", "threads_per_cta", "grid",
+                         "regs_per_thread"), [x.value for x in v]))
+
+
+# ---------------------------------------------------------------------------
+# packing of LqrProblem objects into the C-ABI layout
+# ---------------------------------------------------------------------------
+def _F(a):
+    return np.asarray(a, dtype=np.float64).ravel(order="F")
+
+
+def pack_stage_knot(k, srec):
+    rec = np.concatenate([_F(k.A), _F(k.B), _F(k.f), _F(k.Q), _F(k.S), _F(k.R), _F(k.q), _F(k.r),
+                          _F(k.C), _F(k.D), _F(k.d)])
+    if rec.size < srec:
+        rec = np.concatenate([rec, np.zeros(srec - rec.size)])
+    return rec
+
+
+def pack_term_knot(k):
+    return np.concatenate([_F(k.Q), _F(k.q), _F(k.C), _F(k.d)])
+
+
+def pack_problems(problems):
+    """Uniform-dims problems (terminal knot nu = 0, nth = 0) -> (stage, term, G0, g0)."""
+    p0 = problems[0]
+    N = p0.horizon
+    k0 = p0.stages[0] if N > 0 else None
+    kt = p0.stages[N]
+    nx = kt.nx
+    nu, nc = (k0.nu, k0.nc) if N > 0 else (1, 0)
+    srec = stage_record_doubles(nx, nu, nc)
+    for p in problems:
+        if p.horizon != N or p.nc0 != p0.nc0:
+            raise GarError("all problems of a batch must share horizon and nc0")
+        for t, s in enumerate(p.stages):
+            want = (nx, nu, nc, nx, 0) if t < N else (nx, 0, kt.nc, s.nx2, 0)
+            if s.dims != want:
+                raise GarError("knot %d has dims %s, expected %s (uniform dims, terminal nu=0, nth=0)"
+                               % (t, s.dims, want))
+    stage = np.empty((len(problems), N, srec))
+    for b, p in enumerate(problems):
+        for t in range(N):
+            stage[b, t] = pack_stage_knot(p.stages[t], srec)
+    term = np.stack([pack_term_knot(p.stages[N]) for p in problems])
+    G0 = np.stack([_F(p.G0) for p in problems]) if p0.nc0 else np.zeros((len(problems), 0))
+    g0 = np.stack([np.asarray(p.g0, dtype=np.float64) for p in problems]) if p0.nc0 \
+        else np.zeros((len(problems), 0))
+    return stage, term, G0, g0
+
+
+class ProximalRiccatiSolver:
+    """Mirror of ``gar::ProximalRiccatiSolver`` for ONE ``LqrProblem`` or a list of them
+    (a batch).  Same call sequence as the reference:
+
+        solver = ProximalRiccatiSolver(problem)      # proximal-riccati.hxx:13-31
+        solver.backward(mueq)                        # riccati-base.hpp:19
+        solver.forward(xs, us, vs, lbdas)            # riccati-base.hpp:21-24
+        solver.getFeedforward(i); solver.getFeedback(i)   # riccati-base.hpp:33-34
+
+    Like the reference it keeps a non-owning reference to the problem and re-reads it
+    at every ``backward`` (the knots are rewritten in place between iterations).
+    For a batch, ``forward`` takes lists of per-instance solution lists and the
+    getters take ``(i, b)``.
+    """
+
+    def __init__(self, problem, device=0, variant=-1):
+        self.problems = [problem] if isinstance(problem, LqrProblem) else list(problem)
+        p0 = self.problems[0]
+        N = p0.horizon
+        kt = p0.stages[N]
+        if kt.nu != 0:
+            raise GarError("the terminal knot must have nu = 0")
+        if N > 0:
+            k0 = p0.stages[0]
+            nu, nc = k0.nu, k0.nc
+        else:
+            nu, nc = 1, 0  # no stage knots: any instantiated shape serves
+        if p0.ntheta != 0:
+            raise GarError("parameterised problems (nth > 0) are not supported by the CUDA path")
+        self.nx, self.nu, self.nc, self.nct = kt.nx, nu, nc, kt.nc
+        if N == 0:
+            for cand in (2, 3, 1, 4, 6):
+                if supported(self.nx, cand, 0, p0.nc0):
+                    self.nu = cand
+                    break
+        self.batch = CudaRiccatiBatch(self.nx, self.nu, self.nc, self.nct, p0.nc0, N,
+                                      len(self.problems), device, variant)
+        self._single = isinstance(problem, LqrProblem)
+        self._cache = {}
+
+    # -- RiccatiSolverBase ---------------------------------------------------
+    def backward(self, mueq):
+        stage, term, G0, g0 = pack_problems(self.problems)
+        self.batch.set_problem(stage, term, G0, g0)
+        self.batch.backward(mueq)
+        self._cache = {}
+        st = self.batch.status()
+        if np.any(st & 1):
+            # the reference throws here (riccati-kernel.hxx:239-241)
+            raise GarError("Failed stage LDL factorization (instances %s)"
+                           % np.nonzero(st & 1)[0][:8].tolist())
+        return True
+
+    def forward(self, xs, us, vs, lbdas, theta=None):
+        if theta is not None:
+            raise GarError("theta is not supported (nth = 0 only)")
+        self.batch.forward()
+        B = self.batch
+        N = B.dims.horizon
+        X, U, V, VT = B.get(OUT_XS), B.get(OUT_US), B.get(OUT_VS), B.get(OUT_VST)
+        L0, L = B.get(OUT_LBD0), B.get(OUT_LBDAS)
+        sols = [(xs, us, vs, lbdas)] if self._single else list(zip(xs, us, vs, lbdas))
+        for b, (x, u, v, l) in enumerate(sols):
+            for t in range(N + 1):
+                x[t][:] = X[b, t]
+            for t in range(N):
+                u[t][:] = U[b, t]
+                v[t][:] = V[b, t]
+                l[t + 1][:] = L[b, t]
+            v[N][:] = VT[b]
+            l[0][:] = L0[b]
+        return True
+
+    def collapseFeedback(self):
+        """No-op for the serial solver (riccati-base.hpp:32)."""
+
+    def _get(self, what):
+        if what not in self._cache:
+            self._cache[what] = self.batch.get(what)
+        return self._cache[what]
+
+    def getFeedforward(self, i, b=0):
+        """ff = [k; z; a] of knot i (length nu+nc+nx); the terminal knot's is [z]."""
+        N = self.batch.dims.horizon
+        return self._get(OUT_FFT)[b] if i == N else self._get(OUT_FF)[b, i]
+
+    def getFeedback(self, i, b=0):
+        """fb = [K; Z; Ahat] of knot i, (nu+nc+nx) x nx; the terminal knot's is [Z]."""
+        N = self.batch.dims.horizon
+        return self._get(OUT_FBT)[b] if i == N else self._get(OUT_FB)[b, i]
+
+    def Vxx(self, i, b=0):
+        return self._get(OUT_VXX)[b, i]
+
+    def vx(self, i, b=0):
+        return self._get(OUT_VX)[b, i]
+
+    def kkt0_ff(self, b=0):
+        return self._get(OUT_KKT0)[b]
+
+    def cycleAppend(self, knot):
+        """proximal-riccati.hxx:79-86; `knot`: an LqrKnot (same for the whole batch) or a
+        list of one per instance.  The caller rotates its own problem objects, as
+        SolverProxDDP::cycleProblem does (solver-proxddp.hxx:202-209)."""
+        knots = [knot] * len(self.problems) if not isinstance(knot, (list, tuple)) else knot
+        rec = np.stack([pack_stage_knot(k, self.batch.srec) for k in knots])
+        self.batch.cycle_append(rec)
+        self._cache = {}
+
+
+def lqr_initialize_solution_batch(problems):
+    sols = [lqr_initialize_solution(p) for p in problems]
+    return tuple(list(z) for z in zip(*sols))

