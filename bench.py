@@ -28,6 +28,13 @@ sys.path.insert(0, ROOT)
 NX, NU, NC, NCT, HORIZON, BATCH = 12, 6, 0, 0, 100, 4096
 MUEQ = 1e-11  # bench/gar-riccati.cpp:22
 WORKLOAD = "batched synthetic LQR nx=12 nu=6 nc=0 N=100 batch=4096 per GPU (BASELINE config 2)"
+# other BASELINE configs, selectable with --config for profiling (the default line is config 2)
+CONFIGS = {
+    "c2": (12, 6, 0, 0, 100, 4096, 1e-11, WORKLOAD),
+    "c1": (6, 3, 0, 0, 100, 4096, 1e-11, "nx=6 nu=3 N=100 (BASELINE config 1 dims) batch=4096"),
+    "c3": (4, 2, 2, 0, 100, 16384, 1e-3, "nx=4 nu=2 nc=2 N=100 batch=16384 (BASELINE config 3)"),
+    "c4": (14, 7, 0, 0, 200, 2048, 1e-11, "nx=14 nu=7 N=200 batch=2048 (BASELINE config 4)"),
+}
 
 
 def bytes_per_knot(nx, nu, nc):
@@ -38,7 +45,7 @@ def bytes_per_knot(nx, nu, nc):
     return 8 * (rd + wr + fw)
 
 
-def synth_batch_torch(torch, batch, N, nx, nu, device, seed):
+def synth_batch_torch(torch, batch, N, nx, nu, device, seed, nc=0):
     """SURVEY section 8(d) synthetic inputs (conditioned variant), generated on `device`,
     packed in the C-ABI layout [A|B|f|Q|S|R|q|r] (column-major blocks)."""
     g = torch.Generator(device=device)
@@ -54,8 +61,15 @@ def synth_batch_torch(torch, batch, N, nx, nu, device, seed):
     A = torch.eye(nx, device=device, dtype=f64) + 0.1 * rn(batch, N, nx, nx) / nx ** 0.5
     Bm = ru(batch, N, nx, nu)
     cm = lambda M: M.transpose(-1, -2).reshape(batch, N, -1)  # column-major flatten
-    stage = torch.cat([cm(A), cm(Bm), rn(batch, N, nx), cm(Q), cm(S), cm(R), ru(batch, N, nx),
-                       ru(batch, N, nu)], dim=-1).contiguous()
+    parts = [cm(A), cm(Bm), rn(batch, N, nx), cm(Q), cm(S), cm(R), ru(batch, N, nx), ru(batch, N, nu)]
+    if nc > 0:  # C = 0, D = I rows with a random half zeroed (inactive box rows), d ~ U[-1,1]
+        act = (torch.rand(batch, N, nc, generator=g, device=device, dtype=f64) < 0.5).to(f64)
+        D = torch.eye(nc, nu, device=device, dtype=f64).expand(batch, N, nc, nu) * act[..., None]
+        parts += [torch.zeros(batch, N, nc * nx, device=device, dtype=f64), cm(D), ru(batch, N, nc) * act]
+    stage = torch.cat(parts, dim=-1)
+    if stage.shape[-1] % 2:
+        stage = torch.cat([stage, torch.zeros(batch, N, 1, device=device, dtype=f64)], dim=-1)
+    stage = stage.contiguous()
     Wt = rn(batch, nx, nx + 1)
     Qt = Wt @ Wt.transpose(-1, -2) / nx
     term = torch.cat([Qt.transpose(-1, -2).reshape(batch, -1), ru(batch, nx)], dim=-1).contiguous()
@@ -136,7 +150,7 @@ def run_reference(args, rank, world):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     nb = 256
-    stage, term, G0, g0 = [a.numpy() for a in synth_batch_torch(torch, nb, HORIZON, NX, NU, "cpu", 1234)]
+    stage, term, G0, g0 = [a.numpy() for a in synth_batch_torch(torch, nb, HORIZON, NX, NU, "cpu", 1234, NC)]
     from oracle import gar_oracle as orc
     bo = orc.BatchedOracle(NX, NU, NC, NCT, NX, HORIZON, nb, stage, term, G0, g0)
     threads = orc.num_threads()
@@ -170,7 +184,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     args = ap.parse_args()
+    global NX, NU, NC, NCT, HORIZON, BATCH, MUEQ, WORKLOAD
+    if args.config != "c2":
+        NX, NU, NC, NCT, HORIZON, BATCH, MUEQ, WORKLOAD = CONFIGS[args.config]
+        if args.batch == 4096:
+            args.batch = BATCH
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,7 +218,7 @@ def main():
     import aligator_b200.gar as gar
 
     B, N = args.batch, HORIZON
-    stage, term, G0, g0 = synth_batch_torch(torch, B, N, NX, NU, dev, 1234 + rank)
+    stage, term, G0, g0 = synth_batch_torch(torch, B, N, NX, NU, dev, 1234 + rank, NC)
     solver = gar.CudaRiccatiBatch(NX, NU, NC, NCT, NX, N, B, device=local, variant=args.variant)
     stream = torch.cuda.current_stream().cuda_stream
     solver.set_problem(stage, term, G0, g0, memspace=gar.AB2_DEVICE, stream=stream)
@@ -325,7 +345,7 @@ def main():
                        "batch_per_gpu": B, "mueq": MUEQ, "parallelism": "batch-sharded x%d" % world,
                        "generator": "SURVEY 8(d) conditioned variant, counter-seeded per rank",
                        "l2": "inputs+outputs per sweep (%.2f GB) exceed the 126 MB L2; no flush needed"
-                             % ((stage.numel() * 8 + B * (N + 1) * 8 * 390) / 1e9),
+                             % ((stage.numel() * 8 + B * (N + 1) * 8 * ((NU + NC + NX) * (NX + 1) + NX * NX + NX)) / 1e9),
                        "kernel": solver.kernel_info(), "variant": args.variant},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e,
             "gpu_launches": launches}

@@ -1,0 +1,331 @@
+// aligator_b200/riccati_solver.hpp -- C++ host side above the C ABI (gar.h).
+//
+// Mirrors the reference's operator interface for this path, name for name:
+//   aligator::gar::LqrKnotTpl<double>        gar/lqr-problem.hpp:49-118
+//   aligator::gar::LqrProblemTpl<double>     gar/lqr-problem.hpp:120-210
+//   aligator::gar::RiccatiSolverBase<double> gar/riccati-base.hpp:13-37
+//   aligator::gar::ProximalRiccatiSolver     gar/proximal-riccati.hpp:12-47
+// so that a caller written against the reference (bench/gar-riccati.cpp:42-50,
+// SolverProxDDPTpl::innerLoop, solver-proxddp.hxx:605-632) reads the same.
+//
+// Header-only, C++17, no Eigen (Eigen is not available in this build image); the
+// Eigen-typed adapter a maintainer would use inside aligator is shown in
+// INTEGRATION.md.  Matrices are column-major std::vector<double>, fb is row-major,
+// exactly the reference's storage orders.  Errors: hard failures throw
+// aligator_b200::RuntimeError like the reference throws aligator::RuntimeError
+// (utils/exceptions.hpp:8-10; "Failed stage LDL factorization",
+// riccati-kernel.hxx:239-241).  No CPU fallback exists.
+#pragma once
+
+#include <cstddef>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "gar.h"
+
+namespace aligator_b200 {
+
+struct RuntimeError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+namespace gar {
+
+using uint = unsigned int;
+using VectorXs = std::vector<double>;
+
+/// One stage of the LQ problem; zero-initialised like lqr-problem.hxx:29-72.
+struct LqrKnot {
+  uint nx = 0, nu = 0, nc = 0, nx2 = 0, nth = 0;
+  std::vector<double> Q, S, R, q, r; // Q nx*nx, S nx*nu, R nu*nu (column-major)
+  std::vector<double> A, B, f;       // A nx2*nx, B nx2*nu
+  std::vector<double> C, D, d;       // C nc*nx, D nc*nu
+  LqrKnot() = default;
+  LqrKnot(uint nx_, uint nu_, uint nc_, uint nx2_, uint nth_ = 0)
+      : nx(nx_), nu(nu_), nc(nc_), nx2(nx2_), nth(nth_), Q((size_t)nx_ * nx_), S((size_t)nx_ * nu_),
+        R((size_t)nu_ * nu_), q(nx_), r(nu_), A((size_t)nx2_ * nx_), B((size_t)nx2_ * nu_), f(nx2_),
+        C((size_t)nc_ * nx_), D((size_t)nc_ * nu_), d(nc_) {
+    if (nth_ != 0)
+      throw RuntimeError("parameterised knots (nth > 0) are not supported by the CUDA path");
+  }
+  LqrKnot(uint nx_, uint nu_, uint nc_) : LqrKnot(nx_, nu_, nc_, nx_, 0) {}
+};
+
+struct LqrProblem {
+  std::vector<LqrKnot> stages;
+  std::vector<double> G0; // nc0 x nx0 column-major
+  std::vector<double> g0;
+  LqrProblem() = default;
+  LqrProblem(std::vector<LqrKnot> knots, long nc0)
+      : stages(std::move(knots)), G0((size_t)nc0 * (stages.empty() ? 0 : stages[0].nx)), g0((size_t)nc0) {}
+  int horizon() const noexcept { return (int)stages.size() - 1; }
+  uint nc0() const noexcept { return (uint)g0.size(); }
+};
+
+/// Row-major matrix view (the reference's RowMatrixRef).
+struct RowMatrixRef {
+  double *data;
+  int rows, cols;
+  double &operator()(int i, int j) const { return data[(size_t)i * cols + j]; }
+};
+struct VectorRef {
+  double *data;
+  int size;
+  double &operator[](int i) const { return data[i]; }
+};
+
+/// gar/riccati-base.hpp:13-37, same six virtuals.
+class RiccatiSolverBase {
+public:
+  virtual bool backward(const double mueq) = 0;
+  virtual bool forward(std::vector<VectorXs> &xs, std::vector<VectorXs> &us, std::vector<VectorXs> &vs,
+                       std::vector<VectorXs> &lbdas,
+                       const std::optional<VectorXs> &theta = std::nullopt) const = 0;
+  virtual void cycleAppend(const LqrKnot &knot) = 0;
+  virtual void collapseFeedback() {}
+  virtual VectorRef getFeedforward(size_t i) = 0;
+  virtual RowMatrixRef getFeedback(size_t i) = 0;
+  virtual ~RiccatiSolverBase() = default;
+};
+
+/// gar/utils.hpp:114-142
+inline void lqrInitializeSolution(const LqrProblem &p, std::vector<VectorXs> &xs, std::vector<VectorXs> &us,
+                                  std::vector<VectorXs> &vs, std::vector<VectorXs> &lbdas) {
+  const int N = p.horizon();
+  xs.assign(N + 1, {});
+  us.assign(N + 1, {});
+  vs.assign(N + 1, {});
+  lbdas.assign(N + 1, {});
+  lbdas[0].assign(p.nc0(), 0.);
+  for (int i = 0; i <= N; ++i) {
+    const LqrKnot &k = p.stages[i];
+    xs[i].assign(k.nx, 0.);
+    us[i].assign(k.nu, 0.);
+    vs[i].assign(k.nc, 0.);
+    if (i == N)
+      break;
+    lbdas[i + 1].assign(k.nx2, 0.);
+  }
+  if (p.stages.back().nu == 0)
+    us.pop_back();
+}
+
+/// Drop-in for gar::ProximalRiccatiSolver backed by the B200 sweep.  Constructed from
+/// one problem (batch = 1, the reference's use) or from `batch` problems of identical
+/// dimensions.  Keeps NON-owning pointers to the problems and re-reads them at every
+/// backward(), as the reference does (proximal-riccati.hpp:46).
+class CudaRiccatiSolver : public RiccatiSolverBase {
+public:
+  explicit CudaRiccatiSolver(const LqrProblem &problem, int device = 0)
+      : CudaRiccatiSolver(std::vector<const LqrProblem *>{&problem}, device) {}
+
+  explicit CudaRiccatiSolver(std::vector<const LqrProblem *> problems, int device = 0)
+      : problems_(std::move(problems)) {
+    if (problems_.empty() || problems_[0]->stages.empty())
+      throw RuntimeError("empty problem");
+    const LqrProblem &p0 = *problems_[0];
+    const int N = p0.horizon();
+    const LqrKnot &kt = p0.stages[N];
+    if (kt.nu != 0)
+      throw RuntimeError("the terminal knot must have nu = 0");
+    dims_.nx = (int)kt.nx;
+    dims_.nu = N > 0 ? (int)p0.stages[0].nu : 2;
+    dims_.nc = N > 0 ? (int)p0.stages[0].nc : 0;
+    dims_.nct = (int)kt.nc;
+    dims_.nc0 = (int)p0.nc0();
+    dims_.horizon = N;
+    dims_.batch = (int)problems_.size();
+    dims_.device = device;
+    check(ab2_gar_create(&dims_, &h_));
+    srec_ = ab2_gar_stage_record_doubles(dims_.nx, dims_.nu, dims_.nc);
+    trec_ = ab2_gar_term_record_doubles(dims_.nx, dims_.nct);
+    const int nr = dims_.nu + dims_.nc + dims_.nx;
+    stage_.assign((size_t)dims_.batch * N * srec_, 0.);
+    term_.assign((size_t)dims_.batch * trec_, 0.);
+    G0_.assign((size_t)dims_.batch * dims_.nc0 * dims_.nx, 0.);
+    g0_.assign((size_t)dims_.batch * dims_.nc0, 0.);
+    ff_.assign((size_t)dims_.batch * N * nr, 0.);
+    fb_.assign((size_t)dims_.batch * N * nr * dims_.nx, 0.);
+    ffT_.assign((size_t)dims_.batch * dims_.nct, 0.);
+    fbT_.assign((size_t)dims_.batch * dims_.nct * dims_.nx, 0.);
+  }
+  ~CudaRiccatiSolver() override { ab2_gar_destroy(h_); }
+  CudaRiccatiSolver(const CudaRiccatiSolver &) = delete;
+  CudaRiccatiSolver &operator=(const CudaRiccatiSolver &) = delete;
+
+  /// riccati-base.hpp:19
+  bool backward(const double mueq) override {
+    pack();
+    check(ab2_gar_set_problem(h_, stage_.data(), term_.data(), G0_.data(), g0_.data(), AB2_HOST, nullptr));
+    check(ab2_gar_backward(h_, mueq, nullptr));
+    std::vector<int> st(dims_.batch);
+    check(ab2_gar_status(h_, st.data(), AB2_HOST, nullptr));
+    check(ab2_gar_get(h_, AB2_OUT_FF, ff_.data(), AB2_HOST, nullptr));
+    check(ab2_gar_get(h_, AB2_OUT_FB, fb_.data(), AB2_HOST, nullptr));
+    if (dims_.nct > 0) {
+      check(ab2_gar_get(h_, AB2_OUT_FFT, ffT_.data(), AB2_HOST, nullptr));
+      check(ab2_gar_get(h_, AB2_OUT_FBT, fbT_.data(), AB2_HOST, nullptr));
+    }
+    check(ab2_gar_synchronize(h_, nullptr));
+    for (int b = 0; b < dims_.batch; ++b)
+      if (st[b] & 1)
+        throw RuntimeError("Failed stage LDL factorization (instance " + std::to_string(b) + ")");
+    return true;
+  }
+
+  /// riccati-base.hpp:21-24 (batch = 1)
+  bool forward(std::vector<VectorXs> &xs, std::vector<VectorXs> &us, std::vector<VectorXs> &vs,
+               std::vector<VectorXs> &lbdas, const std::optional<VectorXs> &theta = std::nullopt) const override {
+    if (theta.has_value())
+      throw RuntimeError("theta is not supported (nth = 0 only)");
+    run_forward();
+    scatter(0, xs, us, vs, lbdas);
+    return true;
+  }
+  /// batched variant: one solution set per problem
+  bool forward(std::vector<std::vector<VectorXs>> &xs, std::vector<std::vector<VectorXs>> &us,
+               std::vector<std::vector<VectorXs>> &vs, std::vector<std::vector<VectorXs>> &lbdas) const {
+    run_forward();
+    for (int b = 0; b < dims_.batch; ++b)
+      scatter(b, xs[b], us[b], vs[b], lbdas[b]);
+    return true;
+  }
+
+  /// proximal-riccati.hxx:79-86 (same knot appended to every instance)
+  void cycleAppend(const LqrKnot &knot) override {
+    std::vector<double> rec((size_t)dims_.batch * srec_, 0.);
+    for (int b = 0; b < dims_.batch; ++b)
+      pack_stage(knot, rec.data() + (size_t)b * srec_);
+    check(ab2_gar_cycle_append(h_, rec.data(), AB2_HOST, nullptr));
+    check(ab2_gar_get(h_, AB2_OUT_FF, ff_.data(), AB2_HOST, nullptr));
+    check(ab2_gar_get(h_, AB2_OUT_FB, fb_.data(), AB2_HOST, nullptr));
+    check(ab2_gar_synchronize(h_, nullptr));
+  }
+
+  VectorRef getFeedforward(size_t i) override { return getFeedforward(i, 0); }
+  RowMatrixRef getFeedback(size_t i) override { return getFeedback(i, 0); }
+  VectorRef getFeedforward(size_t i, int b) {
+    const int N = dims_.horizon, nr = dims_.nu + dims_.nc + dims_.nx;
+    if ((int)i == N)
+      return {ffT_.data() + (size_t)b * dims_.nct, dims_.nct};
+    return {ff_.data() + ((size_t)b * N + i) * nr, nr};
+  }
+  RowMatrixRef getFeedback(size_t i, int b) {
+    const int N = dims_.horizon, nr = dims_.nu + dims_.nc + dims_.nx;
+    if ((int)i == N)
+      return {fbT_.data() + (size_t)b * dims_.nct * dims_.nx, dims_.nct, dims_.nx};
+    return {fb_.data() + ((size_t)b * N + i) * nr * dims_.nx, nr, dims_.nx};
+  }
+  /// datas[i].vm.Vxx (column-major nx*nx) / vm.vx, fetched on demand
+  std::vector<double> Vxx(size_t i, int b = 0) const {
+    std::vector<double> out((size_t)dims_.nx * dims_.nx);
+    check(ab2_gar_get_range(h_, AB2_OUT_VXX, b, 1, (int)i, 1, out.data(), AB2_HOST, nullptr));
+    check(ab2_gar_synchronize(h_, nullptr));
+    return out;
+  }
+  std::vector<double> vx(size_t i, int b = 0) const {
+    std::vector<double> out((size_t)dims_.nx);
+    check(ab2_gar_get_range(h_, AB2_OUT_VX, b, 1, (int)i, 1, out.data(), AB2_HOST, nullptr));
+    check(ab2_gar_synchronize(h_, nullptr));
+    return out;
+  }
+  ab2_gar_solver *handle() const { return h_; }
+  const ab2_gar_dims &dims() const { return dims_; }
+
+private:
+  static void check(int rc) {
+    if (rc != AB2_OK)
+      throw RuntimeError(std::string("aligator_b200: ") + ab2_gar_last_error());
+  }
+  static double *put(double *dst, const std::vector<double> &src, size_t n, const char *name) {
+    if (src.size() != n)
+      throw RuntimeError(std::string("knot field has the wrong size: ") + name);
+    for (size_t i = 0; i < n; ++i)
+      dst[i] = src[i];
+    return dst + n;
+  }
+  void pack_stage(const LqrKnot &k, double *o) const {
+    const size_t nx = dims_.nx, nu = dims_.nu, nc = dims_.nc;
+    if (k.nx != nx || k.nu != nu || k.nc != nc || k.nx2 != nx || k.nth != 0)
+      throw RuntimeError("stage knot dims differ from the solver's (uniform dims, nx2 = nx, nth = 0)");
+    o = put(o, k.A, nx * nx, "A");
+    o = put(o, k.B, nx * nu, "B");
+    o = put(o, k.f, nx, "f");
+    o = put(o, k.Q, nx * nx, "Q");
+    o = put(o, k.S, nx * nu, "S");
+    o = put(o, k.R, nu * nu, "R");
+    o = put(o, k.q, nx, "q");
+    o = put(o, k.r, nu, "r");
+    o = put(o, k.C, nc * nx, "C");
+    o = put(o, k.D, nc * nu, "D");
+    o = put(o, k.d, nc, "d");
+  }
+  void pack() {
+    const int N = dims_.horizon;
+    const size_t nx = dims_.nx, nct = dims_.nct;
+    for (int b = 0; b < dims_.batch; ++b) {
+      const LqrProblem &p = *problems_[b];
+      if (p.horizon() != N || (int)p.nc0() != dims_.nc0)
+        throw RuntimeError("problems of a batch must share horizon and nc0");
+      for (int t = 0; t < N; ++t)
+        pack_stage(p.stages[t], stage_.data() + ((size_t)b * N + t) * srec_);
+      const LqrKnot &k = p.stages[N];
+      if (k.nx != nx || k.nu != 0 || k.nc != nct)
+        throw RuntimeError("terminal knot dims differ from the solver's");
+      double *o = term_.data() + (size_t)b * trec_;
+      o = put(o, k.Q, nx * nx, "Q");
+      o = put(o, k.q, nx, "q");
+      o = put(o, k.C, nct * nx, "C");
+      o = put(o, k.d, nct, "d");
+      put(G0_.data() + (size_t)b * dims_.nc0 * nx, p.G0, (size_t)dims_.nc0 * nx, "G0");
+      put(g0_.data() + (size_t)b * dims_.nc0, p.g0, (size_t)dims_.nc0, "g0");
+    }
+  }
+  void run_forward() const {
+    check(ab2_gar_forward(h_, nullptr));
+    const int N = dims_.horizon, B = dims_.batch;
+    xs_.resize((size_t)B * (N + 1) * dims_.nx);
+    us_.resize((size_t)B * N * dims_.nu);
+    vs_.resize((size_t)B * N * dims_.nc);
+    vsT_.resize((size_t)B * dims_.nct);
+    l0_.resize((size_t)B * dims_.nc0);
+    ls_.resize((size_t)B * N * dims_.nx);
+    auto get = [&](int what, std::vector<double> &v) {
+      if (!v.empty())
+        check(ab2_gar_get(h_, what, v.data(), AB2_HOST, nullptr));
+    };
+    get(AB2_OUT_XS, xs_);
+    get(AB2_OUT_US, us_);
+    get(AB2_OUT_VS, vs_);
+    get(AB2_OUT_VST, vsT_);
+    get(AB2_OUT_LBD0, l0_);
+    get(AB2_OUT_LBDAS, ls_);
+    check(ab2_gar_synchronize(h_, nullptr));
+  }
+  void scatter(int b, std::vector<VectorXs> &xs, std::vector<VectorXs> &us, std::vector<VectorXs> &vs,
+               std::vector<VectorXs> &lbdas) const {
+    const int N = dims_.horizon, nx = dims_.nx, nu = dims_.nu, nc = dims_.nc;
+    for (int t = 0; t <= N; ++t)
+      xs[t].assign(xs_.begin() + ((size_t)b * (N + 1) + t) * nx, xs_.begin() + ((size_t)b * (N + 1) + t + 1) * nx);
+    for (int t = 0; t < N; ++t) {
+      us[t].assign(us_.begin() + ((size_t)b * N + t) * nu, us_.begin() + ((size_t)b * N + t + 1) * nu);
+      vs[t].assign(vs_.begin() + ((size_t)b * N + t) * nc, vs_.begin() + ((size_t)b * N + t + 1) * nc);
+      lbdas[t + 1].assign(ls_.begin() + ((size_t)b * N + t) * nx, ls_.begin() + ((size_t)b * N + t + 1) * nx);
+    }
+    vs[N].assign(vsT_.begin() + (size_t)b * dims_.nct, vsT_.begin() + (size_t)(b + 1) * dims_.nct);
+    lbdas[0].assign(l0_.begin() + (size_t)b * dims_.nc0, l0_.begin() + (size_t)(b + 1) * dims_.nc0);
+  }
+
+  std::vector<const LqrProblem *> problems_;
+  ab2_gar_dims dims_{};
+  ab2_gar_solver *h_ = nullptr;
+  size_t srec_ = 0, trec_ = 0;
+  std::vector<double> stage_, term_, G0_, g0_;
+  std::vector<double> ff_, fb_, ffT_, fbT_;
+  mutable std::vector<double> xs_, us_, vs_, vsT_, l0_, ls_;
+};
+
+} // namespace gar
+} // namespace aligator_b200

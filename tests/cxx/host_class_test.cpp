@@ -1,0 +1,120 @@
+// C++ parity test of the host class (include/aligator_b200/riccati_solver.hpp) --
+// written like the reference's tests/gar/riccati.cpp: build a problem, construct the
+// solver from it, backward(mueq), forward(xs,us,vs,lbdas), check the KKT residual, and
+// compare K,k,Vxx with the CPU oracle.  Needs a GPU to run; compiling it is a CPU test.
+#include <cmath>
+#include <cstdio>
+#include <random>
+
+#include "../../include/aligator_b200/riccati_solver.hpp"
+#include "../../oracle/gar_oracle.hpp"
+
+namespace ab = aligator_b200::gar;
+namespace orc = gar_oracle;
+
+static orc::Problem to_oracle(const ab::LqrProblem &p) {
+  orc::Problem o;
+  for (const auto &k : p.stages) {
+    orc::Knot q(k.nx, k.nu, k.nc, k.nx2, 0);
+    q.Q = k.Q; q.S = k.S; q.R = k.R; q.q = k.q; q.r = k.r;
+    q.A = k.A; q.B = k.B; q.f = k.f; q.C = k.C; q.D = k.D; q.d = k.d;
+    o.stages.push_back(q);
+  }
+  o.nc0 = p.nc0();
+  o.G0 = p.G0;
+  o.g0 = p.g0;
+  return o;
+}
+
+static ab::LqrProblem random_problem(std::mt19937 &rng, unsigned nx, unsigned nu, unsigned nc, int N) {
+  std::normal_distribution<double> nrm;
+  std::uniform_real_distribution<double> uni(-1, 1);
+  std::vector<ab::LqrKnot> knots;
+  for (int t = 0; t <= N; ++t) {
+    const unsigned nut = t < N ? nu : 0, nct = t < N ? nc : 0;
+    ab::LqrKnot k(nx, nut, nct, nx);
+    const unsigned n = nx + nut;
+    std::vector<double> W((size_t)n * (n + 1));
+    for (auto &w : W) w = nrm(rng);
+    auto H = [&](unsigned i, unsigned j) {
+      double s = 0;
+      for (unsigned c = 0; c <= n; ++c) s += W[i + (size_t)c * n] * W[j + (size_t)c * n];
+      return s / std::max(nx, nut);
+    };
+    for (unsigned j = 0; j < nx; ++j)
+      for (unsigned i = 0; i < nx; ++i) k.Q[i + j * nx] = H(i, j);
+    for (unsigned j = 0; j < nut; ++j) {
+      for (unsigned i = 0; i < nx; ++i) k.S[i + j * nx] = H(i, nx + j);
+      for (unsigned i = 0; i < nut; ++i) k.R[i + j * nut] = H(nx + i, nx + j) * (i == j ? 1 + 1e-6 : 1);
+    }
+    for (unsigned j = 0; j < nx; ++j)
+      for (unsigned i = 0; i < nx; ++i) k.A[i + j * nx] = (i == j) + 0.1 * nrm(rng) / std::sqrt((double)nx);
+    for (auto &v : k.B) v = uni(rng);
+    for (auto &v : k.f) v = nrm(rng);
+    for (auto &v : k.q) v = uni(rng);
+    for (auto &v : k.r) v = uni(rng);
+    for (unsigned m = 0; m < nct && m < nut; ++m)
+      if (uni(rng) > 0) { k.D[m + m * nct] = 1.0; k.d[m] = uni(rng); }
+    knots.push_back(k);
+  }
+  ab::LqrProblem p(std::move(knots), nx);
+  for (unsigned i = 0; i < nx; ++i) { p.G0[i + i * nx] = -1.0; p.g0[i] = nrm(rng); }
+  return p;
+}
+
+static double rel_fro(const double *a, const double *b, size_t n) {
+  double num = 0, den = 0;
+  for (size_t i = 0; i < n; ++i) { num += (a[i] - b[i]) * (a[i] - b[i]); den += b[i] * b[i]; }
+  return den > 0 ? std::sqrt(num / den) : std::sqrt(num);
+}
+
+static int check_one(unsigned nx, unsigned nu, unsigned nc, int N, double mueq, unsigned seed) {
+  std::mt19937 rng(seed);
+  ab::LqrProblem prob = random_problem(rng, nx, nu, nc, N);
+  ab::CudaRiccatiSolver solver(prob);
+  if (!solver.backward(mueq)) return 1;
+  std::vector<ab::VectorXs> xs, us, vs, lbdas;
+  ab::lqrInitializeSolution(prob, xs, us, vs, lbdas);
+  if (xs.size() != (size_t)N + 1 || us.size() != (size_t)N || lbdas.size() != (size_t)N + 1) return 2;
+  if (!solver.forward(xs, us, vs, lbdas)) return 3;
+
+  orc::Problem op = to_oracle(prob);
+  orc::Solution sol = orc::lqrInitializeSolution(op);
+  sol.xs = xs; sol.us = us; sol.vs = vs; sol.lbdas = lbdas;
+  const orc::KktError e = orc::lqrComputeKktError(op, sol, mueq, nullptr);
+  std::printf("nx=%u nu=%u nc=%u N=%d: KKT dyn %.2e cstr %.2e dual %.2e\n", nx, nu, nc, N, e.dyn, e.cstr, e.dual);
+  if (!(e.max() <= 1e-9)) return 4; // tests/gar/riccati.cpp:84
+
+  orc::ProximalRiccatiSolver ref(op);
+  ref.backward(mueq);
+  double worst = 0;
+  for (int t = 0; t < N; ++t) {
+    auto fb = solver.getFeedback(t);
+    auto ff = solver.getFeedforward(t);
+    worst = std::max(worst, rel_fro(fb.data, ref.datas[t].fb.data(), (size_t)fb.rows * fb.cols));
+    worst = std::max(worst, rel_fro(ff.data, ref.datas[t].ff.data(), (size_t)ff.size));
+    auto V = solver.Vxx(t);
+    worst = std::max(worst, rel_fro(V.data(), ref.datas[t].vm.Vxx.data(), V.size()));
+  }
+  std::printf("   max rel-Frobenius (fb, ff, Vxx) vs oracle: %.2e\n", worst);
+  return worst <= 1e-10 ? 0 : 5;
+}
+
+int main() {
+  int rc = 0;
+  rc |= check_one(2, 2, 0, 8, 1e-14, 1);
+  rc |= check_one(6, 3, 0, 100, 1e-8, 2);
+  rc |= check_one(12, 6, 0, 100, 1e-11, 3);
+  rc |= check_one(4, 2, 2, 50, 1e-3, 4);
+  // error convention: unsupported dims throw like the reference's RuntimeError
+  try {
+    std::mt19937 rng(9);
+    ab::LqrProblem big = random_problem(rng, 40, 3, 0, 2);
+    ab::CudaRiccatiSolver s(big);
+    rc |= 64;
+  } catch (const aligator_b200::RuntimeError &e) {
+    std::printf("unsupported shape -> RuntimeError: %s\n", e.what());
+  }
+  std::printf(rc == 0 ? "ALL OK\n" : "FAILED rc=%d\n", rc);
+  return rc;
+}
