@@ -174,6 +174,7 @@ def run_reference(args, rank, world):
 
 
 def main():
+    global NX, NU, NC, NCT, HORIZON, BATCH, MUEQ, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -186,7 +187,6 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     args = ap.parse_args()
-    global NX, NU, NC, NCT, HORIZON, BATCH, MUEQ, WORKLOAD
     if args.config != "c2":
         NX, NU, NC, NCT, HORIZON, BATCH, MUEQ, WORKLOAD = CONFIGS[args.config]
         if args.batch == 4096:
