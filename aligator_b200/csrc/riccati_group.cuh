@@ -81,7 +81,7 @@ struct SweepParams {
 // ---------------------------------------------------------------------------
 // Compile-time shape of one kernel instantiation.
 // ---------------------------------------------------------------------------
-template <int NX_, int NU_, int NC_, int G_, bool DB_ = false> struct Cfg {
+template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true> struct Cfg {
   static constexpr int NX = NX_, NU = NU_, NC = NC_, G = G_;
   static constexpr bool DB = DB_;          // double-buffered knot records
   static constexpr int NCOL = NX + NU + 1; // columns of M = [A | B | f]
@@ -90,7 +90,7 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false> struct Cfg {
   static constexpr int NR = NU + NC + NX;  // rows of ff / fb
   static constexpr int FCOL = NX + NU;     // the lane that owns f / q,r / ff
   static constexpr bool EVEN = (NX % 2) == 0; // 16-byte aligned rows -> 128-bit LDS
-  static constexpr bool REGBK = NK <= 8;   // Bunch-Kaufman entirely in registers
+  static constexpr bool REGBK = RB_ && (NU_ + NC_ <= 8); // Bunch-Kaufman entirely in registers
   static constexpr int ev(int x) { return (x + 1) & ~1; }
   // stage record offsets (doubles) -- the reference's 11 buffers, concatenated
   static constexpr int OFF_A = 0;
@@ -148,6 +148,37 @@ AB2_D D2 lds2(const double *p) {
 #else
   return D2{p[0], p[1]};
 #endif
+}
+// 128-bit global load of two consecutive doubles (p 16-byte aligned).
+AB2_D D2 ldg2(const double *p) {
+#if defined(__CUDA_ARCH__)
+  const double2 v = *reinterpret_cast<const double2 *>(p);
+  return D2{v.x, v.y};
+#else
+  return D2{p[0], p[1]};
+#endif
+}
+AB2_D void prefetch_l2(const void *p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// v[0..N) = p[0..N)  (global memory; ALIGNED: p 16-byte aligned and N even)
+template <int N, bool ALIGNED> AB2_D void load_row(const double *p, double (&v)[N]) {
+  if constexpr (ALIGNED && (N % 2 == 0)) {
+    AB2_UNROLL
+    for (int k = 0; k < N; k += 2) {
+      const D2 a = ldg2(p + k);
+      v[k] = a.x;
+      v[k + 1 < N ? k + 1 : k] = a.y;
+    }
+  } else {
+    AB2_UNROLL
+    for (int k = 0; k < N; ++k)
+      v[k] = p[k];
+  }
 }
 // acc + sum_k row[k] * v[k]; `row` is read by the whole group at the same address
 // (broadcast).  ALIGNED: row is 16-byte aligned -> LDS.128.
@@ -778,10 +809,18 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           rhs0[(NU + m) * RS + jj] = colF ? -rec[C::OFF_DV + m] : -rec[C::OFF_C + lane * NC + m];
       }
       // state rows: Qhat[:,j] / Shat[:,c] / qhat stay in registers for step (E)
+      // With double-buffered records each lane parks its column in the slot it read
+      // H0[:,j] from (private to the lane) so it does not occupy registers during the
+      // factorisation; the single-buffer variant refills that slot early and keeps it
+      // in registers instead.
+      constexpr bool STASH = C::DB;
       double h[NX];
       AB2_UNROLL
-      for (int i = 0; i < NX; ++i)
+      for (int i = 0; i < NX; ++i) {
         h[i] = dot_bcast<NX, EV>(rec + i * NX, w, rec[base1 + i]);
+        if (STASH && (colA || colF)) // Q column j / q: read by this lane only
+          rec[base1 + i] = h[i];
+      }
       ctx.sync();
       if (!C::DB && t > 0) // part 1 of the record (Q..d) is consumed: fetch the next knot's
         ctx.issue_copy(1, rec + C::SPLIT, stage_b + (size_t)(t - 1) * C::SREC_PAD + C::SPLIT,
@@ -815,7 +854,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
         double ahat[NX];
         AB2_UNROLL
         for (int i = 0; i < NX; ++i)
-          ahat[i] = mcol[i];
+          ahat[i] = STASH ? rec[lane * NX + i] : mcol[i];
         AB2_UNROLL
         for (int c = 0; c < NU; ++c) {
           const double kc = kz[c];
@@ -855,6 +894,11 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       }
       // (E) cost-to-go: [Vxx vx] = [Qhat qhat] + [Shat C^T][K k; Z z]   (:270-277)
       if (colA || colF) {
+        if (STASH) {
+          AB2_UNROLL
+          for (int i = 0; i < NX; ++i)
+            h[i] = rec[base1 + i];
+        }
         // rhs0 still holds -Shat^T (rows 0..NU-1) and -C (rows NU..NK-1)
         AB2_UNROLL
         for (int r = 0; r < NU; ++r) {
@@ -986,17 +1030,68 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       p.lbd0[(size_t)inst * nc0 + m] = k0[NX + m];
     ctx.sync();
     constexpr int RPL = (NR + C::G - 1) / C::G; // gain rows per lane
-    for (int t = 0; t < N; ++t) {
-      const double *fbt = fb_b + (size_t)t * NR * NX;
-      const double *fft = ff_b + (size_t)t * NR;
+    constexpr bool EVF = C::EVEN;
+    constexpr int PF = 3; // knots of L2 prefetch distance
+    // Latency plan: every knot's gains/value are pulled into L2 PF knots ahead
+    // (prefetch.global.L2, no registers); the rows a lane needs for knot t+1 are loaded
+    // into the registers it has just finished using for knot t.
+    double gfb[RPL][NX], gff[RPL], gV[NX], gvx = 0.0;
+    auto prefetch_knot = [&](int t) {
+      if (t < N) {
+        const char *b0 = reinterpret_cast<const char *>(fb_b + (size_t)t * NR * NX);
+        for (int o = lane * 128; o < NR * NX * 8; o += C::G * 128)
+          prefetch_l2(b0 + o);
+        const char *b1 = reinterpret_cast<const char *>(Vxx_b + (size_t)(t + 1) * NX * NX);
+        for (int o = lane * 128; o < NX * NX * 8; o += C::G * 128)
+          prefetch_l2(b1 + o);
+        if (lane == 0) {
+          prefetch_l2(ff_b + (size_t)t * NR);
+          prefetch_l2(vx_b + (size_t)(t + 1) * NX);
+        }
+      }
+    };
+    auto fetch_gain = [&](int t) {
       AB2_UNROLL
       for (int q = 0; q < RPL; ++q) {
         const int r = lane + q * C::G;
         if (r < NR) {
-          double s = fft[r];
-          AB2_UNROLL
-          for (int c = 0; c < NX; ++c)
-            s += fbt[r * NX + c] * xc[c];
+          load_row<NX, EVF>(fb_b + ((size_t)t * NR + r) * NX, gfb[q]);
+          gff[q] = ff_b[(size_t)t * NR + r];
+        }
+      }
+    };
+    auto fetch_value = [&](int t1) { // row `lane` of Vxx_{t1} (symmetric for t1 >= 1: = column)
+      if (lane < NX) {
+        load_row<NX, EVF>(Vxx_b + ((size_t)t1 * NX + lane) * NX, gV);
+        gvx = vx_b[(size_t)t1 * NX + lane];
+      }
+    };
+    for (int t = 0; t < PF; ++t)
+      prefetch_knot(t);
+    if (N > 0) {
+      fetch_gain(0);
+      fetch_value(1);
+    }
+    for (int t = 0; t < N; ++t) {
+      prefetch_knot(t + PF);
+      AB2_UNROLL
+      for (int q = 0; q < RPL; ++q) {
+        const int r = lane + q * C::G;
+        if (r < NR) {
+          double s0 = gff[q], s1 = 0.0; // two chains halve the dependent-FMA latency
+          if (EVF) {
+            AB2_UNROLL
+            for (int c = 0; c < NX; c += 2) {
+              const D2 xx = lds2(xc + c);
+              s0 += gfb[q][c] * xx.x;
+              s1 += gfb[q][c + 1 < NX ? c + 1 : c] * xx.y;
+            }
+          } else {
+            AB2_UNROLL
+            for (int c = 0; c < NX; ++c)
+              s0 += gfb[q][c] * xc[c];
+          }
+          const double s = s0 + s1;
           if (r < NU)
             us_b[(size_t)t * NU + r] = s;
           else if (r < NK)
@@ -1007,15 +1102,27 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           }
         }
       }
+      if (t + 1 < N)
+        fetch_gain(t + 1); // into the registers just consumed
       ctx.sync();
       if (lane < NX) { // lbda_{t+1} = vx_{t+1} + Vxx_{t+1} x_{t+1}
-        const double *Vt = Vxx_b + (size_t)(t + 1) * NX * NX;
-        double s = vx_b[(size_t)(t + 1) * NX + lane];
-        AB2_UNROLL
-        for (int c = 0; c < NX; ++c)
-          s += Vt[lane + c * NX] * xnx[c];
-        lb_b[(size_t)t * NX + lane] = s;
+        double s0 = gvx, s1 = 0.0;
+        if (EVF) {
+          AB2_UNROLL
+          for (int c = 0; c < NX; c += 2) {
+            const D2 xx = lds2(xnx + c);
+            s0 += gV[c] * xx.x;
+            s1 += gV[c + 1 < NX ? c + 1 : c] * xx.y;
+          }
+        } else {
+          AB2_UNROLL
+          for (int c = 0; c < NX; ++c)
+            s0 += gV[c] * xnx[c];
+        }
+        lb_b[(size_t)t * NX + lane] = s0 + s1;
       }
+      if (t + 1 < N)
+        fetch_value(t + 2);
       double *tmp = xc;
       xc = xnx;
       xnx = tmp;

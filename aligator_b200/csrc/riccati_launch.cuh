@@ -86,8 +86,8 @@ template <int G, bool TMA> struct DevCtx {
 // The persistent sweep kernel: every group walks the whole horizon of its
 // instance (backward, initial stage, forward) inside one launch.
 // ---------------------------------------------------------------------------
-template <class C, int WARPS, int MINB, bool TMA>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
+template <class C, int WARPS, int MAXREG, bool TMA>
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
     riccati_sweep_kernel(const SweepParams p, const int group_doubles) {
   extern __shared__ __align__(16) double smem[];
   constexpr int IPW = 32 / C::G; // instances per warp
@@ -118,12 +118,12 @@ struct KernelEntry {
   cudaError_t (*launch)(const SweepParams &, int variant, const int gd[2], cudaStream_t, int *info);
 };
 
-template <class C, int WARPS, int MINB, bool TMA>
+template <class C, int WARPS, int MAXREG, bool TMA>
 inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int *info) {
   constexpr int IPW = 32 / C::G;
   const int groups = WARPS * IPW;
   const size_t smem = (size_t)groups * gd * sizeof(double) + (size_t)groups * 16;
-  auto kern = riccati_sweep_kernel<C, WARPS, MINB, TMA>;
+  auto kern = riccati_sweep_kernel<C, WARPS, MAXREG, TMA>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
     return e;
@@ -143,25 +143,29 @@ inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int
 }
 
 // Launch variants per shape (ab2_gar_tuning.variant):
-//   0: 2 warps/CTA x 7 CTAs/SM (14 warp-groups per SM, <= 144 registers), knot
-//      records double-buffered, one TMA bulk copy per knot          [default]
-//   1: 4 warps/CTA x 7 CTAs/SM (28 per SM: one wave at batch 4096 on 148 SMs,
-//      <= 72 registers), single record buffer refilled in two TMA parts
+//   0: 2 warps/CTA x >=7 CTAs/SM (<= 144 registers), knot records double-buffered,
+//      one TMA bulk copy per knot, Bunch-Kaufman in registers            [default]
+//   1: 4 warps/CTA x 7 CTAs/SM (28 warp-groups per SM: one wave at batch 4096 on
+//      148 SMs, <= 72 registers), single record buffer refilled in two TMA parts
 //   2: as 0 with cp.async (LDGSTS) staging instead of TMA
 //   3: as 1 with cp.async staging
+//   4: as 1 with the cooperative shared-memory Bunch-Kaufman (fewer registers)
+//   5: as 0 with the cooperative shared-memory Bunch-Kaufman
 template <int NX, int NU, int NC, int G>
 inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[2], cudaStream_t st, int *info) {
   using CS = Cfg<NX, NU, NC, G, false>;
   using CD = Cfg<NX, NU, NC, G, true>;
-#ifndef AB2_SINGLE_VARIANT
   if (variant == 1)
-    return launch_one<CS, 4, 7, true>(p, gd[0], st, info);
+    return launch_one<CS, 4, 72, true>(p, gd[0], st, info);
   if (variant == 2)
-    return launch_one<CD, 2, 7, false>(p, gd[1], st, info);
+    return launch_one<CD, 2, 144, false>(p, gd[1], st, info);
   if (variant == 3)
-    return launch_one<CS, 4, 7, false>(p, gd[0], st, info);
-#endif
-  return launch_one<CD, 2, 7, true>(p, gd[1], st, info);
+    return launch_one<CS, 4, 72, false>(p, gd[0], st, info);
+  if (variant == 4)
+    return launch_one<Cfg<NX, NU, NC, G, false, false>, 4, 72, true>(p, gd[0], st, info);
+  if (variant == 5)
+    return launch_one<Cfg<NX, NU, NC, G, true, false>, 2, 144, true>(p, gd[1], st, info);
+  return launch_one<CD, 2, 144, true>(p, gd[1], st, info);
 }
 template <int NX, int NU, int NC, int G> inline void group_doubles_cfg(int nc0, int gd[2]) {
   gd[0] = Cfg<NX, NU, NC, G, false>::group_doubles(nc0);
