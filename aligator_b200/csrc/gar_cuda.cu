@@ -214,8 +214,8 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
 int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t) {
   if (!s || !t)
     return fail(AB2_ERR_INVALID, "null argument");
-  if (t->variant < -1 || t->variant > 5)
-    return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..5");
+  if (t->variant < -1 || t->variant > 6)
+    return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..6");
   s->variant = t->variant < 0 ? 0 : t->variant;
   return AB2_OK;
 }

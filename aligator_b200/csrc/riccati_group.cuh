@@ -91,6 +91,8 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true> 
   static constexpr int FCOL = NX + NU;     // the lane that owns f / q,r / ff
   static constexpr bool EVEN = (NX % 2) == 0; // 16-byte aligned rows -> 128-bit LDS
   static constexpr bool REGBK = RB_ && (NU_ + NC_ <= 8); // Bunch-Kaufman entirely in registers
+  // unconstrained knots: branch-free register fast path, general algorithm as fallback
+  static constexpr bool FASTBK = RB_ && NC_ == 0 && NU_ <= 8;
   static constexpr int ev(int x) { return (x + 1) & ~1; }
   // stage record offsets (doubles) -- the reference's 11 buffers, concatenated
   static constexpr int OFF_A = 0;
@@ -409,6 +411,67 @@ template <int NK> struct SmemFactor { // factor left in shared memory by bk_fact
   AB2_D double sd(int k) const { return s[k]; }
   AB2_D int kind(int k) const { return kd[k]; }
   AB2_D int perm(int i) const { return pm[i]; }
+};
+
+// Fast path of the Bunch-Kaufman factorisation for the common case in which every
+// pivot test of bunch_kaufman_in_place_unblocked picks the 1x1 pivot without an
+// interchange (|a_kk| >= alpha * colmax, core/bunchkaufman.hpp:61; always-true in
+// practice for the SPD matrices Rhat = R + B^T V B of unconstrained knots).  Straight
+// line code, no branches: it performs exactly the arithmetic of the general algorithm
+// on that path and reports whether the assumption held; if it did not, the caller
+// discards this result and runs the general algorithm on the untouched matrix.
+template <int N> struct FastFactor {
+  double a[N][N]; // lower triangle in, L (strictly lower) out
+  double d[N];    // inverted pivots
+  AB2_D double L(int i, int c) const { return a[i][c]; }
+  AB2_D bool factor() {
+    const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
+    bool good = true;
+    AB2_UNROLL
+    for (int k = 0; k < N; ++k) {
+      const double akk = a[k][k];
+      const double abs_akk = fabs(akk);
+      double colmax = 0.0;
+      AB2_UNROLL
+      for (int i = k + 1; i < N; ++i)
+        colmax = fmax(colmax, fabs(a[i][k]));
+      good = good && (abs_akk >= colmax * alpha) && (fmax(abs_akk, colmax) != 0.0);
+      const double d11 = 1.0 / akk;
+      d[k] = d11;
+      AB2_UNROLL
+      for (int j = k + 1; j < N; ++j) {
+        const double d11xj = a[j][k] * d11;
+        AB2_UNROLL
+        for (int i = j; i < N; ++i)
+          a[i][j] -= d11xj * a[i][k];
+      }
+      AB2_UNROLL
+      for (int i = k + 1; i < N; ++i)
+        a[i][k] *= d11;
+    }
+    return good;
+  }
+  // solve with identity interchanges and 1x1 pivots (bunchkaufman.hpp:451-518 on that path)
+  AB2_D void solve(const double *rhs, const int stride, double (&x)[N]) const {
+    AB2_UNROLL
+    for (int i = 0; i < N; ++i)
+      x[i] = rhs[i * stride];
+    AB2_UNROLL
+    for (int c = 0; c < N; ++c) {
+      AB2_UNROLL
+      for (int i = c + 1; i < N; ++i)
+        x[i] -= a[i][c] * x[c];
+    }
+    AB2_UNROLL
+    for (int k = 0; k < N; ++k)
+      x[k] *= d[k];
+    AB2_UNROLL
+    for (int c = N - 1; c >= 0; --c) {
+      AB2_UNROLL
+      for (int i = c + 1; i < N; ++i)
+        x[c] -= a[i][c] * x[i];
+    }
+  }
 };
 
 // Bunch-Kaufman of an N x N matrix held in registers by EVERY lane of the group:
@@ -785,13 +848,16 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       }
       // control rows first: they go straight to the KKT matrix / right-hand sides
       // (:232-257) and never occupy registers afterwards
+      // colB lanes: Rhat[:,c] -> KKT column c (only r >= c is read); colA/colF lanes:
+      // -Shat^T[:,j] / -rhat -> right-hand-side column jj.  One predicated store, no branch.
+      double *const cdst = colB ? kkt + (lane - NX) * NK : rhs0 + jj;
+      const int cstride = colB ? 1 : RS;
+      const double csign = colB ? 1.0 : -1.0;
       AB2_UNROLL
       for (int r = 0; r < NU; ++r) {
         const double hr = dot_bcast<NX, EV>(rec + (NX + r) * NX, w, rec[base2 + r * stride2]);
-        if (colB)
-          kkt[r + (lane - NX) * NK] = hr; // Rhat[r][c]; only r >= c is read
-        else if (colA || colF)
-          rhs0[r * RS + jj] = -hr; // -Shat^T[:,j] / -rhat
+        if (active)
+          cdst[r * cstride] = csign * hr;
       }
       if (colB) {
         AB2_UNROLL
@@ -829,7 +895,26 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       double kz[NK];
       double *fbt = fb_b + (size_t)t * NR * NX;
       double *fft = ff_b + (size_t)t * NR;
-      if constexpr (C::REGBK) {
+      if constexpr (C::FASTBK) {
+        FastFactor<NK> F;
+        AB2_UNROLL
+        for (int c = 0; c < NK; ++c) {
+          AB2_UNROLL
+          for (int i = c; i < NK; ++i)
+            F.a[i][c] = kkt[i + c * NK];
+        }
+        if (F.factor()) { // uniform over the group: every lane factored the same matrix
+          if (colA || colF)
+            F.solve(rhs0 + jj, RS, kz);
+        } else { // an interchange / 2x2 pivot / singular column: general algorithm
+          if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind))
+            st |= ST_STAGE_FACTOR_FAILED;
+          if (colA || colF) {
+            const SmemFactor<NK> G{kkt, dd, sd, perm, kind};
+            bk_solve_column<NK>(G, rhs0 + jj, sol + jj, RS, kz);
+          }
+        }
+      } else if constexpr (C::REGBK) {
         RegFactor<NK> F;
         AB2_UNROLL
         for (int c = 0; c < NK; ++c) {
@@ -871,21 +956,15 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
               ahat[i] += rec[C::OFF_B + c * NX + i] * kc;
           }
         }
-        if (colA) {
-          AB2_UNROLL
-          for (int r = 0; r < NK; ++r)
-            fbt[r * NX + lane] = kz[r];
-          AB2_UNROLL
-          for (int i = 0; i < NX; ++i)
-            fbt[(NK + i) * NX + lane] = ahat[i];
-        } else {
-          AB2_UNROLL
-          for (int r = 0; r < NK; ++r)
-            fft[r] = kz[r];
-          AB2_UNROLL
-          for (int i = 0; i < NX; ++i)
-            fft[NK + i] = ahat[i];
-        }
+        // column `lane` of fb (stride NX) or the vector ff (stride 1): same code
+        double *const odst = colA ? fbt + lane : fft;
+        const int ostride = colA ? NX : 1;
+        AB2_UNROLL
+        for (int r = 0; r < NK; ++r)
+          odst[r * ostride] = kz[r];
+        AB2_UNROLL
+        for (int i = 0; i < NX; ++i)
+          odst[(NK + i) * ostride] = ahat[i];
       }
       if (!C::DB) {
         ctx.sync();
@@ -1031,23 +1110,19 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     ctx.sync();
     constexpr int RPL = (NR + C::G - 1) / C::G; // gain rows per lane
     constexpr bool EVF = C::EVEN;
-    constexpr int PF = 3; // knots of L2 prefetch distance
-    // Latency plan: every knot's gains/value are pulled into L2 PF knots ahead
-    // (prefetch.global.L2, no registers); the rows a lane needs for knot t+1 are loaded
-    // into the registers it has just finished using for knot t.
-    double gfb[RPL][NX], gff[RPL], gV[NX], gvx = 0.0;
+    constexpr int PF = 4; // knots of L2 prefetch distance
+    // Pass 1 -- the sequential part: x_{t+1} = a + Ahat x_t (and u, v, which read the same
+    // rows).  Gains are pulled into L2 PF knots ahead (prefetch.global.L2, no registers);
+    // the rows a lane needs for knot t+1 are loaded into the registers it has just
+    // finished using for knot t, so the load overlaps the shared-memory hand-over of x.
+    double gfb[RPL][NX], gff[RPL];
     auto prefetch_knot = [&](int t) {
       if (t < N) {
         const char *b0 = reinterpret_cast<const char *>(fb_b + (size_t)t * NR * NX);
         for (int o = lane * 128; o < NR * NX * 8; o += C::G * 128)
           prefetch_l2(b0 + o);
-        const char *b1 = reinterpret_cast<const char *>(Vxx_b + (size_t)(t + 1) * NX * NX);
-        for (int o = lane * 128; o < NX * NX * 8; o += C::G * 128)
-          prefetch_l2(b1 + o);
-        if (lane == 0) {
+        if (lane == 0)
           prefetch_l2(ff_b + (size_t)t * NR);
-          prefetch_l2(vx_b + (size_t)(t + 1) * NX);
-        }
       }
     };
     auto fetch_gain = [&](int t) {
@@ -1060,18 +1135,10 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
         }
       }
     };
-    auto fetch_value = [&](int t1) { // row `lane` of Vxx_{t1} (symmetric for t1 >= 1: = column)
-      if (lane < NX) {
-        load_row<NX, EVF>(Vxx_b + ((size_t)t1 * NX + lane) * NX, gV);
-        gvx = vx_b[(size_t)t1 * NX + lane];
-      }
-    };
     for (int t = 0; t < PF; ++t)
       prefetch_knot(t);
-    if (N > 0) {
+    if (N > 0)
       fetch_gain(0);
-      fetch_value(1);
-    }
     for (int t = 0; t < N; ++t) {
       prefetch_knot(t + PF);
       AB2_UNROLL
@@ -1104,28 +1171,38 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       }
       if (t + 1 < N)
         fetch_gain(t + 1); // into the registers just consumed
-      ctx.sync();
-      if (lane < NX) { // lbda_{t+1} = vx_{t+1} + Vxx_{t+1} x_{t+1}
-        double s0 = gvx, s1 = 0.0;
-        if (EVF) {
-          AB2_UNROLL
-          for (int c = 0; c < NX; c += 2) {
-            const D2 xx = lds2(xnx + c);
-            s0 += gV[c] * xx.x;
-            s1 += gV[c + 1 < NX ? c + 1 : c] * xx.y;
-          }
-        } else {
-          AB2_UNROLL
-          for (int c = 0; c < NX; ++c)
-            s0 += gV[c] * xnx[c];
-        }
-        lb_b[(size_t)t * NX + lane] = s0 + s1;
-      }
-      if (t + 1 < N)
-        fetch_value(t + 2);
       double *tmp = xc;
       xc = xnx;
       xnx = tmp;
+      ctx.sync(); // x_{t+1} visible; every lane is done reading x_t
+    }
+    // Pass 2 -- the parallel part: lbda_{t+1} = vx_{t+1} + Vxx_{t+1} x_{t+1} has no
+    // dependence between knots, so G/NX knots are evaluated per iteration and the loop
+    // is unrolled: many independent loads in flight, no synchronisation.
+    {
+      constexpr int KPI = (C::G / NX) > 0 ? (C::G / NX) : 1; // knots per iteration
+      const int sub = lane / NX, i = lane % NX;
+      if (sub < KPI) {
+#if defined(__CUDACC__)
+#pragma unroll 2
+#endif
+        for (int t = sub; t < N; t += KPI) {
+          const double *Vrow = Vxx_b + ((size_t)(t + 1) * NX + i) * NX; // row i (symmetric, t+1 >= 1)
+          const double *xn = xs_b + (size_t)(t + 1) * NX;
+          double vrow[NX], xr[NX];
+          load_row<NX, EVF>(Vrow, vrow);
+          load_row<NX, EVF>(xn, xr);
+          double s0 = vx_b[(size_t)(t + 1) * NX + i], s1 = 0.0;
+          AB2_UNROLL
+          for (int c = 0; c + 1 < NX; c += 2) {
+            s0 += vrow[c] * xr[c];
+            s1 += vrow[c + 1] * xr[c + 1];
+          }
+          if (NX % 2)
+            s0 += vrow[NX - 1] * xr[NX - 1];
+          lb_b[(size_t)t * NX + i] = s0 + s1;
+        }
+      }
       ctx.sync();
     }
     // terminal multipliers v_N = z + Z x_N

@@ -165,6 +165,8 @@ inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[2]
     return launch_one<Cfg<NX, NU, NC, G, false, false>, 4, 72, true>(p, gd[0], st, info);
   if (variant == 5)
     return launch_one<Cfg<NX, NU, NC, G, true, false>, 2, 144, true>(p, gd[1], st, info);
+  if (variant == 6) // as 0 capped at 128 registers (8 CTAs/SM)
+    return launch_one<CD, 2, 128, true>(p, gd[1], st, info);
   return launch_one<CD, 2, 144, true>(p, gd[1], st, info);
 }
 template <int NX, int NU, int NC, int G> inline void group_doubles_cfg(int nc0, int gd[2]) {

@@ -188,3 +188,19 @@ def rel_fro(a, b):
     den = np.linalg.norm(b.ravel())
     num = np.linalg.norm((a - b).ravel())
     return num / den if den > 0 else num
+
+
+def make_pivoting(probs):
+    """Force Bunch-Kaufman interchanges on UNconstrained knots: R = diag([[1,1.8],[1.8,4]], I)
+    (SPD, but |a_00| < alpha*colmax, and the row test then picks an interchange with row 1)
+    and weak B, so Rhat = R + B^T V B keeps the pattern.  Exercises the general-algorithm
+    fallback of the CUDA fast path."""
+    for p in probs:
+        for k in p.stages[:-1]:
+            nu = k.nu
+            R = np.eye(nu)
+            R[:2, :2] = [[1.0, 1.8], [1.8, 4.0]]
+            k.R[:] = R
+            k.B *= 0.02
+            k.S *= 0.0
+    return probs

@@ -104,7 +104,7 @@ def test_cuda_matches_oracle(gar, shape):
     assert got["launches"] == 1  # one persistent launch per sweep
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("shape", [(12, 6, 0, 0, 40, 19, 1e-8), (4, 2, 2, 0, 40, 70, 1e-3),
                                    (6, 3, 0, 0, 30, 9, 1e-8)])
 def test_all_launch_variants(gar, shape, variant):
@@ -292,3 +292,15 @@ def test_full_size_properties_config2(gar):
     ref = bo.get()
     assert gen.rel_fro(FB[idx], ref["fb"]) <= TOL and gen.rel_fro(V[idx], ref["Vxx"]) <= TOL
     assert gen.rel_fro(X[idx], ref["xs"]) <= TOL
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("shape", [(6, 3, 0, 0, 12, 9), (12, 6, 0, 0, 30, 17), (2, 2, 0, 0, 6, 5)])
+def test_unconstrained_knots_that_need_interchanges(gar, shape, variant):
+    """nc = 0 but Rhat needs Bunch-Kaufman interchanges: the branch-free register fast
+    path must detect it and fall back to the general algorithm."""
+    nx, nu, nc, nct, N, B = shape
+    probs = gen.make_pivoting(gen.generate_batch(31, B, N, nx, nu, nc, nct))
+    got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, 1e-8, variant=variant)
+    ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, 1e-8)
+    compare(got, ref, nu, nc, N, 1e-8, tol=1e-9)

@@ -66,8 +66,11 @@ def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0):
     return out
 
 
-def check_against_oracle(nx, nu, nc, nct, N, B, mueq, seed, tol=1e-10, style="conditioned", db=0):
+def check_against_oracle(nx, nu, nc, nct, N, B, mueq, seed, tol=1e-10, style="conditioned", db=0,
+                         pivoting=False):
     probs = gen.generate_batch(seed, B, N, nx, nu, nc, nct, style=style)
+    if pivoting:
+        gen.make_pivoting(probs)
     got = run_emulated(nx, nu, nc, nct, N, probs, mueq, db)
     assert np.all(got["status"] == 0)
     stage, term, G0, g0 = gen.pack_problems(probs)
@@ -132,3 +135,20 @@ def test_emulated_kernel_horizon_zero_and_one():
 def test_emulated_kernel_reference_style_unstable_A():
     """A ~ U[-1,1] (reference generator style): still within 1e-10 for nc = 0."""
     check_against_oracle(6, 3, 0, 0, 40, B=2, mueq=1e-8, seed=3, style="reference")
+
+
+@pytest.mark.parametrize("db", [0, 1])
+@pytest.mark.parametrize("shape", [(6, 3, 0, 0, 12), (12, 6, 0, 0, 8), (2, 2, 0, 0, 6)])
+def test_emulated_kernel_unconstrained_with_interchanges(shape, db):
+    """Rhat needs pivoting although nc = 0: the branch-free fast path must detect it and
+    fall back to the general Bunch-Kaufman (same results as the oracle)."""
+    nx, nu, nc, nct, N = shape
+    probs = gen.make_pivoting(gen.generate_batch(31, 2, N, nx, nu, nc, nct))
+    # the oracle really does pivot on these problems
+    op = orc.OracleProblem(probs[0])
+    ref = orc.ProximalRiccatiSolver(op)
+    ref.backward(1e-8)
+    piv = np.concatenate([ref.factor(t)["bk_piv"] for t in range(N)])
+    ident = np.concatenate([np.arange(nu) for _ in range(N)])
+    assert np.any(piv != ident)
+    check_against_oracle(nx, nu, nc, nct, N, B=2, mueq=1e-8, seed=31, db=db, pivoting=True, tol=1e-9)
