@@ -84,7 +84,7 @@ struct ab2_gar_solver {
   bool have_problem = false, have_backward = false;
   long launches = 0;
   int variant = 0;
-  int group_doubles[2] = {0, 0};
+  int group_doubles[3] = {0, 0, 0};
 };
 
 static size_t stage_total(const ab2_gar_solver *s) {
@@ -214,8 +214,8 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
 int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t) {
   if (!s || !t)
     return fail(AB2_ERR_INVALID, "null argument");
-  if (t->variant < -1 || t->variant > 6)
-    return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..6");
+  if (t->variant < -1 || t->variant > 8)
+    return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..8");
   s->variant = t->variant < 0 ? 0 : t->variant;
   return AB2_OK;
 }

@@ -81,7 +81,7 @@ struct SweepParams {
 // ---------------------------------------------------------------------------
 // Compile-time shape of one kernel instantiation.
 // ---------------------------------------------------------------------------
-template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true> struct Cfg {
+template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, bool MMA_ = false> struct Cfg {
   static constexpr int NX = NX_, NU = NU_, NC = NC_, G = G_;
   static constexpr bool DB = DB_;          // double-buffered knot records
   static constexpr int NCOL = NX + NU + 1; // columns of M = [A | B | f]
@@ -94,6 +94,29 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true> 
   // unconstrained knots: branch-free register fast path, general algorithm as fallback
   static constexpr bool FASTBK = RB_ && NC_ == 0 && NU_ <= 8;
   static constexpr int ev(int x) { return (x + 1) & ~1; }
+  // ---- tensor-core (DMMA m8n8k4) formulation of the stage step ----
+  // logical column order [A | f | B] (state, affine, control); tiles of 8 (rows/cols)
+  // and 4 (contraction).
+  static constexpr bool MMA = MMA_;
+  static constexpr int MTX = (NX + 7) / 8;      // m-tiles over state rows
+  static constexpr int KT = (NX + 3) / 4;       // k-tiles over the state dimension
+  static constexpr int NJ = NX + 1 + NU;        // logical columns
+  static constexpr int NT = (NJ + 7) / 8;       // tiles over logical rows/columns of H
+  static constexpr int NT2 = (NX + 1 + 7) / 8;  // tiles over [state | affine] columns
+  static constexpr int KT2 = (NU + NC + 3) / 4; // k-tiles over the KKT dimension
+  // smallest stride >= n that is 4 or 12 mod 16 (conflict-free 64-bit fragment loads)
+  static constexpr int fstride(int n) {
+    int s = n;
+    while (s % 16 != 4 && s % 16 != 12)
+      ++s;
+    return s;
+  }
+  static constexpr int VS = MMA ? fstride(4 * KT) : NX;   // row stride of V' in smem
+  static constexpr int VROWS = MMA ? 8 * MTX : NX;
+  static constexpr int SW = MMA ? ((8 * NT + 15) / 16 * 16 + 8) : 0; // W row stride (== 8 mod 16)
+  static constexpr int WROWS = MMA ? 4 * KT : 0;
+  static constexpr int SX = MMA ? fstride(8 * NT2) : 0;  // row stride of X / KK
+  static constexpr int XROWS = MMA ? 4 * KT2 : 0;
   // stage record offsets (doubles) -- the reference's 11 buffers, concatenated
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + NX * NX;
@@ -114,7 +137,7 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true> 
   // shared-memory layout of one group (doubles); every region starts 16-byte aligned
   static constexpr int S_REC = 0;
   static constexpr int S_VN = S_REC + (DB ? 2 : 1) * SREC_PAD; // V' (symmetric, full)
-  static constexpr int S_VXN = S_VN + ev(NX * NX);             // vx'
+  static constexpr int S_VXN = S_VN + ev(VROWS * VS);          // vx'
   static constexpr int S_KKT = S_VXN + ev(NX);                 // NK*NK column-major
   static constexpr int S_RHS = S_KKT + ev(NK * NK);            // NK x RS, unsolved rhs
   static constexpr int S_SOL = S_RHS + NK * RS;
@@ -122,7 +145,42 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true> 
   static constexpr int S_SD = S_DD + ev(NK);
   static constexpr int S_X = S_SD + ev(NK);    // forward state x_t (NX) + x_{t+1} (NX)
   static constexpr int S_INT = S_X + 2 * ev(NX); // perm[NK], kind[NK] (ints)
-  static constexpr int S_STAGE_END = S_INT + NK + 1;
+  static constexpr int S_WSM = S_INT + ev(NK + 1);       // MMA: W = V' M, WROWS x SW
+  static constexpr int S_XM = S_WSM + ev(WROWS * SW);    // MMA: control rows of H, XROWS x SX
+  static constexpr int S_KK = S_XM + ev(XROWS * SX);     // MMA: [K k; Z z], XROWS x SX
+  static constexpr int S_STAGE_END = S_KK + ev(XROWS * SX);
+  static_assert(!MMA || (DB_ && G_ == 32 && NC_ == 0 && (NX_ % 2 == 0)),
+                "the tensor-core step needs double-buffered records, a full warp, nc = 0, even nx");
+
+  // rec offset of logical column jp of [A | f | B] (padding columns alias column 0)
+  static AB2_HD int col_offset(int jp) {
+    if (jp < NX)
+      return jp * NX;
+    if (jp == NX)
+      return OFF_F;
+    if (jp <= NX + NU)
+      return OFF_B + (jp - NX - 1) * NX;
+    return 0;
+  }
+  // rec offset of H0[ip][jp] in logical order, H0 = [[Q q S],[.. 0 ..],[S^T r R]]; -1 = zero
+  static AB2_HD int h0_offset(int ip, int jp) {
+    const int ti = ip < NX ? 0 : (ip == NX ? 1 : (ip <= NX + NU ? 2 : 3));
+    const int tj = jp < NX ? 0 : (jp == NX ? 1 : (jp <= NX + NU ? 2 : 3));
+    const int ci = ip - NX - 1, cj = jp - NX - 1;
+    if (ti == 0 && tj == 0)
+      return OFF_Q + jp * NX + ip;
+    if (ti == 0 && tj == 2)
+      return OFF_S + cj * NX + ip;
+    if (ti == 2 && tj == 0)
+      return OFF_S + ci * NX + jp;
+    if (ti == 2 && tj == 2)
+      return OFF_R + cj * NU + ci;
+    if (ti == 0 && tj == 1)
+      return OFF_QV + ip;
+    if (ti == 2 && tj == 1)
+      return OFF_RV + ci;
+    return -1;
+  }
 
   static_assert(NU >= 1, "stage knots need nu >= 1");
   static_assert(NCOL <= G, "lane-per-column mapping needs nx+nu+1 <= G");
@@ -690,6 +748,298 @@ AB2_D void bk_solve_vec_group(Ctx &ctx, const double *a, const int lda, const in
   ctx.sync();
 }
 
+
+// 128-bit shared-memory store of two consecutive doubles (p 16-byte aligned).
+AB2_D void sts2(double *p, double x, double y) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<double2 *>(p) = make_double2(x, y);
+#else
+  p[0] = x;
+  p[1] = y;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// Stage knots N-1..0 on the FP64 tensor cores (mma.sync m8n8k4, SASS DMMA).
+//
+// Same mathematics as the lane-per-column loop below (riccati-kernel.hxx:210-277);
+// the four dense products are tiled 8x8x4 and issued as DMMAs, whose operands live
+// in registers: shared memory is touched once per FRAGMENT instead of once per FMA
+// (the lane-per-column form needs one broadcast shared-memory operand per DFMA and
+// saturates the LSU pipe; measured DMMA throughput on B200 is 4x DFMA's).
+// Logical column order [A | f | B]; with lane = 4 g + q:
+//   A fragment (8x4):  lane holds a[g][q]          B fragment (4x8): lane holds b[q][g]
+//   C/D fragment (8x8): lane holds d[g][2q], d[g][2q+1]
+//  (1) W  = V' M                MTX x NT tiles, KT k-steps   (A: V' from smem, B: M from rec)
+//  (2) H  = H0 + M^T W          NT  x NT tiles, KT k-steps   (A: the SAME M fragments, B: W via smem)
+//  (3) control rows of H -> X (right-hand sides) and the KKT matrix; Bunch-Kaufman + solves
+//  (4) [Ahat a] = [A f] + B KK  MTX x NT2 tiles, KT2 k-steps (A: B from rec, B: KK via smem)
+//  (5) [Vxx vx] = [Qhat qhat] + X^T KK            same shapes (A: X from smem, B: same KK)
+// ---------------------------------------------------------------------------
+template <class C, class Ctx>
+AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ sm, int &st,
+                          const double *stage_b, double *ff_b, double *fb_b, double *Vxx_b,
+                          double *vx_b) {
+  constexpr int NX = C::NX, NU = C::NU, NK = C::NK, NR = C::NR;
+  constexpr int MTX = C::MTX, KT = C::KT, NT = C::NT, NT2 = C::NT2, KT2 = C::KT2;
+  constexpr int VS = C::VS, SW = C::SW, SX = C::SX;
+  const int lane = ctx.lane;
+  const int g = lane >> 2, q = lane & 3;
+  const int N = p.N;
+  double *Vn = sm + C::S_VN;
+  double *vxn = sm + C::S_VXN;
+  double *kkt = sm + C::S_KKT;
+  double *dd = sm + C::S_DD;
+  double *sd = sm + C::S_SD;
+  int *perm = reinterpret_cast<int *>(sm + C::S_INT);
+  int *kind = perm + NK;
+  double *Wsm = sm + C::S_WSM;
+  double *X = sm + C::S_XM;
+  double *KKs = sm + C::S_KK;
+
+  // per-lane constants: record offsets of the logical columns 8t+g, and of H0's entries
+  int moff[NT];
+  AB2_UNROLL
+  for (int t = 0; t < NT; ++t)
+    moff[t] = C::col_offset(8 * t + g);
+  int h0o[NT][NT][2];
+  AB2_UNROLL
+  for (int mt = 0; mt < NT; ++mt) {
+    AB2_UNROLL
+    for (int nt = 0; nt < NT; ++nt) {
+      AB2_UNROLL
+      for (int e = 0; e < 2; ++e)
+        h0o[mt][nt][e] = C::h0_offset(8 * mt + g, 8 * nt + 2 * q + e);
+    }
+  }
+  // zero the padding of the staging matrices once (rows/columns never written later)
+  for (int i = lane; i < C::WROWS * SW; i += C::G)
+    Wsm[i] = 0.0;
+  for (int i = lane; i < C::XROWS * SX; i += C::G) {
+    X[i] = 0.0;
+    KKs[i] = 0.0;
+  }
+  ctx.sync();
+
+  const bool colS = lane <= NX; // this lane solves right-hand-side column `lane` ([K | k])
+  int cur = 0;
+  for (int t = N - 1; t >= 0; --t) {
+    ctx.wait_copy(cur);
+    double *rec = sm + C::S_REC + cur * C::SREC_PAD;
+    if (t > 0) // stream the next knot into the other buffer during this step
+      ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::SREC_PAD,
+                     stage_b + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
+    cur ^= 1;
+
+    // fragments of M = [A | f | B]: B-operand of (1) and A-operand (M^T) of (2)
+    double Mf[NT][KT];
+    AB2_UNROLL
+    for (int tt = 0; tt < NT; ++tt) {
+      AB2_UNROLL
+      for (int kt = 0; kt < KT; ++kt)
+        Mf[tt][kt] = rec[moff[tt] + 4 * kt + q];
+    }
+    // (1) W = V' M   (+ vx' on the affine column: vplus = vx' + V' f, :217-218)
+    {
+      double W[MTX][NT][2];
+      AB2_UNROLL
+      for (int mt = 0; mt < MTX; ++mt) {
+        AB2_UNROLL
+        for (int nt = 0; nt < NT; ++nt) {
+          W[mt][nt][0] = 0.0;
+          W[mt][nt][1] = 0.0;
+        }
+      }
+      AB2_UNROLL
+      for (int mt = 0; mt < MTX; ++mt) {
+        AB2_UNROLL
+        for (int kt = 0; kt < KT; ++kt) {
+          const double va = Vn[(8 * mt + g) * VS + 4 * kt + q];
+          AB2_UNROLL
+          for (int nt = 0; nt < NT; ++nt)
+            ctx.mma(W[mt][nt], va, Mf[nt][kt]);
+        }
+      }
+      AB2_UNROLL
+      for (int mt = 0; mt < MTX; ++mt) {
+        const int i = 8 * mt + g;
+        if (i < NX) {
+          AB2_UNROLL
+          for (int nt = 0; nt < NT; ++nt) {
+            AB2_UNROLL
+            for (int e = 0; e < 2; ++e)
+              if (8 * nt + 2 * q + e == NX)
+                W[mt][nt][e] += vxn[i];
+            sts2(Wsm + i * SW + 8 * nt + 2 * q, W[mt][nt][0], W[mt][nt][1]);
+          }
+        }
+      }
+    }
+    ctx.sync();
+    // (2) H = H0 + M^T W
+    double H[NT][NT][2];
+    AB2_UNROLL
+    for (int mt = 0; mt < NT; ++mt) {
+      AB2_UNROLL
+      for (int nt = 0; nt < NT; ++nt) {
+        AB2_UNROLL
+        for (int e = 0; e < 2; ++e) {
+          const int o = h0o[mt][nt][e];
+          H[mt][nt][e] = (o >= 0) ? rec[o >= 0 ? o : 0] : 0.0;
+        }
+      }
+    }
+    AB2_UNROLL
+    for (int kt = 0; kt < KT; ++kt) {
+      AB2_UNROLL
+      for (int nt = 0; nt < NT; ++nt) {
+        const double wb = Wsm[(4 * kt + q) * SW + 8 * nt + g];
+        AB2_UNROLL
+        for (int mt = 0; mt < NT; ++mt)
+          ctx.mma(H[mt][nt], Mf[mt][kt], wb);
+      }
+    }
+    // (3) control rows of H: [Shat^T | rhat] -> X, Rhat -> KKT matrix (:232-257)
+    AB2_UNROLL
+    for (int mt = 0; mt < NT; ++mt) {
+      const int c = 8 * mt + g - NX - 1;
+      if (c >= 0 && c < NU) {
+        AB2_UNROLL
+        for (int nt = 0; nt < NT; ++nt) {
+          AB2_UNROLL
+          for (int e = 0; e < 2; ++e) {
+            const int jp = 8 * nt + 2 * q + e;
+            if (jp <= NX)
+              X[c * SX + jp] = H[mt][nt][e];
+            else if (jp - NX - 1 < NU)
+              kkt[c + (jp - NX - 1) * NK] = H[mt][nt][e]; // Rhat[c][c2]
+          }
+        }
+      }
+    }
+    ctx.sync();
+    double *fbt = fb_b + (size_t)t * NR * NX;
+    double *fft = ff_b + (size_t)t * NR;
+    {
+      double kz[NK];
+      FastFactor<NK> F;
+      AB2_UNROLL
+      for (int c = 0; c < NK; ++c) {
+        AB2_UNROLL
+        for (int i = c; i < NK; ++i)
+          F.a[i][c] = kkt[i + c * NK];
+      }
+      if (F.factor()) { // uniform over the warp
+        if (colS)
+          F.solve(X + lane, SX, kz);
+      } else { // an interchange / 2x2 pivot / singular column: general algorithm
+        if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind))
+          st |= ST_STAGE_FACTOR_FAILED;
+        if (colS) {
+          const SmemFactor<NK> G{kkt, dd, sd, perm, kind};
+          bk_solve_column<NK>(G, X + lane, KKs + lane, SX, kz); // KKs doubles as scratch
+        }
+      }
+      if (colS) { // the right-hand side is -X: negate the solution; outputs K / k
+        double *const odst = (lane < NX) ? fbt + lane : fft;
+        const int ostride = (lane < NX) ? NX : 1;
+        AB2_UNROLL
+        for (int c = 0; c < NK; ++c) {
+          const double v = -kz[c];
+          KKs[c * SX + lane] = v;
+          odst[c * ostride] = v;
+        }
+      }
+    }
+    ctx.sync();
+    // fragments of KK = [K k] (rows >= NK are zero)
+    double KKf[KT2][NT2];
+    AB2_UNROLL
+    for (int k2 = 0; k2 < KT2; ++k2) {
+      AB2_UNROLL
+      for (int nt = 0; nt < NT2; ++nt)
+        KKf[k2][nt] = KKs[(4 * k2 + q) * SX + 8 * nt + g];
+    }
+    // (4) [Ahat a] = [A f] + B KK   (:266-267)
+    {
+      double EA[MTX][NT2][2];
+      AB2_UNROLL
+      for (int mt = 0; mt < MTX; ++mt) {
+        const int i = 8 * mt + g;
+        AB2_UNROLL
+        for (int nt = 0; nt < NT2; ++nt) {
+          AB2_UNROLL
+          for (int e = 0; e < 2; ++e) {
+            const int jj = 8 * nt + 2 * q + e;
+            EA[mt][nt][e] = (i < NX && jj <= NX) ? rec[C::col_offset(jj <= NX ? jj : 0) + (i < NX ? i : 0)] : 0.0;
+          }
+        }
+        AB2_UNROLL
+        for (int k2 = 0; k2 < KT2; ++k2) {
+          const int c = 4 * k2 + q;
+          const double bf = (c < NU && i < NX) ? rec[C::OFF_B + (c < NU ? c : 0) * NX + (i < NX ? i : 0)] : 0.0;
+          AB2_UNROLL
+          for (int nt = 0; nt < NT2; ++nt)
+            ctx.mma(EA[mt][nt], bf, KKf[k2][nt]);
+        }
+        if (i < NX) {
+          AB2_UNROLL
+          for (int nt = 0; nt < NT2; ++nt) {
+            AB2_UNROLL
+            for (int e = 0; e < 2; ++e) {
+              const int jj = 8 * nt + 2 * q + e;
+              if (jj < NX)
+                fbt[(NK + i) * NX + jj] = EA[mt][nt][e];
+              else if (jj == NX)
+                fft[NK + i] = EA[mt][nt][e];
+            }
+          }
+        }
+      }
+    }
+    // (5) [Vxx vx] = [Qhat qhat] + Shat KK, with Shat[i][c] = X[c][i]   (:270-277)
+    AB2_UNROLL
+    for (int mt = 0; mt < MTX; ++mt) {
+      const int i = 8 * mt + g;
+      AB2_UNROLL
+      for (int k2 = 0; k2 < KT2; ++k2) {
+        const double xf = X[(4 * k2 + q) * SX + i];
+        AB2_UNROLL
+        for (int nt = 0; nt < NT2; ++nt)
+          ctx.mma(H[mt][nt], xf, KKf[k2][nt]);
+      }
+      if (i < NX) {
+        AB2_UNROLL
+        for (int nt = 0; nt < NT2; ++nt) {
+          AB2_UNROLL
+          for (int e = 0; e < 2; ++e) {
+            const int jj = 8 * nt + 2 * q + e;
+            const double v = H[mt][nt][e];
+            if (jj < NX) {
+              if (t == 0)
+                Vxx_b[i + jj * NX] = v; // datas[0].Vxx is left unsymmetrised (A1)
+              if (i >= jj) {            // V' = lower triangle mirrored (:216 of the next step)
+                Vn[i * VS + jj] = v;
+                Vn[jj * VS + i] = v;
+              }
+            } else if (jj == NX) {
+              vx_b[(size_t)t * NX + i] = v;
+              vxn[i] = v;
+            }
+          }
+        }
+      }
+    }
+    ctx.sync();
+    if (t > 0 && lane < NX) { // symmetric Vxx_t, as the next step of the reference leaves it
+      double *Vt = Vxx_b + (size_t)t * NX * NX;
+      AB2_UNROLL
+      for (int i = 0; i < NX; ++i)
+        Vt[i + lane * NX] = Vn[lane * VS + i];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // The sweep of one instance by one group.
 // ---------------------------------------------------------------------------
@@ -740,6 +1090,11 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
         ctx.issue_copy(1, rec + C::SPLIT, src + C::SPLIT, C::SREC_PAD - C::SPLIT);
       }
     }
+    if constexpr (C::MMA) { // padded rows/columns of V' must hold zeros (fragment loads read them)
+      for (int i = lane; i < C::VROWS * C::VS; i += C::G)
+        Vn[i] = 0.0;
+      ctx.sync();
+    }
     // ---------------- terminal knot (nu = 0): riccati-kernel.hxx:146-149,175-183
     {
       const double *tr = p.term + (size_t)inst * C::term_rec(nct);
@@ -776,8 +1131,8 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           } else {
             VN[i + lane * NX] = s; // as computed; re-written symmetric below when N > 0
             if (i >= lane) {       // V' for the next step = lower triangle mirrored (:216)
-              Vn[i * NX + lane] = s;
-              Vn[lane * NX + i] = s;
+              Vn[i * C::VS + lane] = s;
+              Vn[lane * C::VS + i] = s;
             }
           }
         }
@@ -786,11 +1141,14 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       if (colA && N > 0) { // step N-1 of the reference symmetrises datas[N].Vxx in place (A1)
         AB2_UNROLL
         for (int i = 0; i < NX; ++i)
-          VN[i + lane * NX] = Vn[lane * NX + i];
+          VN[i + lane * NX] = Vn[lane * C::VS + i];
       }
     }
 
     // ---------------- stage knots N-1 .. 0: riccati-kernel.hxx:210-277
+    if constexpr (C::MMA) {
+      stage_loop_mma<C>(ctx, p, sm, st, stage_b, ff_b, fb_b, Vxx_b, vx_b);
+    } else {
     constexpr int RS = C::RS;
     constexpr bool EV = C::EVEN;
     int cur = 0; // record buffer in use (DB)
@@ -824,7 +1182,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       double w[NX];
       AB2_UNROLL
       for (int i = 0; i < NX; ++i)
-        w[i] = dot_bcast<NX, EV>(Vn + i * NX, mcol, 0.0);
+        w[i] = dot_bcast<NX, EV>(Vn + i * C::VS, mcol, 0.0);
       if (colF) {
         AB2_UNROLL
         for (int i = 0; i < NX; ++i)
@@ -1021,8 +1379,8 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           AB2_UNROLL
           for (int i = 0; i < NX; ++i)
             if (i >= lane) { // V' = lower triangle mirrored (:216 of the next step)
-              Vn[i * NX + lane] = h[i];
-              Vn[lane * NX + i] = h[i];
+              Vn[i * C::VS + lane] = h[i];
+              Vn[lane * C::VS + i] = h[i];
             }
         } else {
           AB2_UNROLL
@@ -1037,9 +1395,11 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
         double *Vt = Vxx_b + (size_t)t * NX * NX;
         AB2_UNROLL
         for (int i = 0; i < NX; ++i)
-          Vt[i + lane * NX] = Vn[lane * NX + i];
+          Vt[i + lane * NX] = Vn[lane * C::VS + i];
       }
     }
+
+    } // lane-per-column stage loop
 
     // ---------------- initial stage: proximal-riccati.hxx:42-55 (nth = 0)
     {
@@ -1057,7 +1417,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       double vx0 = 0.0;
       AB2_UNROLL
       for (int i = 0; i < NX; ++i)
-        vcol[i] = colA ? Vn[i * NX + lane] : 0.0;
+        vcol[i] = colA ? Vn[i * C::VS + lane] : 0.0;
       if (lane < NX)
         vx0 = vxn[lane];
       ctx.sync();

@@ -23,6 +23,13 @@ template <int G, bool TMA> struct DevCtx {
 
   __device__ __forceinline__ void sync() { __syncwarp(mask); }
 
+  // D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores (SASS: DMMA.884); full warp only.
+  __device__ __forceinline__ void mma(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+  }
+
   __device__ __forceinline__ void init(uint64_t *bars) {
     bar0 = smem_u32(bars);
     phase = 0;
@@ -114,8 +121,8 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
 struct KernelEntry {
   int nx, nu, nc, G;
   int srec_pad;
-  void (*group_doubles)(int nc0, int gd[2]);
-  cudaError_t (*launch)(const SweepParams &, int variant, const int gd[2], cudaStream_t, int *info);
+  void (*group_doubles)(int nc0, int gd[3]);
+  cudaError_t (*launch)(const SweepParams &, int variant, const int gd[3], cudaStream_t, int *info);
 };
 
 template <class C, int WARPS, int MAXREG, bool TMA>
@@ -152,7 +159,7 @@ inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int
 //   4: as 1 with the cooperative shared-memory Bunch-Kaufman (fewer registers)
 //   5: as 0 with the cooperative shared-memory Bunch-Kaufman
 template <int NX, int NU, int NC, int G>
-inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[2], cudaStream_t st, int *info) {
+inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[3], cudaStream_t st, int *info) {
   using CS = Cfg<NX, NU, NC, G, false>;
   using CD = Cfg<NX, NU, NC, G, true>;
   if (variant == 1)
@@ -167,11 +174,21 @@ inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[2]
     return launch_one<Cfg<NX, NU, NC, G, true, false>, 2, 144, true>(p, gd[1], st, info);
   if (variant == 6) // as 0 capped at 128 registers (8 CTAs/SM)
     return launch_one<CD, 2, 128, true>(p, gd[1], st, info);
+  if constexpr (G == 32 && NC == 0 && NX % 2 == 0) {
+    using CM = Cfg<NX, NU, NC, G, true, true, true>;
+    if (variant == 7) // stage step on the FP64 tensor cores (DMMA), 2 warps/CTA
+      return launch_one<CM, 2, 128, true>(p, gd[2], st, info);
+    if (variant == 8) // same, 4 warps/CTA
+      return launch_one<CM, 4, 128, true>(p, gd[2], st, info);
+  }
   return launch_one<CD, 2, 144, true>(p, gd[1], st, info);
 }
-template <int NX, int NU, int NC, int G> inline void group_doubles_cfg(int nc0, int gd[2]) {
+template <int NX, int NU, int NC, int G> inline void group_doubles_cfg(int nc0, int gd[3]) {
   gd[0] = Cfg<NX, NU, NC, G, false>::group_doubles(nc0);
   gd[1] = Cfg<NX, NU, NC, G, true>::group_doubles(nc0);
+  gd[2] = gd[1];
+  if constexpr (G == 32 && NC == 0 && NX % 2 == 0)
+    gd[2] = Cfg<NX, NU, NC, G, true, true, true>::group_doubles(nc0);
 }
 
 } // namespace ab2

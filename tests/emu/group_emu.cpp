@@ -15,7 +15,22 @@ namespace {
 struct HostCtx {
   int lane;
   std::barrier<> *bar;
+  double *xa, *xb; // fragment exchange for the emulated mma (one slot per lane)
   void sync() { bar->arrive_and_wait(); }
+  // mma.sync.m8n8k4 f64: lane = 4g+q holds a[g][q], b[q][g], d[g][2q], d[g][2q+1]
+  void mma(double (&d)[2], double a, double b) {
+    xa[lane] = a;
+    xb[lane] = b;
+    sync();
+    const int g = lane >> 2, q = lane & 3;
+    for (int e = 0; e < 2; ++e) {
+      double s = 0.0;
+      for (int k = 0; k < 4; ++k)
+        s += xa[4 * g + k] * xb[4 * (2 * q + e) + k];
+      d[e] += s;
+    }
+    sync();
+  }
   void issue_copy(int, double *dst, const double *src, int nd) {
     if (lane == 0)
       std::memcpy(dst, src, sizeof(double) * (size_t)nd);
@@ -23,18 +38,19 @@ struct HostCtx {
   void wait_copy(int) { sync(); }
 };
 
-template <int NX, int NU, int NC, int G, bool DB> int run(const ab2::SweepParams &p) {
-  using C = ab2::Cfg<NX, NU, NC, G, DB>;
+template <class C> int run(const ab2::SweepParams &p) {
+  constexpr int NX = C::NX, G = C::G;
   if (NX + p.nc0 > G)
     return 2;
   for (int inst = 0; inst < p.batch; ++inst) {
     std::vector<double> sm((size_t)C::group_doubles(p.nc0),
                            std::numeric_limits<double>::quiet_NaN());
     std::barrier<> bar(G);
+    std::vector<double> xa(G), xb(G);
     std::vector<std::thread> th;
     for (int l = 0; l < G; ++l)
       th.emplace_back([&, l] {
-        HostCtx ctx{l, &bar};
+        HostCtx ctx{l, &bar, xa.data(), xb.data()};
         ab2::riccati_group_sweep<C>(ctx, p, inst, sm.data());
       });
     for (auto &t : th)
@@ -43,6 +59,16 @@ template <int NX, int NU, int NC, int G, bool DB> int run(const ab2::SweepParams
   return 0;
 }
 } // namespace
+
+template <int NX, int NU, int NC, int G> int dispatch(int mode, const ab2::SweepParams &p) {
+  if (mode == 2) { // tensor-core formulation
+    if constexpr (G == 32 && NC == 0 && NX % 2 == 0)
+      return run<ab2::Cfg<NX, NU, NC, G, true, true, true>>(p);
+    else
+      return 3;
+  }
+  return mode ? run<ab2::Cfg<NX, NU, NC, G, true>>(p) : run<ab2::Cfg<NX, NU, NC, G, false>>(p);
+}
 
 extern "C" int emu_stage_record(int nx, int nu, int nc) {
 #define X(NX, NU, NC, G)                                                        \
@@ -56,7 +82,7 @@ extern "C" int emu_stage_record(int nx, int nu, int nc) {
 extern "C" int emu_sweep(int nx, int nu, int nc, int db, const ab2::SweepParams *p) {
 #define X(NX, NU, NC, G)                                                        \
   if (nx == NX && nu == NU && nc == NC)                                         \
-    return db ? run<NX, NU, NC, G, true>(*p) : run<NX, NU, NC, G, false>(*p);
+    return dispatch<NX, NU, NC, G>(db, *p);
   AB2_FOR_EACH_CONFIG(X)
 #undef X
   return 1;

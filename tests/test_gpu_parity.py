@@ -104,7 +104,7 @@ def test_cuda_matches_oracle(gar, shape):
     assert got["launches"] == 1  # one persistent launch per sweep
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("shape", [(12, 6, 0, 0, 40, 19, 1e-8), (4, 2, 2, 0, 40, 70, 1e-3),
                                    (6, 3, 0, 0, 30, 9, 1e-8)])
 def test_all_launch_variants(gar, shape, variant):
@@ -294,7 +294,7 @@ def test_full_size_properties_config2(gar):
     assert gen.rel_fro(X[idx], ref["xs"]) <= TOL
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 7])
 @pytest.mark.parametrize("shape", [(6, 3, 0, 0, 12, 9), (12, 6, 0, 0, 30, 17), (2, 2, 0, 0, 6, 5)])
 def test_unconstrained_knots_that_need_interchanges(gar, shape, variant):
     """nc = 0 but Rhat needs Bunch-Kaufman interchanges: the branch-free register fast
@@ -304,3 +304,15 @@ def test_unconstrained_knots_that_need_interchanges(gar, shape, variant):
     got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, 1e-8, variant=variant)
     ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, 1e-8)
     compare(got, ref, nu, nc, N, 1e-8, tol=1e-9)
+
+
+@pytest.mark.parametrize("variant", [7, 8])
+@pytest.mark.parametrize("shape", [(12, 6, 0, 0, 100, 41, 1e-11), (14, 7, 0, 0, 200, 9, 1e-8),
+                                   (10, 4, 0, 0, 50, 7, 1e-8), (12, 6, 0, 2, 10, 5, 1e-2)])
+def test_tensor_core_variants(gar, shape, variant):
+    """Variants 7/8: the stage step on the FP64 tensor cores (DMMA m8n8k4)."""
+    nx, nu, nc, nct, N, B, mueq = shape
+    probs = gen.generate_batch(55 + nx, B, N, nx, nu, nc, nct)
+    got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, variant=variant)
+    ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
+    compare(got, ref, nu, nc, N, mueq, tol=1e-9 if nct else TOL)
