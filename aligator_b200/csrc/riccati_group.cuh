@@ -113,7 +113,7 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   }
   static constexpr int VS = MMA ? fstride(4 * KT) : NX;   // row stride of V' in smem
   static constexpr int VROWS = MMA ? 8 * MTX : NX;
-  static constexpr int SW = MMA ? ((8 * NT + 15) / 16 * 16 + 8) : 0; // W row stride (== 8 mod 16)
+  static constexpr int SW = MMA ? ((8 * NT) % 16 == 8 ? 8 * NT : 8 * NT + 8) : 0; // W row stride (== 8 mod 16)
   static constexpr int WROWS = MMA ? 4 * KT : 0;
   static constexpr int SX = MMA ? fstride(8 * NT2) : 0;  // row stride of X / KK
   static constexpr int XROWS = MMA ? 4 * KT2 : 0;
@@ -140,8 +140,8 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   static constexpr int S_VXN = S_VN + ev(VROWS * VS);          // vx'
   static constexpr int S_KKT = S_VXN + ev(NX);                 // NK*NK column-major
   static constexpr int S_RHS = S_KKT + ev(NK * NK);            // NK x RS, unsolved rhs
-  static constexpr int S_SOL = S_RHS + NK * RS;
-  static constexpr int S_DD = S_SOL + NK * RS;
+  static constexpr int S_SOL = S_RHS + (MMA ? 0 : NK * RS); // (the tensor-core step keeps these in X / KK)
+  static constexpr int S_DD = S_SOL + (MMA ? 0 : NK * RS);
   static constexpr int S_SD = S_DD + ev(NK);
   static constexpr int S_X = S_SD + ev(NK);    // forward state x_t (NX) + x_{t+1} (NX)
   static constexpr int S_INT = S_X + 2 * ev(NX); // perm[NK], kind[NK] (ints)
@@ -830,6 +830,11 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
       ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::SREC_PAD,
                      stage_b + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
     cur ^= 1;
+    if (t >= 4) { // and pull the record of 4 knots ahead into L2 (one 128-byte line per lane)
+      const char *nxt = reinterpret_cast<const char *>(stage_b + (size_t)(t - 4) * C::SREC_PAD);
+      for (int o = lane * 128; o < C::SREC_PAD * 8; o += C::G * 128)
+        prefetch_l2(nxt + o);
+    }
 
     // fragments of M = [A | f | B]: B-operand of (1) and A-operand (M^T) of (2)
     double Mf[NT][KT];
@@ -1475,7 +1480,8 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     // rows).  Gains are pulled into L2 PF knots ahead (prefetch.global.L2, no registers);
     // the rows a lane needs for knot t+1 are loaded into the registers it has just
     // finished using for knot t, so the load overlaps the shared-memory hand-over of x.
-    double gfb[RPL][NX], gff[RPL];
+    constexpr int DEPTH = 4; // knots of gain rows held in registers ahead of use
+    double gfb[DEPTH][RPL][NX], gff[DEPTH][RPL];
     auto prefetch_knot = [&](int t) {
       if (t < N) {
         const char *b0 = reinterpret_cast<const char *>(fb_b + (size_t)t * NR * NX);
@@ -1485,38 +1491,36 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           prefetch_l2(ff_b + (size_t)t * NR);
       }
     };
-    auto fetch_gain = [&](int t) {
+    for (int t = 0; t < PF + DEPTH; ++t)
+      prefetch_knot(t);
+    // the pipeline slots are named statically (the t-loop is unrolled by DEPTH)
+    auto fetch_gain = [&](int t, double (&fbr)[RPL][NX], double (&ffr)[RPL]) {
       AB2_UNROLL
       for (int q = 0; q < RPL; ++q) {
         const int r = lane + q * C::G;
-        if (r < NR) {
-          load_row<NX, EVF>(fb_b + ((size_t)t * NR + r) * NX, gfb[q]);
-          gff[q] = ff_b[(size_t)t * NR + r];
+        if (r < NR && t < N) {
+          load_row<NX, EVF>(fb_b + ((size_t)t * NR + r) * NX, fbr[q]);
+          ffr[q] = ff_b[(size_t)t * NR + r];
         }
       }
     };
-    for (int t = 0; t < PF; ++t)
-      prefetch_knot(t);
-    if (N > 0)
-      fetch_gain(0);
-    for (int t = 0; t < N; ++t) {
-      prefetch_knot(t + PF);
+    auto apply = [&](int t, const double (&fbr)[RPL][NX], const double (&ffr)[RPL]) {
       AB2_UNROLL
       for (int q = 0; q < RPL; ++q) {
         const int r = lane + q * C::G;
         if (r < NR) {
-          double s0 = gff[q], s1 = 0.0; // two chains halve the dependent-FMA latency
+          double s0 = ffr[q], s1 = 0.0; // two chains halve the dependent-FMA latency
           if (EVF) {
             AB2_UNROLL
             for (int c = 0; c < NX; c += 2) {
               const D2 xx = lds2(xc + c);
-              s0 += gfb[q][c] * xx.x;
-              s1 += gfb[q][c + 1 < NX ? c + 1 : c] * xx.y;
+              s0 += fbr[q][c] * xx.x;
+              s1 += fbr[q][c + 1 < NX ? c + 1 : c] * xx.y;
             }
           } else {
             AB2_UNROLL
             for (int c = 0; c < NX; ++c)
-              s0 += gfb[q][c] * xc[c];
+              s0 += fbr[q][c] * xc[c];
           }
           const double s = s0 + s1;
           if (r < NU)
@@ -1529,12 +1533,24 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           }
         }
       }
-      if (t + 1 < N)
-        fetch_gain(t + 1); // into the registers just consumed
-      double *tmp = xc;
-      xc = xnx;
-      xnx = tmp;
-      ctx.sync(); // x_{t+1} visible; every lane is done reading x_t
+    };
+    AB2_UNROLL
+    for (int d = 0; d < DEPTH; ++d)
+      fetch_gain(d, gfb[d], gff[d]);
+    for (int t0 = 0; t0 < N; t0 += DEPTH) {
+      AB2_UNROLL
+      for (int d = 0; d < DEPTH; ++d) {
+        const int t = t0 + d;
+        if (t < N) {
+          prefetch_knot(t + PF + DEPTH);
+          apply(t, gfb[d], gff[d]);
+          fetch_gain(t + DEPTH, gfb[d], gff[d]); // refill the slot just consumed
+          double *tmp = xc;
+          xc = xnx;
+          xnx = tmp;
+          ctx.sync(); // x_{t+1} visible; every lane is done reading x_t
+        }
+      }
     }
     // Pass 2 -- the parallel part: lbda_{t+1} = vx_{t+1} + Vxx_{t+1} x_{t+1} has no
     // dependence between knots, so G/NX knots are evaluated per iteration and the loop
@@ -1544,7 +1560,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       const int sub = lane / NX, i = lane % NX;
       if (sub < KPI) {
 #if defined(__CUDACC__)
-#pragma unroll 2
+#pragma unroll 4
 #endif
         for (int t = sub; t < N; t += KPI) {
           const double *Vrow = Vxx_b + ((size_t)(t + 1) * NX + i) * NX; // row i (symmetric, t+1 >= 1)
