@@ -182,6 +182,11 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
     return -1;
   }
 
+  // forward rollout: slots of the fb ring (as many as the stage area can hold, at most 8)
+  static constexpr int FWD_RING_RAW = (S_STAGE_END - 2 * ev(NX)) / ev(NR * NX);
+  static constexpr int FWD_RING = FWD_RING_RAW > 8 ? 8 : (FWD_RING_RAW < 1 ? 1 : FWD_RING_RAW);
+  static constexpr bool FB_BULK = ((NR * NX) % 2) == 0; // 16-byte granularity for bulk copies
+  static_assert(FWD_RING * ev(NR * NX) + 2 * ev(NX) <= S_STAGE_END, "forward ring does not fit");
   static_assert(NU >= 1, "stage knots need nu >= 1");
   static_assert(NCOL <= G, "lane-per-column mapping needs nx+nu+1 <= G");
   static_assert(NK <= G, "cooperative Bunch-Kaufman needs nu+nc <= G");
@@ -1462,9 +1467,31 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     double *us_b = p.us + (size_t)inst * N * NU;
     double *vs_b = p.vs + (size_t)inst * N * NC;
     double *lb_b = p.lbdas + (size_t)inst * N * NX;
-    double *xc = xv;       // x_t
-    double *xnx = xv + NX; // x_{t+1}
+    // Pass 1 -- the sequential part: x_{t+1} = a + Ahat x_t (and u, v, which read the same
+    // rows of fb).  The fb records stream through a ring of FWD_RING shared-memory slots
+    // filled by TMA bulk copies issued FWD_RING knots ahead (no registers, deep enough to
+    // cover HBM latency); ff travels in a register pipeline of the same depth.
+    constexpr int RING = C::FWD_RING;
+    constexpr int FS = C::ev(NR * NX);
+    constexpr int RPL = (NR + C::G - 1) / C::G; // gain rows per lane
+    constexpr bool EVF = C::EVEN;
+    double *ring = sm;                 // RING x FS doubles (the backward's buffers are dead)
+    double *xc = sm + RING * FS;       // x_t
+    double *xnx = xc + C::ev(NX);      // x_{t+1}
+    (void)xv;
     ctx.sync();
+    auto fill_slot = [&](int d, int t) { // fb record of knot t -> ring slot d
+      if (C::FB_BULK) {
+        ctx.issue_copy(d, ring + d * FS, fb_b + (size_t)t * NR * NX, NR * NX);
+      } else { // odd record size: no 16-byte granularity, plain cooperative copy
+        for (int i2 = lane; i2 < NR * NX; i2 += C::G)
+          ring[d * FS + i2] = fb_b[(size_t)t * NR * NX + i2];
+      }
+    };
+    AB2_UNROLL
+    for (int d = 0; d < RING; ++d)
+      if (d < N)
+        fill_slot(d, d);
     if (lane < NX) {
       const double v = k0[lane];
       xc[lane] = v;
@@ -1472,111 +1499,97 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     }
     for (int m = lane; m < nc0; m += C::G)
       p.lbd0[(size_t)inst * nc0 + m] = k0[NX + m];
-    ctx.sync();
-    constexpr int RPL = (NR + C::G - 1) / C::G; // gain rows per lane
-    constexpr bool EVF = C::EVEN;
-    constexpr int PF = 4; // knots of L2 prefetch distance
-    // Pass 1 -- the sequential part: x_{t+1} = a + Ahat x_t (and u, v, which read the same
-    // rows).  Gains are pulled into L2 PF knots ahead (prefetch.global.L2, no registers);
-    // the rows a lane needs for knot t+1 are loaded into the registers it has just
-    // finished using for knot t, so the load overlaps the shared-memory hand-over of x.
-    constexpr int DEPTH = 4; // knots of gain rows held in registers ahead of use
-    double gfb[DEPTH][RPL][NX], gff[DEPTH][RPL];
-    auto prefetch_knot = [&](int t) {
-      if (t < N) {
-        const char *b0 = reinterpret_cast<const char *>(fb_b + (size_t)t * NR * NX);
-        for (int o = lane * 128; o < NR * NX * 8; o += C::G * 128)
-          prefetch_l2(b0 + o);
-        if (lane == 0)
-          prefetch_l2(ff_b + (size_t)t * NR);
-      }
-    };
-    for (int t = 0; t < PF + DEPTH; ++t)
-      prefetch_knot(t);
-    // the pipeline slots are named statically (the t-loop is unrolled by DEPTH)
-    auto fetch_gain = [&](int t, double (&fbr)[RPL][NX], double (&ffr)[RPL]) {
-      AB2_UNROLL
-      for (int q = 0; q < RPL; ++q) {
-        const int r = lane + q * C::G;
-        if (r < NR && t < N) {
-          load_row<NX, EVF>(fb_b + ((size_t)t * NR + r) * NX, fbr[q]);
-          ffr[q] = ff_b[(size_t)t * NR + r];
-        }
-      }
-    };
-    auto apply = [&](int t, const double (&fbr)[RPL][NX], const double (&ffr)[RPL]) {
-      AB2_UNROLL
-      for (int q = 0; q < RPL; ++q) {
-        const int r = lane + q * C::G;
-        if (r < NR) {
-          double s0 = ffr[q], s1 = 0.0; // two chains halve the dependent-FMA latency
-          if (EVF) {
-            AB2_UNROLL
-            for (int c = 0; c < NX; c += 2) {
-              const D2 xx = lds2(xc + c);
-              s0 += fbr[q][c] * xx.x;
-              s1 += fbr[q][c + 1 < NX ? c + 1 : c] * xx.y;
-            }
-          } else {
-            AB2_UNROLL
-            for (int c = 0; c < NX; ++c)
-              s0 += fbr[q][c] * xc[c];
-          }
-          const double s = s0 + s1;
-          if (r < NU)
-            us_b[(size_t)t * NU + r] = s;
-          else if (r < NK)
-            vs_b[(size_t)t * NC + (r - NU)] = s;
-          else {
-            xnx[r - NK] = s;
-            xs_b[(size_t)(t + 1) * NX + (r - NK)] = s;
-          }
-        }
-      }
-    };
+    double gff[RING][RPL];
     AB2_UNROLL
-    for (int d = 0; d < DEPTH; ++d)
-      fetch_gain(d, gfb[d], gff[d]);
-    for (int t0 = 0; t0 < N; t0 += DEPTH) {
+    for (int d = 0; d < RING; ++d) {
       AB2_UNROLL
-      for (int d = 0; d < DEPTH; ++d) {
+      for (int q = 0; q < RPL; ++q) {
+        const int r = lane + q * C::G;
+        gff[d][q] = (r < NR && d < N) ? ff_b[(size_t)d * NR + r] : 0.0;
+      }
+    }
+    ctx.sync();
+    for (int t0 = 0; t0 < N; t0 += RING) {
+      AB2_UNROLL
+      for (int d = 0; d < RING; ++d) {
         const int t = t0 + d;
         if (t < N) {
-          prefetch_knot(t + PF + DEPTH);
-          apply(t, gfb[d], gff[d]);
-          fetch_gain(t + DEPTH, gfb[d], gff[d]); // refill the slot just consumed
+          if (C::FB_BULK)
+            ctx.wait_copy(d);
+          const double *slot = ring + d * FS;
+          AB2_UNROLL
+          for (int q = 0; q < RPL; ++q) {
+            const int r = lane + q * C::G;
+            if (r < NR) {
+              double s0 = gff[d][q], s1 = 0.0; // two chains halve the dependent-FMA latency
+              if (EVF) {
+                AB2_UNROLL
+                for (int c = 0; c < NX; c += 2) {
+                  const D2 gg = lds2(slot + r * NX + c);
+                  const D2 xx = lds2(xc + c);
+                  s0 += gg.x * xx.x;
+                  s1 += gg.y * xx.y;
+                }
+              } else {
+                AB2_UNROLL
+                for (int c = 0; c < NX; ++c)
+                  s0 += slot[r * NX + c] * xc[c];
+              }
+              const double s = s0 + s1;
+              if (r < NU)
+                us_b[(size_t)t * NU + r] = s;
+              else if (r < NK)
+                vs_b[(size_t)t * NC + (r - NU)] = s;
+              else {
+                xnx[r - NK] = s;
+                xs_b[(size_t)(t + 1) * NX + (r - NK)] = s;
+              }
+              gff[d][q] = (t + RING < N) ? ff_b[(size_t)(t + RING) * NR + r] : 0.0;
+            }
+          }
           double *tmp = xc;
           xc = xnx;
           xnx = tmp;
-          ctx.sync(); // x_{t+1} visible; every lane is done reading x_t
+          ctx.sync(); // x_{t+1} visible; every lane is done with x_t and with this slot
+          if (t + RING < N)
+            fill_slot(d, t + RING);
         }
       }
     }
     // Pass 2 -- the parallel part: lbda_{t+1} = vx_{t+1} + Vxx_{t+1} x_{t+1} has no
-    // dependence between knots, so G/NX knots are evaluated per iteration and the loop
-    // is unrolled: many independent loads in flight, no synchronisation.
+    // dependence between knots: G/NX knots per iteration, two iterations batched so that
+    // all their loads are in flight together; no synchronisation.
     {
       constexpr int KPI = (C::G / NX) > 0 ? (C::G / NX) : 1; // knots per iteration
+      constexpr int U = 2;
       const int sub = lane / NX, i = lane % NX;
       if (sub < KPI) {
-#if defined(__CUDACC__)
-#pragma unroll 4
-#endif
-        for (int t = sub; t < N; t += KPI) {
-          const double *Vrow = Vxx_b + ((size_t)(t + 1) * NX + i) * NX; // row i (symmetric, t+1 >= 1)
-          const double *xn = xs_b + (size_t)(t + 1) * NX;
-          double vrow[NX], xr[NX];
-          load_row<NX, EVF>(Vrow, vrow);
-          load_row<NX, EVF>(xn, xr);
-          double s0 = vx_b[(size_t)(t + 1) * NX + i], s1 = 0.0;
+        for (int t = sub; t < N; t += KPI * U) {
+          double vrow[U][NX], xr[U][NX], v0[U];
           AB2_UNROLL
-          for (int c = 0; c + 1 < NX; c += 2) {
-            s0 += vrow[c] * xr[c];
-            s1 += vrow[c + 1] * xr[c + 1];
+          for (int u = 0; u < U; ++u) {
+            const int tt = t + u * KPI;
+            if (tt < N) {
+              load_row<NX, EVF>(Vxx_b + ((size_t)(tt + 1) * NX + i) * NX, vrow[u]); // row i (symmetric)
+              load_row<NX, EVF>(xs_b + (size_t)(tt + 1) * NX, xr[u]);
+              v0[u] = vx_b[(size_t)(tt + 1) * NX + i];
+            }
           }
-          if (NX % 2)
-            s0 += vrow[NX - 1] * xr[NX - 1];
-          lb_b[(size_t)t * NX + i] = s0 + s1;
+          AB2_UNROLL
+          for (int u = 0; u < U; ++u) {
+            const int tt = t + u * KPI;
+            if (tt < N) {
+              double s0 = v0[u], s1 = 0.0;
+              AB2_UNROLL
+              for (int c = 0; c + 1 < NX; c += 2) {
+                s0 += vrow[u][c] * xr[u][c];
+                s1 += vrow[u][c + 1] * xr[u][c + 1];
+              }
+              if (NX % 2)
+                s0 += vrow[u][NX - 1] * xr[u][NX - 1];
+              lb_b[(size_t)tt * NX + i] = s0 + s1;
+            }
+          }
         }
       }
       ctx.sync();

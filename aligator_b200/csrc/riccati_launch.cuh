@@ -15,10 +15,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+constexpr int NBAR = 8; // mbarriers per group (backward uses 2, the forward ring up to 8)
+
 template <int G, bool TMA> struct DevCtx {
   int lane;
   unsigned mask;
-  uint32_t bar0; // shared address of this group's two mbarriers
+  uint32_t bar0; // shared address of this group's NBAR mbarriers
   uint32_t phase; // bit p = parity to wait for on barrier p
 
   __device__ __forceinline__ void sync() { __syncwarp(mask); }
@@ -35,8 +37,8 @@ template <int G, bool TMA> struct DevCtx {
     phase = 0;
     if (TMA) {
       if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+        for (int b = 0; b < NBAR; ++b)
+          asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * b));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
     }
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
     return; // whole group leaves together
   double *sm = smem + (size_t)group_in_cta * group_doubles;
   uint64_t *bars =
-      reinterpret_cast<uint64_t *>(smem + (size_t)(WARPS * IPW) * group_doubles) + 2 * group_in_cta;
+      reinterpret_cast<uint64_t *>(smem + (size_t)(WARPS * IPW) * group_doubles) + NBAR * group_in_cta;
   DevCtx<C::G, TMA> ctx;
   ctx.lane = lane32 % C::G;
   ctx.mask = (C::G == 32) ? 0xffffffffu : (((1u << C::G) - 1u) << (gsub * C::G));
@@ -129,7 +131,7 @@ template <class C, int WARPS, int MAXREG, bool TMA>
 inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int *info) {
   constexpr int IPW = 32 / C::G;
   const int groups = WARPS * IPW;
-  const size_t smem = (size_t)groups * gd * sizeof(double) + (size_t)groups * 16;
+  const size_t smem = (size_t)groups * gd * sizeof(double) + (size_t)groups * 8 * NBAR;
   auto kern = riccati_sweep_kernel<C, WARPS, MAXREG, TMA>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)

@@ -27,6 +27,12 @@ def main():
              (find("template <int N> struct FastFactor"), "fastBK+solve"),
              (find("template <int N> struct RegFactor"), "regBK"),
              (find("AB2_D void bk_solve_vec_group"), "solve_vec"),
+             (find("AB2_D void stage_loop_mma"), "mma:setup+load"),
+             (find("// (1) W = V' M   (+ vx'"), "mma:(1)W"),
+             (find("// (2) H = H0 + M^T W"), "mma:(2)H"),
+             (find("// (3) control rows of H: [Shat^T | rhat] -> X"), "mma:(3)dump+BK+solve"),
+             (find("// fragments of KK = [K k] (rows >= NK are zero)"), "mma:(4)Ahat"),
+             (find("// (5) [Vxx vx] = [Qhat qhat] + Shat KK"), "mma:(5)Vxx+stores"),
              (find("AB2_D void riccati_group_sweep"), "setup"),
              (find("terminal knot (nu = 0)"), "terminal"),
              (find("stage knots N-1 .. 0"), "stage:load+A"), (find("(B) H[:,j] = H0"), "stage:B"),
