@@ -186,6 +186,8 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   static constexpr int FWD_RING_RAW = (S_STAGE_END - 2 * ev(NX)) / ev(NR * NX);
   static constexpr int FWD_RING = FWD_RING_RAW > 8 ? 8 : (FWD_RING_RAW < 1 ? 1 : FWD_RING_RAW);
   static constexpr bool FB_BULK = ((NR * NX) % 2) == 0; // 16-byte granularity for bulk copies
+  static constexpr int FWD_SLOT = ev(NR * NX);           // doubles per ring slot
+  static constexpr int NXE = ev(NX);
   static_assert(FWD_RING * ev(NR * NX) + 2 * ev(NX) <= S_STAGE_END, "forward ring does not fit");
   static_assert(NU >= 1, "stage knots need nu >= 1");
   static_assert(NCOL <= G, "lane-per-column mapping needs nx+nu+1 <= G");
@@ -1472,12 +1474,12 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     // filled by TMA bulk copies issued FWD_RING knots ahead (no registers, deep enough to
     // cover HBM latency); ff travels in a register pipeline of the same depth.
     constexpr int RING = C::FWD_RING;
-    constexpr int FS = C::ev(NR * NX);
+    constexpr int FS = C::FWD_SLOT;
     constexpr int RPL = (NR + C::G - 1) / C::G; // gain rows per lane
     constexpr bool EVF = C::EVEN;
     double *ring = sm;                 // RING x FS doubles (the backward's buffers are dead)
     double *xc = sm + RING * FS;       // x_t
-    double *xnx = xc + C::ev(NX);      // x_{t+1}
+    double *xnx = xc + C::NXE;         // x_{t+1}
     (void)xv;
     ctx.sync();
     auto fill_slot = [&](int d, int t) { // fb record of knot t -> ring slot d
