@@ -149,6 +149,7 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   static constexpr int S_XM = S_WSM + ev(WROWS * SW);    // MMA: control rows of H, XROWS x SX
   static constexpr int S_KK = S_XM + ev(XROWS * SX);     // MMA: [K k; Z z], XROWS x SX
   static constexpr int S_STAGE_END = S_KK + ev(XROWS * SX);
+  static_assert(!MMA || SREC_PAD < 0xffff, "record offsets are packed in 16 bits");
   static_assert(!MMA || (DB_ && G_ == 32 && NC_ == 0 && (NX_ % 2 == 0)),
                 "the tensor-core step needs double-buffered records, a full warp, nc = 0, even nx");
 
@@ -809,14 +810,14 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
   AB2_UNROLL
   for (int t = 0; t < NT; ++t)
     moff[t] = C::col_offset(8 * t + g);
-  int h0o[NT][NT][2];
+  unsigned h0p[NT][NT]; // two 16-bit record offsets per register (0xffff = structural zero)
   AB2_UNROLL
   for (int mt = 0; mt < NT; ++mt) {
     AB2_UNROLL
     for (int nt = 0; nt < NT; ++nt) {
-      AB2_UNROLL
-      for (int e = 0; e < 2; ++e)
-        h0o[mt][nt][e] = C::h0_offset(8 * mt + g, 8 * nt + 2 * q + e);
+      const int o0 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q);
+      const int o1 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q + 1);
+      h0p[mt][nt] = (unsigned)(o0 & 0xffff) | ((unsigned)(o1 & 0xffff) << 16);
     }
   }
   // zero the padding of the staging matrices once (rows/columns never written later)
@@ -896,8 +897,8 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
       for (int nt = 0; nt < NT; ++nt) {
         AB2_UNROLL
         for (int e = 0; e < 2; ++e) {
-          const int o = h0o[mt][nt][e];
-          H[mt][nt][e] = (o >= 0) ? rec[o >= 0 ? o : 0] : 0.0;
+          const unsigned o = (h0p[mt][nt] >> (16 * e)) & 0xffffu;
+          H[mt][nt][e] = (o != 0xffffu) ? rec[o != 0xffffu ? o : 0] : 0.0;
         }
       }
     }

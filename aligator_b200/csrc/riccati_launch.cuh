@@ -179,7 +179,7 @@ inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[3]
   if constexpr (G == 32 && NC == 0 && NX % 2 == 0) {
     using CM = Cfg<NX, NU, NC, G, true, true, true>;
     if (variant == 7) // stage step on the FP64 tensor cores (DMMA), 2 warps/CTA
-      return launch_one<CM, 2, 168, true>(p, gd[2], st, info);
+      return launch_one<CM, 2, 144, true>(p, gd[2], st, info);
     if (variant == 8) // same, 4 warps/CTA
       return launch_one<CM, 4, 168, true>(p, gd[2], st, info);
   }
