@@ -136,6 +136,11 @@ inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
     return e;
+  // the sweep lives in shared memory: ask for the largest carve-out (227 KB per SM)
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess)
+    return e;
   const int grid = (p.batch + groups - 1) / groups;
   if (info) {
     cudaFuncAttributes fa;
@@ -179,7 +184,7 @@ inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[3]
   if constexpr (G == 32 && NC == 0 && NX % 2 == 0) {
     using CM = Cfg<NX, NU, NC, G, true, true, true>;
     if (variant == 7) // stage step on the FP64 tensor cores (DMMA), 2 warps/CTA
-      return launch_one<CM, 2, 144, true>(p, gd[2], st, info);
+      return launch_one<CM, 2, 136, true>(p, gd[2], st, info);
     if (variant == 8) // same, 4 warps/CTA
       return launch_one<CM, 4, 168, true>(p, gd[2], st, info);
   }
