@@ -394,7 +394,7 @@ int ab2_gar_kernel_info(const ab2_gar_solver *s, int *group_lanes, int *smem_byt
                         int *threads_per_cta, int *grid, int *regs_per_thread) {
   if (!s)
     return fail(AB2_ERR_INVALID, "null solver");
-  int info[5] = {0, 0, 0, 0, 0};
+  int info[6] = {0, 0, 0, 0, 0, 0};
   CUDA_TRY(cudaSetDevice(s->d.device));
   CUDA_TRY(s->k->launch(s->p, s->variant, s->group_doubles, 0, info));
   if (group_lanes)
@@ -406,7 +406,7 @@ int ab2_gar_kernel_info(const ab2_gar_solver *s, int *group_lanes, int *smem_byt
   if (grid)
     *grid = info[3];
   if (regs_per_thread)
-    *regs_per_thread = info[4];
+    *regs_per_thread = info[4] | (info[5] << 16); /* high half: resident CTAs per SM */
   return AB2_OK;
 }
 

@@ -145,10 +145,13 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   static constexpr int S_SD = S_DD + ev(NK);
   static constexpr int S_X = S_SD + ev(NK);    // forward state x_t (NX) + x_{t+1} (NX)
   static constexpr int S_INT = S_X + 2 * ev(NX); // perm[NK], kind[NK] (ints)
-  static constexpr int S_WSM = S_INT + ev(NK + 1);       // MMA: W = V' M, WROWS x SW
-  static constexpr int S_XM = S_WSM + ev(WROWS * SW);    // MMA: control rows of H, XROWS x SX
-  static constexpr int S_KK = S_XM + ev(XROWS * SX);     // MMA: [K k; Z z], XROWS x SX
-  static constexpr int S_STAGE_END = S_KK + ev(XROWS * SX);
+  // MMA staging: W = V' M (WROWS x SW) is dead once H is formed, so it shares its storage
+  // with X (control rows of H, XROWS x SX) and KK ([K k; Z z], XROWS x SX).
+  static constexpr int S_WSM = S_INT + ev(NK + 1);
+  static constexpr int S_XM = S_WSM;
+  static constexpr int S_KK = S_XM + ev(XROWS * SX);
+  static constexpr int S_MMA_END = S_WSM + (ev(WROWS * SW) > 2 * ev(XROWS * SX) ? ev(WROWS * SW) : 2 * ev(XROWS * SX));
+  static constexpr int S_STAGE_END = S_MMA_END;
   static_assert(!MMA || SREC_PAD < 0xffff, "record offsets are packed in 16 bits");
   static_assert(!MMA || (DB_ && G_ == 32 && NC_ == 0 && (NX_ % 2 == 0)),
                 "the tensor-core step needs double-buffered records, a full warp, nc = 0, even nx");
@@ -820,13 +823,6 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
       h0p[mt][nt] = (unsigned)(o0 & 0xffff) | ((unsigned)(o1 & 0xffff) << 16);
     }
   }
-  // zero the padding of the staging matrices once (rows/columns never written later)
-  for (int i = lane; i < C::WROWS * SW; i += C::G)
-    Wsm[i] = 0.0;
-  for (int i = lane; i < C::XROWS * SX; i += C::G) {
-    X[i] = 0.0;
-    KKs[i] = 0.0;
-  }
   ctx.sync();
 
   const bool colS = lane <= NX; // this lane solves right-hand-side column `lane` ([K | k])
@@ -906,13 +902,15 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     for (int kt = 0; kt < KT; ++kt) {
       AB2_UNROLL
       for (int nt = 0; nt < NT; ++nt) {
-        const double wb = Wsm[(4 * kt + q) * SW + 8 * nt + g];
+        // rows >= NX pad the contraction (never stored): structural zeros
+        const double wb = (4 * kt + q < NX) ? Wsm[(4 * kt + q < NX ? 4 * kt + q : 0) * SW + 8 * nt + g] : 0.0;
         AB2_UNROLL
         for (int mt = 0; mt < NT; ++mt)
           ctx.mma(H[mt][nt], Mf[mt][kt], wb);
       }
     }
     // (3) control rows of H: [Shat^T | rhat] -> X, Rhat -> KKT matrix (:232-257)
+    ctx.sync(); // every lane has its W fragments: the storage becomes X / KK
     AB2_UNROLL
     for (int mt = 0; mt < NT; ++mt) {
       const int c = 8 * mt + g - NX - 1;
@@ -971,7 +969,9 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     for (int k2 = 0; k2 < KT2; ++k2) {
       AB2_UNROLL
       for (int nt = 0; nt < NT2; ++nt)
-        KKf[k2][nt] = KKs[(4 * k2 + q) * SX + 8 * nt + g];
+        KKf[k2][nt] = (4 * k2 + q < NK && 8 * nt + g <= NX)
+                          ? KKs[(4 * k2 + q < NK ? 4 * k2 + q : 0) * SX + (8 * nt + g <= NX ? 8 * nt + g : 0)]
+                          : 0.0; // padding of the fragment: structural zeros
     }
     // (4) [Ahat a] = [A f] + B KK   (:266-267)
     {
@@ -1016,7 +1016,9 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
       const int i = 8 * mt + g;
       AB2_UNROLL
       for (int k2 = 0; k2 < KT2; ++k2) {
-        const double xf = X[(4 * k2 + q) * SX + i];
+        const double xf = (4 * k2 + q < NK && i <= NX)
+                              ? X[(4 * k2 + q < NK ? 4 * k2 + q : 0) * SX + (i <= NX ? i : 0)]
+                              : 0.0;
         AB2_UNROLL
         for (int nt = 0; nt < NT2; ++nt)
           ctx.mma(H[mt][nt], xf, KKf[k2][nt]);

@@ -150,6 +150,9 @@ inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int
     info[2] = WARPS * 32;
     info[3] = grid;
     info[4] = fa.numRegs;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem);
+    info[5] = nb;
     return cudaSuccess;
   }
   kern<<<grid, WARPS * 32, smem, st>>>(p, gd);
@@ -184,9 +187,9 @@ inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[3]
   if constexpr (G == 32 && NC == 0 && NX % 2 == 0) {
     using CM = Cfg<NX, NU, NC, G, true, true, true>;
     if (variant == 7) // stage step on the FP64 tensor cores (DMMA), 2 warps/CTA
-      return launch_one<CM, 2, 136, true>(p, gd[2], st, info);
+      return launch_one<CM, 2, 128, true>(p, gd[2], st, info);
     if (variant == 8) // same, 4 warps/CTA
-      return launch_one<CM, 4, 168, true>(p, gd[2], st, info);
+      return launch_one<CM, 2, 168, true>(p, gd[2], st, info);
   }
   return launch_one<CD, 2, 144, true>(p, gd[1], st, info);
 }

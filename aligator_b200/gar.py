@@ -216,8 +216,11 @@ class CudaRiccatiBatch:
     def kernel_info(self):
         v = [C.c_int() for _ in range(5)]
         _check(lib().ab2_gar_kernel_info(self.h, *[C.byref(x) for x in v]))
-        return dict(zip(("group_lanes", "smem_bytes_per_cta", "threads_per_cta", "grid",
-                         "regs_per_thread"), [x.value for x in v]))
+        d = dict(zip(("group_lanes", "smem_bytes_per_cta", "threads_per_cta", "grid",
+                      "regs_per_thread"), [x.value for x in v]))
+        d["ctas_per_sm"] = d["regs_per_thread"] >> 16
+        d["regs_per_thread"] &= 0xffff
+        return d
 
 
 # ---------------------------------------------------------------------------

@@ -148,7 +148,8 @@ int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace
 int ab2_gar_synchronize(ab2_gar_solver *s, void *stream);
 /* Kernels launched by this solver since creation (for bench accounting). */
 long ab2_gar_launch_count(const ab2_gar_solver *s);
-/* Shared memory per CTA / registers etc. of the kernel serving this solver. */
+/* Shared memory per CTA / registers etc. of the kernel serving this solver
+ * (*regs_per_thread: low 16 bits = registers, high 16 bits = resident CTAs per SM). */
 int ab2_gar_kernel_info(const ab2_gar_solver *s, int *group_lanes, int *smem_bytes_per_cta,
                         int *threads_per_cta, int *grid, int *regs_per_thread);
 const char *ab2_gar_last_error(void);
