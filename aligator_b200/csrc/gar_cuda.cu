@@ -83,7 +83,7 @@ struct ab2_gar_solver {
   int *status = nullptr;
   bool have_problem = false, have_backward = false;
   long launches = 0;
-  int variant = 0;
+  int variant = -1;
   int group_doubles[3] = {0, 0, 0};
 };
 
@@ -216,7 +216,7 @@ int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t) {
     return fail(AB2_ERR_INVALID, "null argument");
   if (t->variant < -1 || t->variant > 8)
     return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..8");
-  s->variant = t->variant < 0 ? 0 : t->variant;
+  s->variant = t->variant;
   return AB2_OK;
 }
 

@@ -159,19 +159,24 @@ inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int
   return cudaGetLastError();
 }
 
-// Launch variants per shape (ab2_gar_tuning.variant):
-//   0: 2 warps/CTA x >=7 CTAs/SM (<= 144 registers), knot records double-buffered,
-//      one TMA bulk copy per knot, Bunch-Kaufman in registers            [default]
-//   1: 4 warps/CTA x 7 CTAs/SM (28 warp-groups per SM: one wave at batch 4096 on
-//      148 SMs, <= 72 registers), single record buffer refilled in two TMA parts
+// Launch variants per shape (ab2_gar_tuning.variant); -1 = automatic:
+//   the tensor-core variant 7 where the shape allows it (full warp per instance, nc = 0,
+//   even nx), else variant 6.
+//   0: lane-per-column step, 2 warps/CTA, <= 144 registers, double-buffered records, TMA
+//   1: lane-per-column, 4 warps/CTA x 7 CTAs/SM (<= 72 registers), single record buffer, TMA
 //   2: as 0 with cp.async (LDGSTS) staging instead of TMA
 //   3: as 1 with cp.async staging
-//   4: as 1 with the cooperative shared-memory Bunch-Kaufman (fewer registers)
+//   4: as 1 with the cooperative shared-memory Bunch-Kaufman
 //   5: as 0 with the cooperative shared-memory Bunch-Kaufman
+//   6: as 0 capped at 128 registers (8 CTAs = 16 warps per SM)
+//   7: stage step on the FP64 tensor cores (DMMA m8n8k4), 128 registers, 16 warps per SM
+//   8: as 7 with 168 registers (12 warps per SM, no spills)
 template <int NX, int NU, int NC, int G>
 inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[3], cudaStream_t st, int *info) {
   using CS = Cfg<NX, NU, NC, G, false>;
   using CD = Cfg<NX, NU, NC, G, true>;
+  if (variant < 0)
+    variant = (G == 32 && NC == 0 && NX % 2 == 0) ? 7 : 6;
   if (variant == 1)
     return launch_one<CS, 4, 72, true>(p, gd[0], st, info);
   if (variant == 2)

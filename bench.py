@@ -228,14 +228,15 @@ def main():
     ff0 = torch.empty(B, NU + NX, dtype=torch.float64, device=dev)
     fb0 = torch.empty(B, NU + NX, NX, dtype=torch.float64, device=dev)
 
+    from aligator_b200 import sharding
+
     def step():
         solver.sweep(MUEQ, stream=stream)
-        if world > 1:
+        if world > 1:  # the one exchange: all-gather of the first-step policy [K0 | k0]
             solver.get_range_into(gar.OUT_FB, 0, B, 0, 1, fb0, gar.AB2_DEVICE, stream=stream)
             solver.get_range_into(gar.OUT_FF, 0, B, 0, 1, ff0, gar.AB2_DEVICE, stream=stream)
-            pol[:, :, :NX] = fb0[:, :NU]
-            pol[:, :, NX] = ff0[:, :NU]
-            dist.all_gather_into_tensor(pol_all, pol)
+            sharding.pack_first_step_policy(torch, fb0, ff0, NU, NX, out=pol)
+            sharding.all_gather_policy(torch, dist, pol, world, out=pol_all)
 
     def barrier():
         if world > 1:

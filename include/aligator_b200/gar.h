@@ -87,9 +87,9 @@ typedef struct ab2_gar_dims {
   int device;  /* CUDA device ordinal                               */
 } ab2_gar_dims;
 
-/* launch tuning.  variant: -1/0 = default (2 warps/CTA, 7 CTAs/SM, double-buffered
- * knot records, TMA bulk copies); 1 = 4 warps/CTA, 7 CTAs/SM, single record buffer,
- * TMA; 2 = as 0 with cp.async staging; 3 = as 1 with cp.async staging. */
+/* launch tuning.  variant: -1 = automatic (the FP64 tensor-core formulation where the
+ * shape allows it, else the lane-per-column one); 0..8 select a specific kernel build,
+ * see csrc/riccati_launch.cuh. */
 typedef struct ab2_gar_tuning {
   int variant;
 } ab2_gar_tuning;
