@@ -154,8 +154,11 @@ def run_reference(args, rank, world):
     from oracle import gar_oracle as orc
     bo = orc.BatchedOracle(NX, NU, NC, NCT, NX, HORIZON, nb, stage, term, G0, g0)
     threads = orc.num_threads()
+    t1 = 1e9
     for _ in range(max(args.warmup, 1)):
-        bo.sweep(MUEQ, reps=1)
+        t1 = min(t1, bo.sweep(MUEQ, reps=1))
+    if args.ref_seconds > 0:  # bounded sample sized in seconds (used for cpu_baseline)
+        args.steps = max(1, int(args.ref_seconds / max(t1, 1e-5)))
     t = bo.sweep(MUEQ, reps=args.steps)
     knots = nb * (HORIZON + 1) * args.steps
     v = knots / t
@@ -167,7 +170,8 @@ def run_reference(args, rank, world):
                        "mueq": MUEQ, "note": "reference cannot be built here (no Eigen); "
                        "restated C++ port of gar::ProximalRiccatiSolver, OpenMP over instances"},
             "cpu_baseline": {"value": v, "unit": "knots/s", "cores": threads, "kind": "port",
-                             "sample": "%d instances x %d sweeps" % (nb, args.steps)},
+                             "sample": "%d instances x %d sweeps (%.1f s), OpenMP over instances, %d threads"
+                                       % (nb, args.steps, t, threads)},
             "e2e": {"value": v, "unit": "knots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -186,6 +190,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--ref-seconds", type=float, default=0.0)
     args = ap.parse_args()
     if args.config != "c2":
         NX, NU, NC, NCT, HORIZON, BATCH, MUEQ, WORKLOAD = CONFIGS[args.config]
@@ -334,9 +339,17 @@ def main():
 
     cpu = None
     if not args.no_cpu:
-        nb = 512
-        cpu, _ = cpu_baseline(stage[:nb].cpu().numpy(), term[:nb].cpu().numpy(), G0[:nb].cpu().numpy(),
-                              g0[:nb].cpu().numpy(), NX, NU, NC, NCT, N)
+        # The CPU arm runs in a fresh process: inside this one torch's own OpenMP runtime
+        # competes with the oracle's thread pool (measured 5x slower), which would flatter
+        # the GPU.  Same code path as `--impl reference`, sized to ~12 s of CPU work.
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
+                            "--config", args.config, "--warmup", "2", "--ref-seconds", "12"],
+                           capture_output=True, text=True)
+        try:
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception:
+            cpu = {"value": None, "unit": "knots/s", "cores": None, "kind": "port",
+                   "sample": "reference arm failed: " + (r.stderr or r.stdout)[-200:]}
 
     line = {"metric": "riccati_knots_per_sec", "value": value, "unit": "knots/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
