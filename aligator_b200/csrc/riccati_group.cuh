@@ -860,9 +860,9 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
         }
       }
       AB2_UNROLL
-      for (int mt = 0; mt < MTX; ++mt) {
+      for (int kt = 0; kt < KT; ++kt) { // contraction outermost: MTX*NT independent DMMAs per step
         AB2_UNROLL
-        for (int kt = 0; kt < KT; ++kt) {
+        for (int mt = 0; mt < MTX; ++mt) {
           const double va = Vn[(8 * mt + g) * VS + 4 * kt + q];
           AB2_UNROLL
           for (int nt = 0; nt < NT; ++nt)
@@ -973,28 +973,50 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
                           ? KKs[(4 * k2 + q < NK ? 4 * k2 + q : 0) * SX + (8 * nt + g <= NX ? 8 * nt + g : 0)]
                           : 0.0; // padding of the fragment: structural zeros
     }
-    // (4) [Ahat a] = [A f] + B KK   (:266-267)
+    // (4) [Ahat a] = [A f] + B KK   (:266-267)   and
+    // (5) [Vxx vx] = [Qhat qhat] + Shat KK, with Shat[i][c] = X[c][i]   (:270-277)
+    // All operand fragments are fetched first and the two products are interleaved with the
+    // contraction outermost: 2*MTX*NT2 independent DMMAs per k-step.
     {
-      double EA[MTX][NT2][2];
+      double EA[MTX][NT2][2], Bf[MTX][KT2], Xf[MTX][KT2];
       AB2_UNROLL
       for (int mt = 0; mt < MTX; ++mt) {
         const int i = 8 * mt + g;
+        const int ic = i < NX ? i : 0;
         AB2_UNROLL
         for (int nt = 0; nt < NT2; ++nt) {
           AB2_UNROLL
           for (int e = 0; e < 2; ++e) {
             const int jj = 8 * nt + 2 * q + e;
-            EA[mt][nt][e] = (i < NX && jj <= NX) ? rec[C::col_offset(jj <= NX ? jj : 0) + (i < NX ? i : 0)] : 0.0;
+            const double v = rec[C::col_offset(jj <= NX ? jj : 0) + ic];
+            EA[mt][nt][e] = (i < NX && jj <= NX) ? v : 0.0;
           }
         }
         AB2_UNROLL
         for (int k2 = 0; k2 < KT2; ++k2) {
           const int c = 4 * k2 + q;
-          const double bf = (c < NU && i < NX) ? rec[C::OFF_B + (c < NU ? c : 0) * NX + (i < NX ? i : 0)] : 0.0;
-          AB2_UNROLL
-          for (int nt = 0; nt < NT2; ++nt)
-            ctx.mma(EA[mt][nt], bf, KKf[k2][nt]);
+          const double bv = rec[C::OFF_B + (c < NU ? c : 0) * NX + ic];
+          Bf[mt][k2] = (c < NU && i < NX) ? bv : 0.0;
+          const double xv = X[(c < NK ? c : 0) * SX + (i <= NX ? i : 0)];
+          Xf[mt][k2] = (c < NK && i <= NX) ? xv : 0.0;
         }
+      }
+      AB2_UNROLL
+      for (int k2 = 0; k2 < KT2; ++k2) {
+        AB2_UNROLL
+        for (int mt = 0; mt < MTX; ++mt) {
+          AB2_UNROLL
+          for (int nt = 0; nt < NT2; ++nt) {
+            ctx.mma(EA[mt][nt], Bf[mt][k2], KKf[k2][nt]);
+            ctx.mma(H[mt][nt], Xf[mt][k2], KKf[k2][nt]);
+          }
+        }
+      }
+      if (C::VS == NX && t > 0)
+        ctx.bulk_store_wait_read(); // the previous knot's Vxx store has finished reading V'
+      AB2_UNROLL
+      for (int mt = 0; mt < MTX; ++mt) {
+        const int i = 8 * mt + g;
         if (i < NX) {
           AB2_UNROLL
           for (int nt = 0; nt < NT2; ++nt) {
@@ -1009,49 +1031,51 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
           }
         }
       }
-    }
-    // (5) [Vxx vx] = [Qhat qhat] + Shat KK, with Shat[i][c] = X[c][i]   (:270-277)
-    AB2_UNROLL
-    for (int mt = 0; mt < MTX; ++mt) {
-      const int i = 8 * mt + g;
+      if (C::VS == NX)
+        ctx.sync(); // (lane 0 waited above) nobody overwrites V' before the store has read it
       AB2_UNROLL
-      for (int k2 = 0; k2 < KT2; ++k2) {
-        const double xf = (4 * k2 + q < NK && i <= NX)
-                              ? X[(4 * k2 + q < NK ? 4 * k2 + q : 0) * SX + (i <= NX ? i : 0)]
-                              : 0.0;
-        AB2_UNROLL
-        for (int nt = 0; nt < NT2; ++nt)
-          ctx.mma(H[mt][nt], xf, KKf[k2][nt]);
-      }
-      if (i < NX) {
-        AB2_UNROLL
-        for (int nt = 0; nt < NT2; ++nt) {
+      for (int mt = 0; mt < MTX; ++mt) {
+        const int i = 8 * mt + g;
+        if (i < NX) {
           AB2_UNROLL
-          for (int e = 0; e < 2; ++e) {
-            const int jj = 8 * nt + 2 * q + e;
-            const double v = H[mt][nt][e];
-            if (jj < NX) {
-              if (t == 0)
-                Vxx_b[i + jj * NX] = v; // datas[0].Vxx is left unsymmetrised (A1)
-              if (i >= jj) {            // V' = lower triangle mirrored (:216 of the next step)
-                Vn[i * VS + jj] = v;
-                Vn[jj * VS + i] = v;
+          for (int nt = 0; nt < NT2; ++nt) {
+            AB2_UNROLL
+            for (int e = 0; e < 2; ++e) {
+              const int jj = 8 * nt + 2 * q + e;
+              const double v = H[mt][nt][e];
+              if (jj < NX) {
+                if (t == 0)
+                  Vxx_b[i + jj * NX] = v; // datas[0].Vxx is left unsymmetrised (A1)
+                if (i >= jj) {            // V' = lower triangle mirrored (:216 of the next step)
+                  Vn[i * VS + jj] = v;
+                  Vn[jj * VS + i] = v;
+                }
+              } else if (jj == NX) {
+                vx_b[(size_t)t * NX + i] = v;
+                vxn[i] = v;
               }
-            } else if (jj == NX) {
-              vx_b[(size_t)t * NX + i] = v;
-              vxn[i] = v;
             }
           }
         }
       }
     }
+    if (C::VS == NX && t > 0)
+      ctx.async_fence(); // this lane's writes to V' become visible to the TMA store below
     ctx.sync();
-    if (t > 0 && lane < NX) { // symmetric Vxx_t, as the next step of the reference leaves it
+    if (t > 0) { // symmetric Vxx_t, as the next step of the reference leaves it
       double *Vt = Vxx_b + (size_t)t * NX * NX;
-      AB2_UNROLL
-      for (int i = 0; i < NX; ++i)
-        Vt[i + lane * NX] = Vn[lane * VS + i];
+      if (C::VS == NX) { // V' is dense in shared memory: one TMA bulk store, no LDS/STG
+        ctx.bulk_store(Vt, Vn, NX * NX);
+      } else if (lane < NX) {
+        AB2_UNROLL
+        for (int i = 0; i < NX; ++i)
+          Vt[i + lane * NX] = Vn[lane * VS + i];
+      }
     }
+  }
+  if (C::VS == NX) { // the last store must have read V' before the initial stage reuses the buffers
+    ctx.bulk_store_wait_read();
+    ctx.sync();
   }
 }
 

@@ -51,9 +51,9 @@ template <int G, bool TMA> struct DevCtx {
       if (lane == 0) {
         const uint32_t bar = bar0 + 8 * part;
         const uint32_t bytes = (uint32_t)nd * 8u;
-        // order this group's earlier generic-proxy reads of the buffer before the
-        // async-proxy writes of the bulk copy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // No proxy fence: every refill targets a buffer whose last generic-proxy READS have
+        // completed (their values were consumed before the group synchronisation that
+        // precedes this call), and nothing was written to it through the generic proxy.
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                      : "memory");
         asm volatile(
@@ -69,6 +69,24 @@ template <int G, bool TMA> struct DevCtx {
                      : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
+  }
+
+  // Every lane that wrote (through the generic proxy) shared memory a bulk store will read
+  // calls this BEFORE the group synchronisation that precedes bulk_store().
+  __device__ __forceinline__ void async_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+  // Shared -> global bulk store of `nd` doubles (TMA).  One lane issues.
+  __device__ __forceinline__ void bulk_store(double *gdst, const double *ssrc, int nd) {
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                   "r"(smem_u32(ssrc)), "r"((uint32_t)nd * 8u)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  // the source of every earlier bulk_store may be overwritten after this + a sync
+  __device__ __forceinline__ void bulk_store_wait_read() {
+    if (lane == 0)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   __device__ __forceinline__ void wait_copy(int part) {

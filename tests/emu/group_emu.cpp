@@ -36,6 +36,12 @@ struct HostCtx {
       std::memcpy(dst, src, sizeof(double) * (size_t)nd);
   }
   void wait_copy(int) { sync(); }
+  void bulk_store(double *gdst, const double *ssrc, int nd) {
+    if (lane == 0)
+      std::memcpy(gdst, ssrc, sizeof(double) * (size_t)nd);
+  }
+  void bulk_store_wait_read() {}
+  void async_fence() {}
 };
 
 template <class C> int run(const ab2::SweepParams &p) {
