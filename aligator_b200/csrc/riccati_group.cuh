@@ -789,14 +789,20 @@ AB2_D void sts2(double *p, double x, double y) {
 // ---------------------------------------------------------------------------
 template <class C, class Ctx>
 AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ sm, int &st,
-                          const double *stage_b, double *ff_b, double *fb_b, double *Vxx_b,
-                          double *vx_b) {
+                          const int inst) {
   constexpr int NX = C::NX, NU = C::NU, NK = C::NK, NR = C::NR;
   constexpr int MTX = C::MTX, KT = C::KT, NT = C::NT, NT2 = C::NT2, KT2 = C::KT2;
   constexpr int VS = C::VS, SW = C::SW, SX = C::SX;
   const int lane = ctx.lane;
   const int g = lane >> 2, q = lane & 3;
   const int N = p.N;
+  // Output / input bases are re-derived from the kernel parameters (constant bank) where
+  // they are used instead of being carried in registers across the whole loop.
+#define AB2_STAGE_B (p.stage + (size_t)inst * N * C::SREC_PAD)
+#define AB2_FF_B (p.ff + (size_t)inst * N * NR)
+#define AB2_FB_B (p.fb + (size_t)inst * N * NR * NX)
+#define AB2_VXX_B (p.Vxx + (size_t)inst * (N + 1) * NX * NX)
+#define AB2_VX_B (p.vx + (size_t)inst * (N + 1) * NX)
   double *Vn = sm + C::S_VN;
   double *vxn = sm + C::S_VXN;
   double *kkt = sm + C::S_KKT;
@@ -832,10 +838,10 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     double *rec = sm + C::S_REC + cur * C::SREC_PAD;
     if (t > 0) // stream the next knot into the other buffer during this step
       ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::SREC_PAD,
-                     stage_b + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
+                     AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
     cur ^= 1;
     if (t >= 4) { // and pull the record of 4 knots ahead into L2 (one 128-byte line per lane)
-      const char *nxt = reinterpret_cast<const char *>(stage_b + (size_t)(t - 4) * C::SREC_PAD);
+      const char *nxt = reinterpret_cast<const char *>(AB2_STAGE_B + (size_t)(t - 4) * C::SREC_PAD);
       for (int o = lane * 128; o < C::SREC_PAD * 8; o += C::G * 128)
         prefetch_l2(nxt + o);
     }
@@ -929,8 +935,8 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
       }
     }
     ctx.sync();
-    double *fbt = fb_b + (size_t)t * NR * NX;
-    double *fft = ff_b + (size_t)t * NR;
+    double *fbt = AB2_FB_B + (size_t)t * NR * NX;
+    double *fft = AB2_FF_B + (size_t)t * NR;
     {
       double kz[NK];
       FastFactor<NK> F;
@@ -1045,13 +1051,13 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
               const double v = H[mt][nt][e];
               if (jj < NX) {
                 if (t == 0)
-                  Vxx_b[i + jj * NX] = v; // datas[0].Vxx is left unsymmetrised (A1)
+                  AB2_VXX_B[i + jj * NX] = v; // datas[0].Vxx is left unsymmetrised (A1)
                 if (i >= jj) {            // V' = lower triangle mirrored (:216 of the next step)
                   Vn[i * VS + jj] = v;
                   Vn[jj * VS + i] = v;
                 }
               } else if (jj == NX) {
-                vx_b[(size_t)t * NX + i] = v;
+                AB2_VX_B[(size_t)t * NX + i] = v;
                 vxn[i] = v;
               }
             }
@@ -1063,7 +1069,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
       ctx.async_fence(); // this lane's writes to V' become visible to the TMA store below
     ctx.sync();
     if (t > 0) { // symmetric Vxx_t, as the next step of the reference leaves it
-      double *Vt = Vxx_b + (size_t)t * NX * NX;
+      double *Vt = AB2_VXX_B + (size_t)t * NX * NX;
       if (C::VS == NX) { // V' is dense in shared memory: one TMA bulk store, no LDS/STG
         ctx.bulk_store(Vt, Vn, NX * NX);
       } else if (lane < NX) {
@@ -1078,6 +1084,11 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     ctx.sync();
   }
 }
+#undef AB2_STAGE_B
+#undef AB2_FF_B
+#undef AB2_FB_B
+#undef AB2_VXX_B
+#undef AB2_VX_B
 
 // ---------------------------------------------------------------------------
 // The sweep of one instance by one group.
@@ -1186,7 +1197,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
 
     // ---------------- stage knots N-1 .. 0: riccati-kernel.hxx:210-277
     if constexpr (C::MMA) {
-      stage_loop_mma<C>(ctx, p, sm, st, stage_b, ff_b, fb_b, Vxx_b, vx_b);
+      stage_loop_mma<C>(ctx, p, sm, st, inst);
     } else {
     constexpr int RS = C::RS;
     constexpr bool EV = C::EVEN;
