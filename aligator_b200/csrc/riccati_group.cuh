@@ -117,6 +117,9 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   static constexpr int WROWS = MMA ? 4 * KT : 0;
   static constexpr int SX = MMA ? fstride(8 * NT2) : 0;  // row stride of X / KK
   static constexpr int XROWS = MMA ? 4 * KT2 : 0;
+  // Vxx_t via a TMA bulk store straight from V' in shared memory: measured SLOWER than
+  // LDS.128+STG.128 (the proxy fence every lane must execute costs more than it saves).
+  static constexpr bool VXX_BULK = false;
   // stage record offsets (doubles) -- the reference's 11 buffers, concatenated
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + NX * NX;
@@ -760,6 +763,16 @@ AB2_D void bk_solve_vec_group(Ctx &ctx, const double *a, const int lda, const in
 }
 
 
+// 128-bit global store of two consecutive doubles (p 16-byte aligned).
+AB2_D void stg2(double *p, double x, double y) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<double2 *>(p) = make_double2(x, y);
+#else
+  p[0] = x;
+  p[1] = y;
+#endif
+}
+
 // 128-bit shared-memory store of two consecutive doubles (p 16-byte aligned).
 AB2_D void sts2(double *p, double x, double y) {
 #if defined(__CUDA_ARCH__)
@@ -1018,7 +1031,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
           }
         }
       }
-      if (C::VS == NX && t > 0)
+      if (C::VXX_BULK && t > 0)
         ctx.bulk_store_wait_read(); // the previous knot's Vxx store has finished reading V'
       AB2_UNROLL
       for (int mt = 0; mt < MTX; ++mt) {
@@ -1037,7 +1050,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
           }
         }
       }
-      if (C::VS == NX)
+      if (C::VXX_BULK)
         ctx.sync(); // (lane 0 waited above) nobody overwrites V' before the store has read it
       AB2_UNROLL
       for (int mt = 0; mt < MTX; ++mt) {
@@ -1065,21 +1078,29 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
         }
       }
     }
-    if (C::VS == NX && t > 0)
+    if (C::VXX_BULK && t > 0)
       ctx.async_fence(); // this lane's writes to V' become visible to the TMA store below
     ctx.sync();
     if (t > 0) { // symmetric Vxx_t, as the next step of the reference leaves it
       double *Vt = AB2_VXX_B + (size_t)t * NX * NX;
-      if (C::VS == NX) { // V' is dense in shared memory: one TMA bulk store, no LDS/STG
+      if (C::VXX_BULK) { // V' is dense in shared memory: one TMA bulk store, no LDS/STG
         ctx.bulk_store(Vt, Vn, NX * NX);
-      } else if (lane < NX) {
-        AB2_UNROLL
-        for (int i = 0; i < NX; ++i)
-          Vt[i + lane * NX] = Vn[lane * VS + i];
+      } else if (lane < NX) { // row `lane` of the symmetric V' = column `lane` of Vxx_t
+        if (C::EVEN && (VS % 2 == 0)) {
+          AB2_UNROLL
+          for (int i = 0; i < NX; i += 2) {
+            const D2 v = lds2(Vn + lane * VS + i);
+            stg2(Vt + i + lane * NX, v.x, v.y);
+          }
+        } else {
+          AB2_UNROLL
+          for (int i = 0; i < NX; ++i)
+            Vt[i + lane * NX] = Vn[lane * VS + i];
+        }
       }
     }
   }
-  if (C::VS == NX) { // the last store must have read V' before the initial stage reuses the buffers
+  if (C::VXX_BULK) { // the last store must have read V' before the initial stage reuses the buffers
     ctx.bulk_store_wait_read();
     ctx.sync();
   }
