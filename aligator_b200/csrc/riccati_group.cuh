@@ -120,6 +120,7 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   // Vxx_t via a TMA bulk store straight from V' in shared memory: measured SLOWER than
   // LDS.128+STG.128 (the proxy fence every lane must execute costs more than it saves).
   static constexpr bool VXX_BULK = false;
+  static constexpr int LUT_INTS = MMA ? 32 * (NT + NT * NT) : 0; // per-CTA table of per-lane constants
   // stage record offsets (doubles) -- the reference's 11 buffers, concatenated
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + NX * NX;
@@ -827,19 +828,21 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
   double *X = sm + C::S_XM;
   double *KKs = sm + C::S_KK;
 
-  // per-lane constants: record offsets of the logical columns 8t+g, and of H0's entries
-  int moff[NT];
+  // per-lane constants: record offsets of the logical columns 8t+g and of H0's entries.
+  // They live in a small per-CTA table in shared memory (identical for every warp of the
+  // CTA; each warp writes and reads only its own lanes' entries) instead of 12 registers
+  // that would be spilled to local memory, which has no L1 behind it in this kernel.
+  int *lut = ctx.cta_ints(); // [(NT + NT*NT)][32]
   AB2_UNROLL
   for (int t = 0; t < NT; ++t)
-    moff[t] = C::col_offset(8 * t + g);
-  unsigned h0p[NT][NT]; // two 16-bit record offsets per register (0xffff = structural zero)
+    lut[t * 32 + lane] = C::col_offset(8 * t + g);
   AB2_UNROLL
   for (int mt = 0; mt < NT; ++mt) {
     AB2_UNROLL
     for (int nt = 0; nt < NT; ++nt) {
       const int o0 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q);
       const int o1 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q + 1);
-      h0p[mt][nt] = (unsigned)(o0 & 0xffff) | ((unsigned)(o1 & 0xffff) << 16);
+      lut[(NT + mt * NT + nt) * 32 + lane] = (int)((unsigned)(o0 & 0xffff) | ((unsigned)(o1 & 0xffff) << 16));
     }
   }
   ctx.sync();
@@ -865,7 +868,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     for (int tt = 0; tt < NT; ++tt) {
       AB2_UNROLL
       for (int kt = 0; kt < KT; ++kt)
-        Mf[tt][kt] = rec[moff[tt] + 4 * kt + q];
+        Mf[tt][kt] = rec[lut[tt * 32 + lane] + 4 * kt + q];
     }
     // (1) W = V' M   (+ vx' on the affine column: vplus = vx' + V' f, :217-218)
     {
@@ -912,7 +915,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
       for (int nt = 0; nt < NT; ++nt) {
         AB2_UNROLL
         for (int e = 0; e < 2; ++e) {
-          const unsigned o = (h0p[mt][nt] >> (16 * e)) & 0xffffu;
+          const unsigned o = ((unsigned)lut[(NT + mt * NT + nt) * 32 + lane] >> (16 * e)) & 0xffffu;
           H[mt][nt][e] = (o != 0xffffu) ? rec[o != 0xffffu ? o : 0] : 0.0;
         }
       }

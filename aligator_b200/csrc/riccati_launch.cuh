@@ -22,6 +22,8 @@ template <int G, bool TMA> struct DevCtx {
   unsigned mask;
   uint32_t bar0; // shared address of this group's NBAR mbarriers
   uint32_t phase; // bit p = parity to wait for on barrier p
+  int *cta_lut;   // per-CTA scratch for per-lane constants (tensor-core step)
+  __device__ __forceinline__ int *cta_ints() const { return cta_lut; }
 
   __device__ __forceinline__ void sync() { __syncwarp(mask); }
 
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
   uint64_t *bars =
       reinterpret_cast<uint64_t *>(smem + (size_t)(WARPS * IPW) * group_doubles) + NBAR * group_in_cta;
   DevCtx<C::G, TMA> ctx;
+  ctx.cta_lut = reinterpret_cast<int *>(smem + (size_t)(WARPS * IPW) * group_doubles + (size_t)(WARPS * IPW) * NBAR);
   ctx.lane = lane32 % C::G;
   ctx.mask = (C::G == 32) ? 0xffffffffu : (((1u << C::G) - 1u) << (gsub * C::G));
   ctx.init(bars);
@@ -149,7 +152,7 @@ template <class C, int WARPS, int MAXREG, bool TMA>
 inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int *info) {
   constexpr int IPW = 32 / C::G;
   const int groups = WARPS * IPW;
-  const size_t smem = (size_t)groups * gd * sizeof(double) + (size_t)groups * 8 * NBAR;
+  const size_t smem = (size_t)groups * gd * sizeof(double) + (size_t)groups * 8 * NBAR + (size_t)C::LUT_INTS * 4;
   auto kern = riccati_sweep_kernel<C, WARPS, MAXREG, TMA>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)

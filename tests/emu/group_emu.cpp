@@ -16,6 +16,8 @@ struct HostCtx {
   int lane;
   std::barrier<> *bar;
   double *xa, *xb; // fragment exchange for the emulated mma (one slot per lane)
+  int *lutp;
+  int *cta_ints() const { return lutp; }
   void sync() { bar->arrive_and_wait(); }
   // mma.sync.m8n8k4 f64: lane = 4g+q holds a[g][q], b[q][g], d[g][2q], d[g][2q+1]
   void mma(double (&d)[2], double a, double b) {
@@ -53,10 +55,11 @@ template <class C> int run(const ab2::SweepParams &p) {
                            std::numeric_limits<double>::quiet_NaN());
     std::barrier<> bar(G);
     std::vector<double> xa(G), xb(G);
+    std::vector<int> lutv(C::LUT_INTS + 32);
     std::vector<std::thread> th;
     for (int l = 0; l < G; ++l)
       th.emplace_back([&, l] {
-        HostCtx ctx{l, &bar, xa.data(), xb.data()};
+        HostCtx ctx{l, &bar, xa.data(), xb.data(), lutv.data()};
         ab2::riccati_group_sweep<C>(ctx, p, inst, sm.data());
       });
     for (auto &t : th)
