@@ -196,8 +196,16 @@ template <int NX, int NU, int NC, int G>
 inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[3], cudaStream_t st, int *info) {
   using CS = Cfg<NX, NU, NC, G, false>;
   using CD = Cfg<NX, NU, NC, G, true>;
-  if (variant < 0)
-    variant = (G == 32 && NC == 0 && NX % 2 == 0) ? 7 : 6;
+  if (variant < 0) {
+    variant = 6;
+    if constexpr (G == 32 && NC == 0 && NX % 2 == 0) {
+      // 16 warps/SM (128 registers) needs <= 27 KB of shared memory per 2-warp CTA;
+      // larger states run the 168-register build (12 warps/SM, no spills).
+      const size_t smem2 = (size_t)2 * gd[2] * sizeof(double) + 2 * 8 * NBAR +
+                           (size_t)Cfg<NX, NU, NC, G, true, true, true>::LUT_INTS * 4;
+      variant = (smem2 + 1024) * 8 <= 227 * 1024 ? 7 : 8;
+    }
+  }
   if (variant == 1)
     return launch_one<CS, 4, 72, true>(p, gd[0], st, info);
   if (variant == 2)
