@@ -46,6 +46,7 @@ def build(verbose=False, force=False, ptxas_v=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, f) for f in ("riccati_group.cuh", "riccati_launch.cuh", "riccati_configs.h")]
     hdrs.append(os.path.join(PKG, "..", "include", "aligator_b200", "gar.h"))
+    hdrs_block = hdrs + [os.path.join(CSRC, f) for f in ("riccati_block.cuh", "riccati_block_launch.h")]
     extra = ["-Xptxas", "-v"] if ptxas_v else []
     jobs = []
     for (nx, nu, nc, g) in configs():
@@ -56,9 +57,12 @@ def build(verbose=False, force=False, ptxas_v=False):
                                               "-DAB2_G=%d" % g, "-c", src, "-o", obj]
         jobs.append((obj, cmd))
     src = os.path.join(CSRC, "gar_cuda.cu")
-    tag = _digest(hdrs + [src])
+    tag = _digest(hdrs_block + [src])
     obj = os.path.join(OBJ, "capi_%s.o" % tag)
     jobs.append((obj, [NVCC] + ARCH + FLAGS + ["-c", src, "-o", obj]))
+    src = os.path.join(CSRC, "block_kernel.cu")
+    obj = os.path.join(OBJ, "block_%s.o" % _digest(hdrs_block + [src], str(extra)))
+    jobs.append((obj, [NVCC] + ARCH + FLAGS + extra + ["-c", src, "-o", obj]))
     todo = [(o, c) for (o, c) in jobs if force or not os.path.exists(o)]
     logs = []
     if todo:

@@ -1,0 +1,150 @@
+// block_kernel.cu -- device context, kernel and launcher of the CTA-per-instance sweep
+// for run-time dimensions (riccati_block.cuh).  One CTA walks the whole horizon of one
+// instance; the stage records stream in by TMA bulk copies (two mbarrier-tracked parts),
+// the forward gains through a ring of up to 8 TMA-filled slots.
+#include <cuda_runtime.h>
+
+#include "riccati_block.cuh"
+#include "riccati_block_launch.h"
+#include "riccati_launch.cuh"
+
+namespace ab2 {
+
+struct BlockDevCtx {
+  int tid, nthreads, warp, lane, nwarps;
+  uint32_t bar0;  // shared address of the CTA's NBAR mbarriers
+  uint32_t phase; // bit p = parity to wait for on barrier p
+
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void mma(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+  }
+  __device__ __forceinline__ void init(uint64_t *bars) {
+    bar0 = smem_u32(bars);
+    phase = 0;
+    if (tid == 0) {
+      for (int b = 0; b < NBAR; ++b)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * b));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  // `nd` doubles (even, 16-byte aligned both sides) global -> shared; called by every
+  // thread after a CTA barrier that orders the last generic-proxy accesses to dst.
+  __device__ __forceinline__ void issue_copy(int part, double *dst, const double *src, int nd) {
+    if (tid == 0) {
+      const uint32_t bar = bar0 + 8 * part;
+      const uint32_t bytes = (uint32_t)nd * 8u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      const uint32_t CH = 32768u;
+      for (uint32_t o = 0; o < bytes; o += CH) {
+        const uint32_t n = bytes - o < CH ? bytes - o : CH;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(dst) + o),
+            "l"(reinterpret_cast<const char *>(src) + o), "r"(n), "r"(bar)
+            : "memory");
+      }
+    }
+  }
+  __device__ __forceinline__ void wait_copy(int part) {
+    const uint32_t bar = bar0 + 8 * part;
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\t"
+                   "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                   "selp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done)
+                   : "r"(bar), "r"((phase >> part) & 1u)
+                   : "memory");
+    }
+    phase ^= (1u << part);
+  }
+};
+
+__global__ void __launch_bounds__(256) riccati_block_kernel(const SweepParams p, const BlockDims d) {
+  extern __shared__ __align__(16) double smem[];
+  BlockDevCtx ctx;
+  ctx.tid = threadIdx.x;
+  ctx.nthreads = blockDim.x;
+  ctx.warp = threadIdx.x >> 5;
+  ctx.lane = threadIdx.x & 31;
+  ctx.nwarps = blockDim.x >> 5;
+  ctx.init(reinterpret_cast<uint64_t *>(smem + d.s_end));
+  for (int inst = blockIdx.x; inst < p.batch; inst += gridDim.x) {
+    riccati_block_sweep(ctx, p, d, inst, smem);
+    __syncthreads();
+  }
+}
+
+int block_threads(int nx, int nu, int nc, int nc0) {
+  const BlockDims d = make_block_dims(nx, nu, nc, nc0);
+  int need = nx + 1;
+  if (d.nk > need)
+    need = d.nk;
+  if (nx + nc0 > need)
+    need = nx + nc0;
+  if (d.nr > need)
+    need = d.nr;
+  if (need > 256)
+    return 0;
+  const int nchunk = (d.nt + BLK_CH - 1) / BLK_CH;
+  int warps = d.nt * nchunk; // work items of the largest product
+  if (warps > 8)
+    warps = 8;
+  const int wneed = (need + 31) / 32;
+  if (warps < wneed)
+    warps = wneed;
+  return 32 * warps;
+}
+
+size_t block_smem_bytes(int nx, int nu, int nc, int nc0) {
+  const BlockDims d = make_block_dims(nx, nu, nc, nc0);
+  return (size_t)d.s_end * sizeof(double) + 8 * NBAR;
+}
+
+bool block_supported(int nx, int nu, int nc, int nc0) {
+  return block_threads(nx, nu, nc, nc0) > 0 && block_smem_bytes(nx, nu, nc, nc0) <= (size_t)227 * 1024;
+}
+
+cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st, int *info) {
+  const BlockDims d = make_block_dims(nx, nu, nc, p.nc0);
+  const int threads = block_threads(nx, nu, nc, p.nc0);
+  const size_t smem = block_smem_bytes(nx, nu, nc, p.nc0);
+  cudaError_t e =
+      cudaFuncSetAttribute(riccati_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return e;
+  e = cudaFuncSetAttribute(riccati_block_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess)
+    return e;
+  int nb = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, riccati_block_kernel, threads, smem);
+  if (e != cudaSuccess)
+    return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms * (nb > 0 ? nb : 1); // persistent CTAs, instances strided over them
+  if (grid > p.batch)
+    grid = p.batch;
+  if (info) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, riccati_block_kernel);
+    info[0] = threads;
+    info[1] = (int)smem;
+    info[2] = threads;
+    info[3] = grid;
+    info[4] = fa.numRegs;
+    info[5] = nb;
+    return cudaSuccess;
+  }
+  riccati_block_kernel<<<grid, threads, smem, st>>>(p, d);
+  return cudaGetLastError();
+}
+
+} // namespace ab2

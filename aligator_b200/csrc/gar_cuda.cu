@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/aligator_b200/gar.h"
+#include "riccati_block_launch.h"
 #include "riccati_configs.h"
 #include "riccati_launch.cuh"
 
@@ -105,8 +106,12 @@ size_t ab2_gar_term_record_doubles(int nx, int nct) {
   return (size_t)nx * nx + nx + (size_t)nct * nx + nct;
 }
 int ab2_gar_supported(int nx, int nu, int nc, int nc0) {
+  if (nx < 1 || nu < 1 || nc < 0 || nc0 < 0)
+    return 0;
   const ab2::KernelEntry *k = ab2::find_kernel(nx, nu, nc);
-  return (k && nx + nc0 <= k->G) ? 1 : 0;
+  if (k && nx + nc0 <= k->G)
+    return 1; // compile-time shape, one warp (or part of one) per instance
+  return ab2::block_supported(nx, nu, nc, nc0) ? 2 : 0; // run-time shape, one CTA per instance
 }
 
 int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
@@ -115,12 +120,16 @@ int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
   const ab2_gar_dims &d = *dims;
   if (d.nx < 1 || d.nu < 1 || d.nc < 0 || d.nct < 0 || d.nc0 < 0 || d.horizon < 0 || d.batch < 1)
     return fail(AB2_ERR_INVALID, "bad dimensions");
+  // compile-time shapes run one warp (or part of one) per instance; every other shape runs
+  // the CTA-per-instance kernel with run-time dimensions (block_kernel.cu)
   const ab2::KernelEntry *k = ab2::find_kernel(d.nx, d.nu, d.nc);
-  if (!k)
-    return fail(AB2_ERR_UNSUPPORTED, "no kernel instantiation for (nx,nu,nc) = (" + std::to_string(d.nx) +
-                                         "," + std::to_string(d.nu) + "," + std::to_string(d.nc) + ")");
-  if (d.nx + d.nc0 > k->G)
-    return fail(AB2_ERR_UNSUPPORTED, "nx + nc0 exceeds the group size of this kernel");
+  if (k && d.nx + d.nc0 > k->G)
+    k = nullptr;
+  if (!k && !ab2::block_supported(d.nx, d.nu, d.nc, d.nc0))
+    return fail(AB2_ERR_UNSUPPORTED,
+                "(nx,nu,nc,nc0) = (" + std::to_string(d.nx) + "," + std::to_string(d.nu) + "," +
+                    std::to_string(d.nc) + "," + std::to_string(d.nc0) +
+                    ") does not fit one CTA (227 KB of shared memory, 256 rows)");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (d.device < 0 || d.device >= ndev)
@@ -129,10 +138,15 @@ int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
   auto *s = new ab2_gar_solver();
   s->d = d;
   s->k = k;
-  s->srec = k->srec_pad;
+  s->srec = (int)ab2_gar_stage_record_doubles(d.nx, d.nu, d.nc);
+  if (k && k->srec_pad != s->srec) {
+    delete s;
+    return fail(AB2_ERR_INVALID, "internal: record size mismatch");
+  }
   s->trec = (int)ab2_gar_term_record_doubles(d.nx, d.nct);
   s->nr = d.nu + d.nc + d.nx;
-  k->group_doubles(d.nc0, s->group_doubles);
+  if (k)
+    k->group_doubles(d.nc0, s->group_doubles);
   const int N = d.horizon, B = d.batch, nx = d.nx;
   auto setup = [&](int what, size_t rec, int knots) {
     s->out_rec[what] = rec;
@@ -214,8 +228,10 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
 int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t) {
   if (!s || !t)
     return fail(AB2_ERR_INVALID, "null argument");
-  if (t->variant < -1 || t->variant > 8)
-    return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..8");
+  if (t->variant < -1 || t->variant > 9)
+    return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..9");
+  if (t->variant == 9 && !ab2::block_supported(s->d.nx, s->d.nu, s->d.nc, s->d.nc0))
+    return fail(AB2_ERR_UNSUPPORTED, "variant 9 (CTA per instance) does not fit this shape");
   s->variant = t->variant;
   return AB2_OK;
 }
@@ -279,7 +295,10 @@ static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream
   s->p.mueq = mueq;
   s->p.do_bwd = bwd;
   s->p.do_fwd = fwd;
-  CUDA_TRY(s->k->launch(s->p, s->variant, s->group_doubles, (cudaStream_t)stream, nullptr));
+  if (s->k && s->variant != 9)
+    CUDA_TRY(s->k->launch(s->p, s->variant, s->group_doubles, (cudaStream_t)stream, nullptr));
+  else
+    CUDA_TRY(ab2::launch_block(s->p, s->d.nx, s->d.nu, s->d.nc, (cudaStream_t)stream, nullptr));
   s->launches += 1;
   if (bwd)
     s->have_backward = true;
@@ -396,7 +415,10 @@ int ab2_gar_kernel_info(const ab2_gar_solver *s, int *group_lanes, int *smem_byt
     return fail(AB2_ERR_INVALID, "null solver");
   int info[6] = {0, 0, 0, 0, 0, 0};
   CUDA_TRY(cudaSetDevice(s->d.device));
-  CUDA_TRY(s->k->launch(s->p, s->variant, s->group_doubles, 0, info));
+  if (s->k && s->variant != 9)
+    CUDA_TRY(s->k->launch(s->p, s->variant, s->group_doubles, 0, info));
+  else
+    CUDA_TRY(ab2::launch_block(s->p, s->d.nx, s->d.nu, s->d.nc, 0, info));
   if (group_lanes)
     *group_lanes = info[0];
   if (smem_bytes_per_cta)

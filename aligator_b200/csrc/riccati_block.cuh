@@ -1,0 +1,650 @@
+// riccati_block.cuh -- the sweep for ARBITRARY (run-time) dimensions: one CTA per
+// instance, every matrix in shared memory, the dense products of the knot step tiled
+// 8x8x4 on the FP64 tensor cores (DMMA) and spread over the CTA's warps.
+//
+// Serves the shapes the warp-per-instance kernels of riccati_group.cuh cannot hold:
+// large states (BASELINE config 5: nx = 56, nu = 22), constrained knots with
+// nu + nc > 32 rows in the reduced KKT matrix, and any (nx, nu, nc) that was not
+// instantiated at compile time.  Same mathematics, same reference citations
+// (gar/riccati-kernel.hxx:105-377, core/bunchkaufman.hpp) and the same logical column
+// order [A | f | B] as stage_loop_mma; the Bunch-Kaufman factorisation is the
+// cooperative bk_factor_group with one THREAD per matrix row.
+//
+// Compiles for the host as well (tests/emu/block_emu.cpp): a CTA is T std::threads.
+//
+// Ctx: tid, nthreads, warp, lane, nwarps; sync() = CTA barrier; mma(d, a, b) = one
+// warp-wide m8n8k4 f64 MMA; issue_copy(part, dst, src, nd) / wait_copy(part) = TMA bulk
+// copy global -> shared completing on mbarrier `part` (issued by one thread, waited by all).
+#pragma once
+
+#include "riccati_group.cuh"
+
+namespace ab2 {
+
+struct BlockDims {
+  int nx, nu, nc; // stage knots
+  int nk, nr, nj, mtx, kt, nt, nt2, kt2, njp;
+  int off_b, off_f, off_q, off_s, off_r, off_qv, off_rv, off_c, off_d, off_dv, srec_pad;
+  int split; // [0, split) = [A B f] (live until the closing products), [split, srec_pad) = the rest
+  int vs, vrows, sw, wrows, sh, sx, xrows;
+  int s_rec, s_vn, s_vxn, s_w, s_x, s_kk, s_y, s_h, s_kkt, s_dd, s_sd, s_int, s_end; // doubles
+  int fwd_ring, fwd_slot;
+};
+
+AB2_HD int blk_ev(int x) { return (x + 1) & ~1; }
+AB2_HD int blk_fstride(int n) { // smallest stride >= n that is 4 or 12 mod 16
+  int s = n;
+  while (s % 16 != 4 && s % 16 != 12)
+    ++s;
+  return s;
+}
+AB2_HD int blk_s8(int n) { // smallest stride >= n that is 8 mod 16
+  int s = n;
+  while (s % 16 != 8)
+    ++s;
+  return s;
+}
+
+// Layout shared by the host (sizing the launch) and the device.
+AB2_HD BlockDims make_block_dims(int nx, int nu, int nc, int nc0) {
+  BlockDims d;
+  d.nx = nx;
+  d.nu = nu;
+  d.nc = nc;
+  d.nk = nu + nc;
+  d.nr = nu + nc + nx;
+  d.nj = nx + 1 + nu;
+  d.mtx = (nx + 7) / 8;
+  d.kt = (nx + 3) / 4;
+  d.nt = (d.nj + 7) / 8;
+  d.nt2 = (nx + 1 + 7) / 8;
+  d.kt2 = (d.nk + 3) / 4;
+  d.njp = 8 * d.nt;
+  d.off_b = nx * nx;
+  d.off_f = d.off_b + nx * nu;
+  d.off_q = d.off_f + nx;
+  d.off_s = d.off_q + nx * nx;
+  d.off_r = d.off_s + nx * nu;
+  d.off_qv = d.off_r + nu * nu;
+  d.off_rv = d.off_qv + nx;
+  d.off_c = d.off_rv + nu;
+  d.off_d = d.off_c + nc * nx;
+  d.off_dv = d.off_d + nc * nu;
+  d.srec_pad = blk_ev(d.off_dv + nc);
+  d.split = (d.off_q % 2 == 0) ? d.off_q : d.srec_pad;
+  d.vs = blk_fstride(4 * d.kt);
+  d.vrows = 8 * d.mtx;
+  d.sw = blk_s8(d.njp);
+  d.wrows = 4 * d.kt;
+  d.sh = blk_s8(d.njp);
+  d.sx = blk_fstride(8 * d.nt2);
+  d.xrows = 4 * d.kt2;
+  int o = 0;
+  d.s_rec = o;
+  o += d.srec_pad + 16; // slack: fragment loads of padded rows read (and discard) past the record
+  d.s_vn = o;
+  o += blk_ev(d.vrows * d.vs);
+  d.s_vxn = o;
+  o += blk_ev(nx);
+  d.s_h = o;
+  o += blk_ev(d.njp * d.sh);
+  const int xsz = blk_ev(d.xrows * d.sx);
+  d.s_w = o; // W; once consumed, the same space holds X, KK and the solve scratch Y
+  d.s_x = o;
+  d.s_kk = o + xsz;
+  {
+    // the solve scratch Y lives in the control rows of Hs (dead once X and the KKT matrix
+    // are built) when it fits there, else behind KK
+    const bool y_in_h = xsz <= (d.njp - nx - 1) * d.sh;
+    d.s_y = y_in_h ? d.s_h + (nx + 1) * d.sh : o + 2 * xsz;
+    const int a = blk_ev(d.wrows * d.sw), b = (y_in_h ? 2 : 3) * xsz;
+    o += a > b ? a : b;
+  }
+  d.s_kkt = o;
+  o += blk_ev(d.nk * d.nk);
+  d.s_dd = o;
+  o += blk_ev(d.nk);
+  d.s_sd = o;
+  o += blk_ev(d.nk);
+  d.s_int = o;
+  o += blk_ev(d.nk + 1);
+  // the initial-stage saddle system overlays everything: K0 n0*n0, 5 vectors, 2*n0 ints
+  const int n0 = nx + nc0;
+  const int k0 = n0 * n0 + 6 * n0 + 2;
+  d.s_end = blk_ev(o > k0 ? o : k0);
+  // forward: ring of fb records + two state vectors
+  d.fwd_slot = blk_ev(d.nr * nx);
+  int ring = (d.s_end - 2 * blk_ev(nx)) / d.fwd_slot;
+  if (ring < 1) {
+    ring = 1;
+    d.s_end = d.fwd_slot + 2 * blk_ev(nx);
+  }
+  d.fwd_ring = ring > 8 ? 8 : ring;
+  return d;
+}
+
+AB2_D int blk_col_offset(const BlockDims &d, int jp) { // logical column jp of [A | f | B]
+  if (jp < d.nx)
+    return jp * d.nx;
+  if (jp == d.nx)
+    return d.off_f;
+  if (jp <= d.nx + d.nu)
+    return d.off_b + (jp - d.nx - 1) * d.nx;
+  return d.srec_pad; // padding column: the zeroed slack behind the record
+}
+AB2_D int blk_h0_offset(const BlockDims &d, int ip, int jp) { // -1 = structural zero
+  const int nx = d.nx, nu = d.nu;
+  const int ti = ip < nx ? 0 : (ip == nx ? 1 : (ip <= nx + nu ? 2 : 3));
+  const int tj = jp < nx ? 0 : (jp == nx ? 1 : (jp <= nx + nu ? 2 : 3));
+  const int ci = ip - nx - 1, cj = jp - nx - 1;
+  if (ti == 0 && tj == 0)
+    return d.off_q + jp * nx + ip;
+  if (ti == 0 && tj == 2)
+    return d.off_s + cj * nx + ip;
+  if (ti == 2 && tj == 0)
+    return d.off_s + ci * nx + jp;
+  if (ti == 2 && tj == 2)
+    return d.off_r + cj * nu + ci;
+  if (ti == 0 && tj == 1)
+    return d.off_qv + ip;
+  if (ti == 2 && tj == 1)
+    return d.off_rv + ci;
+  return -1;
+}
+
+// The whole CTA seen as one "group" by the cooperative Bunch-Kaufman routines
+// (one thread per matrix row, CTA-wide barrier).
+template <class Ctx> struct CtaAsGroup {
+  Ctx &c;
+  int lane;
+  AB2_D void sync() { c.sync(); }
+};
+
+// Per-thread solve of one right-hand-side column with the factor left by
+// bk_factor_group (run-time n; same sequence as bk_solve_column).
+// rhs/work/sol: column pointers, rows `stride` apart; the result is -(KKT^-1 rhs).
+AB2_D void bk_solve_column_rt(const double *a, const int n, const double *dd, const double *sd,
+                              const int *perm, const int *kind, const double *rhs, double *work,
+                              double *sol, const int stride) {
+  for (int i = 0; i < n; ++i)
+    work[i * stride] = rhs[perm[i] * stride];
+  for (int c = 0; c < n; ++c) {
+    const double xc = work[c * stride];
+    for (int i = c + 1; i < n; ++i)
+      work[i * stride] -= a[i + c * n] * xc;
+  }
+  for (int k = 0; k < n; ++k) {
+    const int kd = kind[k];
+    if (kd == 0) {
+      work[k * stride] *= dd[k];
+    } else if (kd == 1 && k + 1 < n) {
+      const double xk = work[k * stride], xk1 = work[(k + 1) * stride], s = sd[k];
+      work[k * stride] = xk * dd[k] + xk1 * s;
+      work[(k + 1) * stride] = xk1 * dd[k + 1] + xk * s;
+    }
+  }
+  for (int c = n - 1; c >= 0; --c) {
+    double xc = work[c * stride];
+    for (int i = c + 1; i < n; ++i)
+      xc -= a[i + c * n] * work[i * stride];
+    work[c * stride] = xc;
+  }
+  for (int i = 0; i < n; ++i)
+    sol[perm[i] * stride] = -work[i * stride];
+}
+
+// The same solve with the column held in registers (n <= NMAX; every loop fully unrolled
+// and predicated on the run-time n): the loads of the factor are independent of the
+// arithmetic, so they pipeline instead of serialising on the shared-memory round trip.
+template <int NMAX>
+AB2_D void bk_solve_column_reg(const double *a, const int n, const double *dd, const double *sd,
+                               const int *perm, const int *kind, const double *rhs, double *sol,
+                               const int stride) {
+  double x[NMAX];
+  AB2_UNROLL
+  for (int i = 0; i < NMAX; ++i)
+    x[i] = (i < n) ? rhs[perm[i < n ? i : 0] * stride] : 0.0;
+  AB2_UNROLL
+  for (int c = 0; c < NMAX; ++c) {
+    if (c < n) {
+      AB2_UNROLL
+      for (int i = c + 1; i < NMAX; ++i)
+        if (i < n)
+          x[i] -= a[i + c * n] * x[c];
+    }
+  }
+  AB2_UNROLL
+  for (int k = 0; k < NMAX; ++k) {
+    if (k < n) {
+      const int kd = kind[k];
+      if (kd == 0) {
+        x[k] *= dd[k];
+      } else if (kd == 1 && k + 1 < NMAX) {
+        const int k1 = (k + 1 < NMAX) ? k + 1 : k;
+        const double xk = x[k], xk1 = x[k1], s = sd[k];
+        x[k] = xk * dd[k] + xk1 * s;
+        x[k1] = xk1 * dd[k1] + xk * s;
+      }
+    }
+  }
+  AB2_UNROLL
+  for (int c = NMAX - 1; c >= 0; --c) {
+    if (c < n) {
+      AB2_UNROLL
+      for (int i = c + 1; i < NMAX; ++i)
+        if (i < n)
+          x[c] -= a[i + c * n] * x[i];
+    }
+  }
+  AB2_UNROLL
+  for (int i = 0; i < NMAX; ++i)
+    if (i < n)
+      sol[perm[i] * stride] = -x[i];
+}
+
+constexpr int BLK_CH = 4; // n-tiles accumulated together by one warp (one work item)
+
+// ---------------------------------------------------------------------------
+// The sweep of one instance by one CTA.
+// ---------------------------------------------------------------------------
+template <class Ctx>
+AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &d, const int inst,
+                               double *__restrict__ sm) {
+  const int nx = d.nx, nu = d.nu, nc = d.nc, nk = d.nk, nr = d.nr;
+  const int tid = ctx.tid, T = ctx.nthreads, warp = ctx.warp, lane = ctx.lane, NW = ctx.nwarps;
+  const int g = lane >> 2, q = lane & 3;
+  const int N = p.N, nct = p.nct, nc0 = p.nc0;
+  const double mueq = p.mueq;
+
+  double *rec = sm + d.s_rec;
+  double *Vn = sm + d.s_vn;
+  double *vxn = sm + d.s_vxn;
+  double *Hs = sm + d.s_h;
+  double *Wsm = sm + d.s_w;
+  double *X = sm + d.s_x;
+  double *KKs = sm + d.s_kk;
+  double *Ys = sm + d.s_y;
+  double *kkt = sm + d.s_kkt;
+  double *dd = sm + d.s_dd;
+  double *sd = sm + d.s_sd;
+  int *perm = reinterpret_cast<int *>(sm + d.s_int);
+  int *kind = perm + nk;
+
+  const double *stage_b = p.stage + (size_t)inst * N * d.srec_pad;
+  double *ff_b = p.ff + (size_t)inst * N * nr;
+  double *fb_b = p.fb + (size_t)inst * N * nr * nx;
+  double *Vxx_b = p.Vxx + (size_t)inst * (N + 1) * nx * nx;
+  double *vx_b = p.vx + (size_t)inst * (N + 1) * nx;
+  CtaAsGroup<Ctx> grp{ctx, tid};
+  const bool two_parts = d.split < d.srec_pad;
+
+  if (p.do_bwd) {
+    int st = ST_OK;
+    if (N > 0) {
+      const double *src = stage_b + (size_t)(N - 1) * d.srec_pad;
+      ctx.issue_copy(0, rec, src, d.split);
+      if (two_parts)
+        ctx.issue_copy(1, rec + d.split, src + d.split, d.srec_pad - d.split);
+    }
+    for (int i = tid; i < d.vrows * d.vs; i += T)
+      Vn[i] = 0.0;
+    for (int i = tid; i < 16; i += T)
+      rec[d.srec_pad + i] = 0.0; // the slack behind the record
+    ctx.sync();
+    // ---------------- terminal knot (nu = 0): riccati-kernel.hxx:146-149,175-183
+    {
+      const int trec = nx * nx + nx + nct * nx + nct;
+      const double *tr = p.term + (size_t)inst * trec;
+      const double *Qt = tr, *qt = tr + nx * nx, *Ct = qt + nx, *dt = Ct + (size_t)nct * nx;
+      double *VN = Vxx_b + (size_t)N * nx * nx;
+      for (int m = tid; m < nct * nx; m += T) { // Z = C / mu (stored row-major nct x nx)
+        const int r = m / nx, j = m % nx;
+        p.fbT[(size_t)inst * nct * nx + m] = Ct[r + (size_t)j * nct] / mueq;
+      }
+      for (int m = tid; m < nct; m += T)
+        p.ffT[(size_t)inst * nct + m] = dt[m] / mueq;
+      for (int e = tid; e < nx * nx; e += T) { // Vxx = Q + C^T Z
+        const int i = e % nx, j = e / nx;
+        double acc = 0.0;
+        for (int m = 0; m < nct; ++m)
+          acc += Ct[m + (size_t)i * nct] * (Ct[m + (size_t)j * nct] / mueq);
+        const double s = Qt[i + j * nx] + acc;
+        VN[i + j * nx] = s;
+        if (i >= j) {
+          Vn[i * d.vs + j] = s;
+          Vn[j * d.vs + i] = s;
+        }
+      }
+      for (int i = tid; i < nx; i += T) { // vx = q + C^T z
+        double acc = 0.0;
+        for (int m = 0; m < nct; ++m)
+          acc += Ct[m + (size_t)i * nct] * (dt[m] / mueq);
+        const double s = qt[i] + acc;
+        vx_b[(size_t)N * nx + i] = s;
+        vxn[i] = s;
+      }
+      ctx.sync();
+      if (N > 0) // symmetrised by the step N-1 of the reference (A1)
+        for (int e = tid; e < nx * nx; e += T)
+          VN[(e % nx) + (e / nx) * nx] = Vn[(e / nx) * d.vs + (e % nx)];
+    }
+
+    // ---------------- stage knots N-1 .. 0: riccati-kernel.hxx:210-277
+    const int nchunk = (d.nt + BLK_CH - 1) / BLK_CH;
+    const int nchunk2 = (d.nt2 + BLK_CH - 1) / BLK_CH;
+    for (int t = N - 1; t >= 0; --t) {
+      double *fbt = fb_b + (size_t)t * nr * nx;
+      double *fft = ff_b + (size_t)t * nr;
+      ctx.wait_copy(0);
+      // (1) W = V' M (+ vx' on the affine column), :216-224.  Work item = (m-tile, chunk).
+      for (int it = warp; it < d.mtx * nchunk; it += NW) {
+        const int mt = it / nchunk, n0 = (it % nchunk) * BLK_CH;
+        double acc[BLK_CH][2];
+        int moff[BLK_CH];
+        AB2_UNROLL
+        for (int c = 0; c < BLK_CH; ++c) {
+          acc[c][0] = acc[c][1] = 0.0;
+          moff[c] = blk_col_offset(d, 8 * (n0 + c) + g);
+        }
+        for (int kt = 0; kt < d.kt; ++kt) {
+          const int kr = 4 * kt + q;
+          const double va = Vn[(8 * mt + g) * d.vs + kr];
+          AB2_UNROLL
+          for (int c = 0; c < BLK_CH; ++c)
+            if (n0 + c < d.nt) { // warp-uniform
+              const double mb = rec[moff[c] + (moff[c] == d.srec_pad ? 0 : kr)];
+              ctx.mma(acc[c], va, (kr < nx) ? mb : 0.0);
+            }
+        }
+        const int i = 8 * mt + g;
+        AB2_UNROLL
+        for (int c = 0; c < BLK_CH; ++c)
+          if (n0 + c < d.nt && i < nx) {
+            const int jp = 8 * (n0 + c) + 2 * q;
+            if (jp == nx)
+              acc[c][0] += vxn[i];
+            if (jp + 1 == nx)
+              acc[c][1] += vxn[i];
+            sts2(Wsm + i * d.sw + jp, acc[c][0], acc[c][1]);
+          }
+      }
+      ctx.sync();
+      if (two_parts)
+        ctx.wait_copy(1);
+      // (2) H = H0 + M^T W  -> Hs, :226-241
+      for (int it = warp; it < d.nt * nchunk; it += NW) {
+        const int mt = it / nchunk, n0 = (it % nchunk) * BLK_CH;
+        double acc[BLK_CH][2];
+        AB2_UNROLL
+        for (int c = 0; c < BLK_CH; ++c) {
+          AB2_UNROLL
+          for (int e = 0; e < 2; ++e) {
+            const int o = (n0 + c < d.nt) ? blk_h0_offset(d, 8 * mt + g, 8 * (n0 + c) + 2 * q + e) : -1;
+            const double hv = rec[o >= 0 ? o : 0];
+            acc[c][e] = (o >= 0) ? hv : 0.0;
+          }
+        }
+        const int mo = blk_col_offset(d, 8 * mt + g);
+        for (int kt = 0; kt < d.kt; ++kt) {
+          const int kr = 4 * kt + q;
+          const double mv = rec[mo + (mo == d.srec_pad ? 0 : kr)];
+          const double ma = (kr < nx) ? mv : 0.0;
+          AB2_UNROLL
+          for (int c = 0; c < BLK_CH; ++c)
+            if (n0 + c < d.nt) {
+              const double wb = Wsm[(kr < nx ? kr : 0) * d.sw + 8 * (n0 + c) + g];
+              ctx.mma(acc[c], ma, (kr < nx) ? wb : 0.0);
+            }
+        }
+        AB2_UNROLL
+        for (int c = 0; c < BLK_CH; ++c)
+          if (n0 + c < d.nt)
+            sts2(Hs + (8 * mt + g) * d.sh + 8 * (n0 + c) + 2 * q, acc[c][0], acc[c][1]);
+      }
+      ctx.sync();
+      // (3) X = [Shat^T rhat; C d] (nk rows, columns 0..nx) and the KKT matrix, :232-257
+      for (int e = tid; e < nk * (nx + 1); e += T) {
+        const int c = e / (nx + 1), j = e % (nx + 1);
+        double v;
+        if (c < nu)
+          v = Hs[(nx + 1 + c) * d.sh + j];
+        else
+          v = (j < nx) ? rec[d.off_c + j * nc + (c - nu)] : rec[d.off_dv + (c - nu)];
+        X[c * d.sx + j] = v;
+      }
+      for (int e = tid; e < nk * nk; e += T) {
+        const int r = e % nk, c = e / nk;
+        double v = 0.0;
+        if (r < nu && c < nu)
+          v = Hs[(nx + 1 + r) * d.sh + (nx + 1 + c)];
+        else if (r >= nu && c < nu)
+          v = rec[d.off_d + c * nc + (r - nu)];
+        else if (r >= nu && c >= nu)
+          v = (r == c) ? -mueq : 0.0;
+        kkt[r + c * nk] = v;
+      }
+      ctx.sync();
+      // the tail of the record (cost blocks, C, D, d) is consumed: fetch the next knot's
+      if (two_parts && t > 0) {
+        const double *src = stage_b + (size_t)(t - 1) * d.srec_pad;
+        ctx.issue_copy(1, rec + d.split, src + d.split, d.srec_pad - d.split);
+      }
+      if (!bk_factor_group<8>(grp, kkt, nk, nk, dd, sd, perm, kind))
+        st |= ST_STAGE_FACTOR_FAILED;
+      if (tid <= nx) { // column tid of [K k; Z z] = -KKT^-1 X[:, tid]
+        if (nk <= 8)
+          bk_solve_column_reg<8>(kkt, nk, dd, sd, perm, kind, X + tid, KKs + tid, d.sx);
+        else if (nk <= 16)
+          bk_solve_column_reg<16>(kkt, nk, dd, sd, perm, kind, X + tid, KKs + tid, d.sx);
+        else if (nk <= 32)
+          bk_solve_column_reg<32>(kkt, nk, dd, sd, perm, kind, X + tid, KKs + tid, d.sx);
+        else
+          bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, X + tid, Ys + tid, KKs + tid, d.sx);
+      }
+      ctx.sync();
+      for (int e = tid; e < nk * nx; e += T) // gains K, Z (row-major nk x nx)
+        fbt[e] = KKs[(e / nx) * d.sx + (e % nx)];
+      for (int c = tid; c < nk; c += T)
+        fft[c] = KKs[c * d.sx + nx];
+      // (4) [Ahat a] = [A f] + B KK (:266-267) and (5) [Vxx vx] = [Qhat qhat] + X^T KK (:270-277)
+      for (int it = warp; it < d.mtx * nchunk2; it += NW) {
+        const int mt = it / nchunk2, n0 = (it % nchunk2) * BLK_CH;
+        const int i = 8 * mt + g, ic = i < nx ? i : 0;
+        double EA[BLK_CH][2], VV[BLK_CH][2];
+        AB2_UNROLL
+        for (int c = 0; c < BLK_CH; ++c) {
+          AB2_UNROLL
+          for (int e = 0; e < 2; ++e) {
+            const int jj = 8 * (n0 + c) + 2 * q + e;
+            const bool in = (n0 + c < d.nt2) && i < nx && jj <= nx;
+            const int jc = in ? jj : 0;
+            const double ev = rec[blk_col_offset(d, jc) + ic];
+            const double hv = Hs[ic * d.sh + jc];
+            EA[c][e] = in ? ev : 0.0;
+            VV[c][e] = in ? hv : 0.0;
+          }
+        }
+        for (int k2 = 0; k2 < d.kt2; ++k2) {
+          const int c4 = 4 * k2 + q;
+          const double bv = rec[d.off_b + (c4 < nu ? c4 : 0) * nx + ic];
+          const double bf = (c4 < nu && i < nx) ? bv : 0.0;
+          const double xr = X[(c4 < nk ? c4 : 0) * d.sx + ic];
+          const double xf = (c4 < nk && i < nx) ? xr : 0.0;
+          AB2_UNROLL
+          for (int c = 0; c < BLK_CH; ++c)
+            if (n0 + c < d.nt2) {
+              const int col = 8 * (n0 + c) + g;
+              const double kv = KKs[(c4 < nk ? c4 : 0) * d.sx + (col <= nx ? col : 0)];
+              const double kf = (c4 < nk && col <= nx) ? kv : 0.0;
+              ctx.mma(EA[c], bf, kf);
+              ctx.mma(VV[c], xf, kf);
+            }
+        }
+        if (i < nx) {
+          AB2_UNROLL
+          for (int c = 0; c < BLK_CH; ++c)
+            if (n0 + c < d.nt2) {
+              AB2_UNROLL
+              for (int e = 0; e < 2; ++e) {
+                const int jj = 8 * (n0 + c) + 2 * q + e;
+                if (jj < nx) {
+                  fbt[(nk + i) * nx + jj] = EA[c][e];
+                  if (t == 0)
+                    Vxx_b[i + jj * nx] = VV[c][e]; // datas[0].Vxx is left unsymmetrised (A1)
+                  if (i >= jj) { // V' = lower triangle mirrored (:216 of the next step)
+                    Vn[i * d.vs + jj] = VV[c][e];
+                    Vn[jj * d.vs + i] = VV[c][e];
+                  }
+                } else if (jj == nx) {
+                  fft[nk + i] = EA[c][e];
+                  vx_b[(size_t)t * nx + i] = VV[c][e];
+                  vxn[i] = VV[c][e];
+                }
+              }
+            }
+        }
+      }
+      ctx.sync();
+      if (t > 0) {
+        const double *src = stage_b + (size_t)(t - 1) * d.srec_pad;
+        ctx.issue_copy(0, rec, src, d.split);
+        double *Vt = Vxx_b + (size_t)t * nx * nx; // symmetric Vxx_t, as the next step leaves it
+        for (int e = tid; e < nx * nx; e += T)
+          Vt[e] = Vn[(e / nx) * d.vs + (e % nx)];
+      }
+    }
+
+    // ---------------- initial stage: proximal-riccati.hxx:42-55 (nth = 0)
+    {
+      const int n0 = nx + nc0;
+      double *K0 = sm; // n0 x n0 column-major (overlays the stage buffers)
+      double *b0 = K0 + n0 * n0;
+      double *x0w = b0 + n0;
+      double *dd0 = x0w + n0;
+      double *sd0 = dd0 + n0;
+      double *o0 = sd0 + n0;
+      int *perm0 = reinterpret_cast<int *>(o0 + n0);
+      int *kind0 = perm0 + n0;
+      ctx.sync(); // Vxx_0 / vx_0 of this instance are in global memory, written by this CTA
+      const double *G0 = p.G0 + (size_t)inst * nc0 * nx;
+      const double *g0 = p.g0 + (size_t)inst * nc0;
+      for (int e = tid; e < n0 * n0; e += T) {
+        const int i = e % n0, j = e / n0;
+        double v = 0.0;
+        if (i >= j) {
+          if (i < nx)
+            v = Vxx_b[i + j * nx]; // lower triangle of Vxx_0
+          else if (j < nx)
+            v = G0[(i - nx) + (size_t)j * nc0];
+        }
+        K0[e] = v;
+      }
+      for (int i = tid; i < n0; i += T)
+        b0[i] = (i < nx) ? -vx_b[i] : -g0[i - nx];
+      ctx.sync();
+      if (!bk_factor_group<8>(grp, K0, n0, n0, dd0, sd0, perm0, kind0))
+        st |= ST_INIT_FACTOR_FAILED;
+      bk_solve_vec_group(grp, K0, n0, n0, dd0, sd0, perm0, kind0, b0, x0w, o0);
+      for (int i = tid; i < n0; i += T)
+        p.kkt0[(size_t)inst * n0 + i] = o0[i];
+      ctx.sync();
+    }
+    if (tid == 0)
+      p.status[inst] = st;
+  }
+
+  // ---------------- forward rollout: riccati-kernel.hxx:196-207, 315-377
+  if (p.do_fwd) {
+    const int n0 = nx + nc0;
+    const double *k0 = p.kkt0 + (size_t)inst * n0;
+    double *xs_b = p.xs + (size_t)inst * (N + 1) * nx;
+    double *us_b = p.us + (size_t)inst * N * nu;
+    double *vs_b = p.vs + (size_t)inst * N * nc;
+    double *lb_b = p.lbdas + (size_t)inst * N * nx;
+    const int RING = d.fwd_ring, FS = d.fwd_slot;
+    const bool bulk = (nr * nx) % 2 == 0;
+    double *ring = sm;
+    double *xc = sm + RING * FS;
+    double *xnx = xc + blk_ev(nx);
+    ctx.sync();
+    auto fill_slot = [&](int s, int t) { // fb record of knot t -> ring slot s
+      if (bulk) {
+        ctx.issue_copy(s, ring + s * FS, fb_b + (size_t)t * nr * nx, nr * nx);
+      } else {
+        for (int i2 = tid; i2 < nr * nx; i2 += T)
+          ring[s * FS + i2] = fb_b[(size_t)t * nr * nx + i2];
+      }
+    };
+    for (int s = 0; s < RING && s < N; ++s)
+      fill_slot(s, s);
+    for (int i = tid; i < nx; i += T) {
+      const double v = k0[i];
+      xc[i] = v;
+      xs_b[i] = v;
+    }
+    for (int m = tid; m < nc0; m += T)
+      p.lbd0[(size_t)inst * nc0 + m] = k0[nx + m];
+    // Pass 1: x_{t+1} = a + Ahat x_t (and u, v): thread r owns gain row r (nr <= T).
+    double gff = (tid < nr && N > 0) ? ff_b[tid] : 0.0;
+    ctx.sync();
+    for (int t = 0; t < N; ++t) {
+      const int s = t % RING;
+      if (bulk)
+        ctx.wait_copy(s);
+      const double *slot = ring + s * FS;
+      if (tid < nr) {
+        const int r = tid;
+        double s0 = gff, s1 = 0.0;
+        int c = 0;
+        for (; c + 1 < nx; c += 2) {
+          s0 += slot[r * nx + c] * xc[c];
+          s1 += slot[r * nx + c + 1] * xc[c + 1];
+        }
+        if (c < nx)
+          s0 += slot[r * nx + c] * xc[c];
+        const double sv = s0 + s1;
+        if (r < nu)
+          us_b[(size_t)t * nu + r] = sv;
+        else if (r < nk)
+          vs_b[(size_t)t * nc + (r - nu)] = sv;
+        else {
+          xnx[r - nk] = sv;
+          xs_b[(size_t)(t + 1) * nx + (r - nk)] = sv;
+        }
+        gff = (t + 1 < N) ? ff_b[(size_t)(t + 1) * nr + r] : 0.0;
+      }
+      double *tmp = xc;
+      xc = xnx;
+      xnx = tmp;
+      ctx.sync(); // x_{t+1} visible; everyone is done with x_t and with this slot
+      if (t + RING < N)
+        fill_slot(s, t + RING);
+    }
+    // Pass 2: lbda_{t+1} = vx_{t+1} + Vxx_{t+1} x_{t+1}: independent over knots
+    // (Vxx_{t+1} is symmetric: row i = column i, contiguous).
+    for (int e = tid; e < N * nx; e += T) {
+      const int tt = e / nx, i = e % nx;
+      const double *vcol = Vxx_b + ((size_t)(tt + 1) * nx + i) * nx;
+      const double *xr = xs_b + (size_t)(tt + 1) * nx;
+      double s0 = vx_b[(size_t)(tt + 1) * nx + i], s1 = 0.0;
+      int c = 0;
+      for (; c + 1 < nx; c += 2) {
+        s0 += vcol[c] * xr[c];
+        s1 += vcol[c + 1] * xr[c + 1];
+      }
+      if (c < nx)
+        s0 += vcol[c] * xr[c];
+      lb_b[(size_t)tt * nx + i] = s0 + s1;
+    }
+    // terminal multipliers v_N = z + Z x_N
+    for (int m = tid; m < nct; m += T) {
+      double s = p.ffT[(size_t)inst * nct + m];
+      for (int c = 0; c < nx; ++c)
+        s += p.fbT[(size_t)inst * nct * nx + (size_t)m * nx + c] * xc[c];
+      p.vsT[(size_t)inst * nct + m] = s;
+    }
+    ctx.sync();
+  }
+}
+
+} // namespace ab2

@@ -285,7 +285,10 @@ template <int N, bool ALIGNED> AB2_D double dot_bcast(const double *row, const d
 //   perm[i]  = original index now at position i  (the composed interchanges).
 // Returns false where the reference reports NumericalIssue (:58-59).
 // ---------------------------------------------------------------------------
-template <class Ctx>
+// CHUNK > 1: the trailing-row updates fetch CHUNK operand pairs before storing any result
+// (the stores to the row would otherwise serialise the loop on possible aliasing); used by
+// the CTA-per-instance kernel, whose matrices are large.
+template <int CHUNK = 1, class Ctx>
 AB2_D bool bk_factor_group(Ctx &ctx, double *a, const int lda, const int n,
                             double *dd, double *sd, int *perm, int *kind) {
   const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
@@ -387,9 +390,26 @@ AB2_D bool bk_factor_group(Ctx &ctx, double *a, const int lda, const int n,
         kind[k] = 0;
       }
       ctx.sync(); // S2
-      if (lane > k && lane < n)
-        for (int j = k + 1; j <= lane; ++j)
-          A_(lane, j) -= A_(j, k) * xi;
+      if (lane > k && lane < n) {
+        if constexpr (CHUNK > 1) {
+          for (int j0 = k + 1; j0 <= lane; j0 += CHUNK) {
+            double l[CHUNK], r[CHUNK];
+            AB2_UNROLL
+            for (int u = 0; u < CHUNK; ++u) {
+              const int j = (j0 + u <= lane) ? j0 + u : lane;
+              l[u] = A_(j, k);
+              r[u] = A_(lane, j);
+            }
+            AB2_UNROLL
+            for (int u = 0; u < CHUNK; ++u)
+              if (j0 + u <= lane)
+                A_(lane, j0 + u) = r[u] - l[u] * xi;
+          }
+        } else {
+          for (int j = k + 1; j <= lane; ++j)
+            A_(lane, j) -= A_(j, k) * xi;
+        }
+      }
     } else {
       // 2x2 pivot on (k, k+1): a11 = akk, a22 = aii, a21 = the column-k entry
       // that was at row imax (cval); identical whether or not rows moved.
@@ -419,9 +439,27 @@ AB2_D bool bk_factor_group(Ctx &ctx, double *a, const int lda, const int n,
         A_(k + 1, k) = 0.0;
       }
       ctx.sync(); // S2
-      if (lane > k + 1 && lane < n)
-        for (int j = k + 2; j <= lane; ++j)
-          A_(lane, j) -= x0 * A_(j, k) + x1 * A_(j, k + 1);
+      if (lane > k + 1 && lane < n) {
+        if constexpr (CHUNK > 1) {
+          for (int j0 = k + 2; j0 <= lane; j0 += CHUNK) {
+            double l0[CHUNK], l1[CHUNK], r[CHUNK];
+            AB2_UNROLL
+            for (int u = 0; u < CHUNK; ++u) {
+              const int j = (j0 + u <= lane) ? j0 + u : lane;
+              l0[u] = A_(j, k);
+              l1[u] = A_(j, k + 1);
+              r[u] = A_(lane, j);
+            }
+            AB2_UNROLL
+            for (int u = 0; u < CHUNK; ++u)
+              if (j0 + u <= lane)
+                A_(lane, j0 + u) = r[u] - (x0 * l0[u] + x1 * l1[u]);
+          }
+        } else {
+          for (int j = k + 2; j <= lane; ++j)
+            A_(lane, j) -= x0 * A_(j, k) + x1 * A_(j, k + 1);
+        }
+      }
     }
     ctx.sync(); // S3: trailing block complete before the next search
     k += kstep;

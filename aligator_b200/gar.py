@@ -90,7 +90,9 @@ def term_record_doubles(nx, nct):
 
 
 def supported(nx, nu, nc, nc0):
-    return bool(lib().ab2_gar_supported(nx, nu, nc, nc0))
+    """0: not served; 1: compile-time shape (warp per instance); 2: run-time shape (CTA per
+    instance, csrc/riccati_block.cuh)."""
+    return int(lib().ab2_gar_supported(nx, nu, nc, nc0))
 
 
 def _ptr(a):

@@ -34,6 +34,7 @@ CONFIGS = {
     "c1": (6, 3, 0, 0, 100, 4096, 1e-11, "nx=6 nu=3 N=100 (BASELINE config 1 dims) batch=4096"),
     "c3": (4, 2, 2, 0, 100, 16384, 1e-3, "nx=4 nu=2 nc=2 N=100 batch=16384 (BASELINE config 3)"),
     "c4": (14, 7, 0, 0, 200, 2048, 1e-11, "nx=14 nu=7 N=200 batch=2048 (BASELINE config 4)"),
+    "c5": (57, 28, 0, 0, 150, 512, 1e-11, "nx=57 nu=28 N=150 batch=512 (BASELINE config 5, CTA per instance)"),
 }
 
 

@@ -88,8 +88,9 @@ typedef struct ab2_gar_dims {
 } ab2_gar_dims;
 
 /* launch tuning.  variant: -1 = automatic (the FP64 tensor-core formulation where the
- * shape allows it, else the lane-per-column one); 0..8 select a specific kernel build,
- * see csrc/riccati_launch.cuh. */
+ * shape allows it, else the lane-per-column one; the CTA-per-instance kernel for shapes
+ * without a compile-time instantiation); 0..8 select a specific warp-per-instance build,
+ * see csrc/riccati_launch.cuh; 9 forces the CTA-per-instance kernel (csrc/riccati_block.cuh). */
 typedef struct ab2_gar_tuning {
   int variant;
 } ab2_gar_tuning;
@@ -98,7 +99,10 @@ typedef struct ab2_gar_tuning {
  * Replaces: the 11 ArenaMatrix members of LqrKnotTpl, gar/lqr-problem.hpp:60-65. */
 size_t ab2_gar_stage_record_doubles(int nx, int nu, int nc);
 size_t ab2_gar_term_record_doubles(int nx, int nct);
-/* 1 if (nx,nu,nc,nc0) is served by a kernel instantiation of this build. */
+/* 1 if (nx,nu,nc,nc0) is served by a compile-time kernel instantiation of this build (one
+ * warp or part of one per instance), 2 if by the run-time-dimension kernel (one CTA per
+ * instance: any shape whose buffers fit 227 KB of shared memory and whose row counts
+ * nx+1, nu+nc, nx+nc0, nu+nc+nx are <= 256), 0 if not served. */
 int ab2_gar_supported(int nx, int nu, int nc, int nc0);
 
 /* Replaces: ProximalRiccatiSolver(const LqrProblemTpl&), gar/proximal-riccati.hxx:13-31

@@ -279,6 +279,12 @@ class BatchedOracle:
 
     def __init__(self, nx, nu, nc, nct, nc0, N, batch, stage, term, G0, g0):
         self.dims = (nx, nu, nc, nct, nc0, N, batch)
+        # the product pads odd-sized stage records to an even number of doubles (16-byte
+        # TMA granularity); the C driver reads dense records
+        srec = 2 * nx * nx + 2 * nx * nu + nu * nu + 2 * nx + nu + nc * (nx + nu + 1)
+        stage = np.asarray(stage, dtype=np.float64)
+        if N > 0 and stage.shape[-1] > srec:
+            stage = stage.reshape(batch, N, -1)[..., :srec]
         self._keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (stage, term, G0, g0)]
         s, t, g, h = self._keep
         self.h = C.c_void_p(lib().gar_oracle_batched_create(

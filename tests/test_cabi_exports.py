@@ -42,9 +42,12 @@ def test_record_sizes_match_reference_layout(lib):
 def test_supported_shapes(lib):
     import aligator_b200.gar as gar
     for shape in [(6, 3, 0, 6), (12, 6, 0, 12), (4, 2, 2, 4), (14, 7, 0, 14)]:
-        assert gar.supported(*shape), shape
-    assert not gar.supported(56, 22, 0, 56)   # large-state shape: not in this build
-    assert not gar.supported(12, 6, 0, 30)    # nx + nc0 exceeds the group
+        assert gar.supported(*shape) == 1, shape   # compile-time shape, warp per instance
+    assert gar.supported(57, 28, 0, 57) == 2      # BASELINE config 5: CTA per instance
+    assert gar.supported(12, 6, 0, 30) == 2       # nx + nc0 exceeds the warp: CTA per instance
+    assert gar.supported(7, 5, 3, 7) == 2         # arbitrary run-time shape
+    assert gar.supported(120, 40, 0, 120) == 0    # does not fit one CTA's shared memory
+    assert gar.supported(0, 1, 0, 0) == 0
 
 
 def test_create_fails_loudly_without_cuda(lib):

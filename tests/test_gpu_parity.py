@@ -316,3 +316,56 @@ def test_tensor_core_variants(gar, shape, variant):
     got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, variant=variant)
     ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
     compare(got, ref, nu, nc, N, mueq, tol=1e-9 if nct else TOL)
+
+
+BLOCK_SHAPES = [  # (nx, nu, nc, nct, N, batch, mueq): no compile-time instantiation -> CTA per instance
+    (7, 3, 0, 0, 30, 9, 1e-8),
+    (9, 5, 3, 0, 20, 7, 1e-3),
+    (20, 9, 0, 0, 40, 5, 1e-8),
+    (13, 4, 0, 2, 12, 300, 1e-2),     # more instances than resident CTAs: the persistent loop
+    (24, 20, 20, 0, 6, 3, 1e-3),      # 40 KKT rows, 48 rows in the initial-stage system
+    (57, 28, 0, 0, 25, 4, 1e-8),      # BASELINE config 5 dims (Talos whole-body)
+    (1, 1, 0, 0, 5, 3, 1e-8),
+]
+
+
+@pytest.mark.parametrize("shape", BLOCK_SHAPES)
+def test_block_kernel_runtime_shapes(gar, shape):
+    """Shapes without a compile-time instantiation run the CTA-per-instance kernel
+    (riccati_block.cuh): DMMA-tiled products over the CTA's warps, thread-per-row BK."""
+    nx, nu, nc, nct, N, B, mueq = shape
+    assert gar.supported(nx, nu, nc, nx) == 2
+    probs = gen.generate_batch(200 + nx, B, N, nx, nu, nc, nct)
+    got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq)
+    ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
+    compare(got, ref, nu, nc, N, mueq, tol=1e-9 if (nct or nc) else TOL)
+    assert got["launches"] == 1
+
+
+@pytest.mark.parametrize("shape", [(12, 6, 0, 0, 40, 19, 1e-8), (4, 2, 2, 0, 40, 70, 1e-3),
+                                   (12, 6, 6, 0, 20, 5, 1e-3)])
+def test_block_kernel_forced_on_instantiated_shapes(gar, shape):
+    """variant 9 forces the CTA-per-instance kernel; same results as the oracle, and the
+    split backward()/forward() calls reproduce the fused sweep bit for bit."""
+    nx, nu, nc, nct, N, B, mueq = shape
+    probs = gen.generate_batch(9, B, N, nx, nu, nc, nct)
+    got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, variant=9)
+    ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
+    compare(got, ref, nu, nc, N, mueq)
+    got2, _ = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, variant=9, split_calls=True)
+    for k in ("fb", "ff", "Vxx", "xs", "us", "lbdas"):
+        assert np.array_equal(got[k], got2[k]), k
+
+
+def test_block_kernel_interchanges(gar):
+    nx, nu, nc, nct, N, B = 9, 5, 0, 0, 12, 6
+    probs = gen.make_pivoting(gen.generate_batch(31, B, N, nx, nu, nc, nct))
+    got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, 1e-8)
+    ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, 1e-8)
+    compare(got, ref, nu, nc, N, 1e-8, tol=1e-9)
+
+
+def test_shape_too_large_for_one_cta_is_refused(gar):
+    assert gar.supported(120, 40, 0, 120) == 0
+    with pytest.raises(gar.GarError):
+        gar.CudaRiccatiBatch(120, 40, 0, 0, 120, 4, 2)

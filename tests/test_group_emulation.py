@@ -37,12 +37,28 @@ def _lib():
     return C.CDLL(EMU_LIB)
 
 
-def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0):
-    lib = _lib()
+BLOCK_LIB = os.path.join(EMU_DIR, "libblock_emu.so")
+
+
+def _block_lib():
+    srcs = [os.path.join(EMU_DIR, "block_emu.cpp"),
+            os.path.join(HERE, "..", "aligator_b200", "csrc", "riccati_block.cuh"),
+            os.path.join(HERE, "..", "aligator_b200", "csrc", "riccati_group.cuh")]
+    if (not os.path.exists(BLOCK_LIB)
+            or os.path.getmtime(BLOCK_LIB) < max(os.path.getmtime(s) for s in srcs)):
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread",
+                               "-o", BLOCK_LIB, srcs[0]])
+    return C.CDLL(BLOCK_LIB)
+
+
+def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0, block=0):
+    """block = 0: the warp-per-instance group program; block = NW > 0: the
+    CTA-per-instance program of riccati_block.cuh with NW emulated warps."""
+    lib = _block_lib() if block else _lib()
     B = len(probs)
     nc0 = probs[0].nc0
     stage, term, G0, g0 = gen.pack_problems(probs)
-    srec = lib.emu_stage_record(nx, nu, nc)
+    srec = lib.emu_block_stage_record(nx, nu, nc) if block else lib.emu_stage_record(nx, nu, nc)
     assert srec > 0, "shape not instantiated"
     if N > 0 and stage.shape[-1] != srec:
         stage = np.concatenate([stage, np.zeros(stage.shape[:-1] + (srec - stage.shape[-1],))], -1)
@@ -59,7 +75,10 @@ def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0):
     for k, v in keep.items():
         setattr(p, k, v.ctypes.data_as(_dp))
     p.status = status.ctypes.data_as(C.POINTER(C.c_int))
-    rc = lib.emu_sweep(nx, nu, nc, int(db), C.byref(p))
+    if block:
+        rc = lib.emu_block_sweep(nx, nu, nc, int(block), C.byref(p))
+    else:
+        rc = lib.emu_sweep(nx, nu, nc, int(db), C.byref(p))
     assert rc == 0
     out["Vxx"] = out["Vxx"].reshape(B, N + 1, nx, nx).transpose(0, 1, 3, 2)
     out["status"] = status
@@ -67,11 +86,11 @@ def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0):
 
 
 def check_against_oracle(nx, nu, nc, nct, N, B, mueq, seed, tol=1e-10, style="conditioned", db=0,
-                         pivoting=False):
+                         pivoting=False, block=0):
     probs = gen.generate_batch(seed, B, N, nx, nu, nc, nct, style=style)
     if pivoting:
         gen.make_pivoting(probs)
-    got = run_emulated(nx, nu, nc, nct, N, probs, mueq, db)
+    got = run_emulated(nx, nu, nc, nct, N, probs, mueq, db, block)
     assert np.all(got["status"] == 0)
     stage, term, G0, g0 = gen.pack_problems(probs)
     bo = orc.BatchedOracle(nx, nu, nc, nct, probs[0].nc0, N, B, stage, term, G0, g0)
