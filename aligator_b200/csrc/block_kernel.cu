@@ -16,6 +16,8 @@ struct BlockDevCtx {
   uint32_t phase; // bit p = parity to wait for on barrier p
 
   __device__ __forceinline__ void sync() { __syncthreads(); }
+  // barrier over the first `nth` threads (whole warps) of the CTA: named barrier 1
+  __device__ __forceinline__ void sync_sub(int nth) { asm volatile("bar.sync 1, %0;" ::"r"(nth) : "memory"); }
   __device__ __forceinline__ void mma(double (&d)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d[0]), "+d"(d[1])
@@ -65,7 +67,11 @@ struct BlockDevCtx {
   }
 };
 
-__global__ void __launch_bounds__(256) riccati_block_kernel(const SweepParams p, const BlockDims d) {
+// MAXREG 128: two or more CTAs per SM for the shapes whose buffers allow it; 255: the
+// large shapes, which own the SM anyway.
+template <int MAXREG>
+__global__ void __launch_bounds__(256) __maxnreg__(MAXREG)
+    riccati_block_kernel(const SweepParams p, const BlockDims d) {
   extern __shared__ __align__(16) double smem[];
   BlockDevCtx ctx;
   ctx.tid = threadIdx.x;
@@ -110,20 +116,19 @@ bool block_supported(int nx, int nu, int nc, int nc0) {
   return block_threads(nx, nu, nc, nc0) > 0 && block_smem_bytes(nx, nu, nc, nc0) <= (size_t)227 * 1024;
 }
 
-cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st, int *info) {
-  const BlockDims d = make_block_dims(nx, nu, nc, p.nc0);
-  const int threads = block_threads(nx, nu, nc, p.nc0);
-  const size_t smem = block_smem_bytes(nx, nu, nc, p.nc0);
-  cudaError_t e =
-      cudaFuncSetAttribute(riccati_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int MAXREG>
+static cudaError_t launch_block_t(const SweepParams &p, const BlockDims &d, int threads, size_t smem,
+                                  cudaStream_t st, int *info) {
+  auto kern = riccati_block_kernel<MAXREG>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
     return e;
-  e = cudaFuncSetAttribute(riccati_block_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess)
     return e;
   int nb = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, riccati_block_kernel, threads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem);
   if (e != cudaSuccess)
     return e;
   int dev = 0, sms = 148;
@@ -134,7 +139,7 @@ cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStrea
     grid = p.batch;
   if (info) {
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, riccati_block_kernel);
+    cudaFuncGetAttributes(&fa, kern);
     info[0] = threads;
     info[1] = (int)smem;
     info[2] = threads;
@@ -143,8 +148,18 @@ cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStrea
     info[5] = nb;
     return cudaSuccess;
   }
-  riccati_block_kernel<<<grid, threads, smem, st>>>(p, d);
+  kern<<<grid, threads, smem, st>>>(p, d);
   return cudaGetLastError();
+}
+
+cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st, int *info) {
+  const BlockDims d = make_block_dims(nx, nu, nc, p.nc0);
+  const int threads = block_threads(nx, nu, nc, p.nc0);
+  const size_t smem = block_smem_bytes(nx, nu, nc, p.nc0);
+  // one CTA per SM anyway (shared memory): let it use the whole register file
+  if (2 * (smem + 1024) > (size_t)227 * 1024)
+    return launch_block_t<255>(p, d, threads, smem, st, info);
+  return launch_block_t<128>(p, d, threads, smem, st, info);
 }
 
 } // namespace ab2

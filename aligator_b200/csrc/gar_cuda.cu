@@ -167,7 +167,9 @@ int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
   setup(AB2_OUT_LBD0, d.nc0, 1);
   setup(AB2_OUT_LBDAS, nx, N);
   for (int w = 0; w < AB2_OUT_COUNT; ++w) {
-    const size_t bytes = (s->out_doubles[w] > 0 ? s->out_doubles[w] : 1) * sizeof(double);
+    // (+2: the forward pass of the CTA-per-instance kernel fetches odd-sized gain records
+    // with 16-byte granularity, up to one double past the end of the array)
+    const size_t bytes = (s->out_doubles[w] > 0 ? s->out_doubles[w] + 2 : 2) * sizeof(double);
     cudaError_t e = cudaMalloc(&s->out[w], bytes);
     if (e == cudaSuccess)
       e = cudaMemset(s->out[w], 0, bytes);

@@ -28,7 +28,7 @@ struct BlockDims {
   int split; // [0, split) = [A B f] (live until the closing products), [split, srec_pad) = the rest
   int vs, vrows, sw, wrows, sh, sx, xrows;
   int s_rec, s_vn, s_vxn, s_w, s_x, s_kk, s_y, s_h, s_kkt, s_dd, s_sd, s_int, s_end; // doubles
-  int fwd_ring, fwd_slot;
+  int fwd_ring, fwd_slot, slack;
 };
 
 AB2_HD int blk_ev(int x) { return (x + 1) & ~1; }
@@ -81,7 +81,8 @@ AB2_HD BlockDims make_block_dims(int nx, int nu, int nc, int nc0) {
   d.xrows = 4 * d.kt2;
   int o = 0;
   d.s_rec = o;
-  o += d.srec_pad + 16; // slack: fragment loads of padded rows read (and discard) past the record
+  d.slack = blk_ev(4 * d.kt + 8); // zeroed: the "column" every padding column of M points at
+  o += d.srec_pad + d.slack;
   d.s_vn = o;
   o += blk_ev(d.vrows * d.vs);
   d.s_vxn = o;
@@ -113,7 +114,7 @@ AB2_HD BlockDims make_block_dims(int nx, int nu, int nc, int nc0) {
   const int k0 = n0 * n0 + 6 * n0 + 2;
   d.s_end = blk_ev(o > k0 ? o : k0);
   // forward: ring of fb records + two state vectors
-  d.fwd_slot = blk_ev(d.nr * nx);
+  d.fwd_slot = blk_ev(d.nr * nx) + 2; // an odd-sized record is fetched from the aligned double before it
   int ring = (d.s_end - 2 * blk_ev(nx)) / d.fwd_slot;
   if (ring < 1) {
     ring = 1;
@@ -157,7 +158,8 @@ AB2_D int blk_h0_offset(const BlockDims &d, int ip, int jp) { // -1 = structural
 template <class Ctx> struct CtaAsGroup {
   Ctx &c;
   int lane;
-  AB2_D void sync() { c.sync(); }
+  int nthreads; // participating threads (a multiple of 32): barrier over those warps only
+  AB2_D void sync() { c.sync_sub(nthreads); }
 };
 
 // Per-thread solve of one right-hand-side column with the factor left by
@@ -275,7 +277,8 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
   double *fb_b = p.fb + (size_t)inst * N * nr * nx;
   double *Vxx_b = p.Vxx + (size_t)inst * (N + 1) * nx * nx;
   double *vx_b = p.vx + (size_t)inst * (N + 1) * nx;
-  CtaAsGroup<Ctx> grp{ctx, tid};
+  const int bk_threads = 32 * ((nk + 31) / 32); // warps that own rows of the KKT matrix
+  CtaAsGroup<Ctx> grp{ctx, tid, bk_threads};
   const bool two_parts = d.split < d.srec_pad;
 
   if (p.do_bwd) {
@@ -288,8 +291,11 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
     }
     for (int i = tid; i < d.vrows * d.vs; i += T)
       Vn[i] = 0.0;
-    for (int i = tid; i < 16; i += T)
+    for (int i = tid; i < d.slack; i += T)
       rec[d.srec_pad + i] = 0.0; // the slack behind the record
+    // W / X / KK / Y: padding entries are multiplied by structural zeros, so they must be finite
+    for (int i = tid; i < d.s_kkt - d.s_w; i += T)
+      Wsm[i] = 0.0;
     ctx.sync();
     // ---------------- terminal knot (nu = 0): riccati-kernel.hxx:146-149,175-183
     {
@@ -337,29 +343,39 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
       double *fft = ff_b + (size_t)t * nr;
       ctx.wait_copy(0);
       // (1) W = V' M (+ vx' on the affine column), :216-224.  Work item = (m-tile, chunk).
+      // No predicates inside: padding columns of M point at the zeroed slack, padding rows
+      // of the contraction meet the zero columns of V'.
       for (int it = warp; it < d.mtx * nchunk; it += NW) {
         const int mt = it / nchunk, n0 = (it % nchunk) * BLK_CH;
+        const int ncol = d.nt - n0; // warp-uniform
         double acc[BLK_CH][2];
-        int moff[BLK_CH];
+        const double *mp[BLK_CH];
         AB2_UNROLL
         for (int c = 0; c < BLK_CH; ++c) {
           acc[c][0] = acc[c][1] = 0.0;
-          moff[c] = blk_col_offset(d, 8 * (n0 + c) + g);
+          mp[c] = rec + blk_col_offset(d, 8 * (n0 + c) + g) + q;
         }
-        for (int kt = 0; kt < d.kt; ++kt) {
-          const int kr = 4 * kt + q;
-          const double va = Vn[(8 * mt + g) * d.vs + kr];
-          AB2_UNROLL
-          for (int c = 0; c < BLK_CH; ++c)
-            if (n0 + c < d.nt) { // warp-uniform
-              const double mb = rec[moff[c] + (moff[c] == d.srec_pad ? 0 : kr)];
-              ctx.mma(acc[c], va, (kr < nx) ? mb : 0.0);
-            }
+        const double *vp = Vn + (8 * mt + g) * d.vs + q;
+        if (ncol >= BLK_CH) {
+          for (int kt = 0; kt < d.kt; ++kt) {
+            const double va = vp[4 * kt];
+            AB2_UNROLL
+            for (int c = 0; c < BLK_CH; ++c)
+              ctx.mma(acc[c], va, mp[c][4 * kt]);
+          }
+        } else {
+          for (int kt = 0; kt < d.kt; ++kt) {
+            const double va = vp[4 * kt];
+            AB2_UNROLL
+            for (int c = 0; c < BLK_CH; ++c)
+              if (c < ncol)
+                ctx.mma(acc[c], va, mp[c][4 * kt]);
+          }
         }
         const int i = 8 * mt + g;
         AB2_UNROLL
         for (int c = 0; c < BLK_CH; ++c)
-          if (n0 + c < d.nt && i < nx) {
+          if (c < ncol && i < nx) {
             const int jp = 8 * (n0 + c) + 2 * q;
             if (jp == nx)
               acc[c][0] += vxn[i];
@@ -374,31 +390,40 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
       // (2) H = H0 + M^T W  -> Hs, :226-241
       for (int it = warp; it < d.nt * nchunk; it += NW) {
         const int mt = it / nchunk, n0 = (it % nchunk) * BLK_CH;
+        const int ncol = d.nt - n0;
         double acc[BLK_CH][2];
         AB2_UNROLL
         for (int c = 0; c < BLK_CH; ++c) {
           AB2_UNROLL
           for (int e = 0; e < 2; ++e) {
-            const int o = (n0 + c < d.nt) ? blk_h0_offset(d, 8 * mt + g, 8 * (n0 + c) + 2 * q + e) : -1;
+            const int o = (c < ncol) ? blk_h0_offset(d, 8 * mt + g, 8 * (n0 + c) + 2 * q + e) : -1;
             const double hv = rec[o >= 0 ? o : 0];
             acc[c][e] = (o >= 0) ? hv : 0.0;
           }
         }
-        const int mo = blk_col_offset(d, 8 * mt + g);
-        for (int kt = 0; kt < d.kt; ++kt) {
-          const int kr = 4 * kt + q;
-          const double mv = rec[mo + (mo == d.srec_pad ? 0 : kr)];
-          const double ma = (kr < nx) ? mv : 0.0;
-          AB2_UNROLL
-          for (int c = 0; c < BLK_CH; ++c)
-            if (n0 + c < d.nt) {
-              const double wb = Wsm[(kr < nx ? kr : 0) * d.sw + 8 * (n0 + c) + g];
-              ctx.mma(acc[c], ma, (kr < nx) ? wb : 0.0);
-            }
+        const double *ap = rec + blk_col_offset(d, 8 * mt + g) + q; // M^T: row = column of M
+        const double *wp = Wsm + q * d.sw + 8 * n0 + g;
+        if (ncol >= BLK_CH) {
+          for (int kt = 0; kt < d.kt; ++kt) {
+            const double mv = ap[4 * kt];
+            const double ma = (4 * kt + q < nx) ? mv : 0.0; // W's rows beyond nx are not W
+            AB2_UNROLL
+            for (int c = 0; c < BLK_CH; ++c)
+              ctx.mma(acc[c], ma, wp[4 * kt * d.sw + 8 * c]);
+          }
+        } else {
+          for (int kt = 0; kt < d.kt; ++kt) {
+            const double mv = ap[4 * kt];
+            const double ma = (4 * kt + q < nx) ? mv : 0.0;
+            AB2_UNROLL
+            for (int c = 0; c < BLK_CH; ++c)
+              if (c < ncol)
+                ctx.mma(acc[c], ma, wp[4 * kt * d.sw + 8 * c]);
+          }
         }
         AB2_UNROLL
         for (int c = 0; c < BLK_CH; ++c)
-          if (n0 + c < d.nt)
+          if (c < ncol)
             sts2(Hs + (8 * mt + g) * d.sh + 8 * (n0 + c) + 2 * q, acc[c][0], acc[c][1]);
       }
       ctx.sync();
@@ -429,8 +454,10 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
         const double *src = stage_b + (size_t)(t - 1) * d.srec_pad;
         ctx.issue_copy(1, rec + d.split, src + d.split, d.srec_pad - d.split);
       }
-      if (!bk_factor_group<8>(grp, kkt, nk, nk, dd, sd, perm, kind))
-        st |= ST_STAGE_FACTOR_FAILED;
+      if (tid < bk_threads) // the other warps go straight to the CTA barrier below
+        if (!bk_factor_group<8>(grp, kkt, nk, nk, dd, sd, perm, kind))
+          st |= ST_STAGE_FACTOR_FAILED;
+      ctx.sync();
       if (tid <= nx) { // column tid of [K k; Z z] = -KKT^-1 X[:, tid]
         if (nk <= 8)
           bk_solve_column_reg<8>(kkt, nk, dd, sd, perm, kind, X + tid, KKs + tid, d.sx);
@@ -464,18 +491,22 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
             VV[c][e] = in ? hv : 0.0;
           }
         }
+        // KK rows >= nk meet zero operands, KK columns > nx feed outputs nobody stores:
+        // no predicate on the KK fragments
+        const double *bp = rec + d.off_b + ic;
+        const double *xp = X + ic;
+        const double *kp = KKs + q * d.sx + 8 * n0 + g;
+        const int ncol = d.nt2 - n0;
         for (int k2 = 0; k2 < d.kt2; ++k2) {
           const int c4 = 4 * k2 + q;
-          const double bv = rec[d.off_b + (c4 < nu ? c4 : 0) * nx + ic];
+          const double bv = bp[(c4 < nu ? c4 : 0) * nx];
           const double bf = (c4 < nu && i < nx) ? bv : 0.0;
-          const double xr = X[(c4 < nk ? c4 : 0) * d.sx + ic];
+          const double xr = xp[c4 * d.sx];
           const double xf = (c4 < nk && i < nx) ? xr : 0.0;
           AB2_UNROLL
           for (int c = 0; c < BLK_CH; ++c)
-            if (n0 + c < d.nt2) {
-              const int col = 8 * (n0 + c) + g;
-              const double kv = KKs[(c4 < nk ? c4 : 0) * d.sx + (col <= nx ? col : 0)];
-              const double kf = (c4 < nk && col <= nx) ? kv : 0.0;
+            if (c < ncol) {
+              const double kf = kp[4 * k2 * d.sx + 8 * c];
               ctx.mma(EA[c], bf, kf);
               ctx.mma(VV[c], xf, kf);
             }
@@ -542,9 +573,13 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
       for (int i = tid; i < n0; i += T)
         b0[i] = (i < nx) ? -vx_b[i] : -g0[i - nx];
       ctx.sync();
-      if (!bk_factor_group<8>(grp, K0, n0, n0, dd0, sd0, perm0, kind0))
-        st |= ST_INIT_FACTOR_FAILED;
-      bk_solve_vec_group(grp, K0, n0, n0, dd0, sd0, perm0, kind0, b0, x0w, o0);
+      CtaAsGroup<Ctx> grp0{ctx, tid, 32 * ((n0 + 31) / 32)};
+      if (tid < grp0.nthreads) {
+        if (!bk_factor_group<8>(grp0, K0, n0, n0, dd0, sd0, perm0, kind0))
+          st |= ST_INIT_FACTOR_FAILED;
+        bk_solve_vec_group(grp0, K0, n0, n0, dd0, sd0, perm0, kind0, b0, x0w, o0);
+      }
+      ctx.sync();
       for (int i = tid; i < n0; i += T)
         p.kkt0[(size_t)inst * n0 + i] = o0[i];
       ctx.sync();
@@ -562,21 +597,22 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
     double *vs_b = p.vs + (size_t)inst * N * nc;
     double *lb_b = p.lbdas + (size_t)inst * N * nx;
     const int RING = d.fwd_ring, FS = d.fwd_slot;
-    const bool bulk = (nr * nx) % 2 == 0;
+    const int R = nr * nx;
     double *ring = sm;
     double *xc = sm + RING * FS;
     double *xnx = xc + blk_ev(nx);
     ctx.sync();
-    auto fill_slot = [&](int s, int t) { // fb record of knot t -> ring slot s
-      if (bulk) {
-        ctx.issue_copy(s, ring + s * FS, fb_b + (size_t)t * nr * nx, nr * nx);
-      } else {
-        for (int i2 = tid; i2 < nr * nx; i2 += T)
-          ring[s * FS + i2] = fb_b[(size_t)t * nr * nx + i2];
-      }
+    // fb record of knot t -> ring slot s by one TMA bulk copy.  A record that starts at an
+    // odd double (odd-sized records) is fetched from the aligned double before it; the
+    // record then sits one double into the slot.
+    const size_t e_inst = (size_t)inst * N * R;
+    auto rec_shift = [&](int t) { return (int)((e_inst + (size_t)t * R) & 1); };
+    auto fill_slot = [&](int s_, int t) {
+      const int a = rec_shift(t);
+      ctx.issue_copy(s_, ring + s_ * FS, p.fb + (e_inst + (size_t)t * R - a), blk_ev(R + a));
     };
-    for (int s = 0; s < RING && s < N; ++s)
-      fill_slot(s, s);
+    for (int s_ = 0; s_ < RING && s_ < N; ++s_)
+      fill_slot(s_, s_);
     for (int i = tid; i < nx; i += T) {
       const double v = k0[i];
       xc[i] = v;
@@ -584,14 +620,31 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
     }
     for (int m = tid; m < nc0; m += T)
       p.lbd0[(size_t)inst * nc0 + m] = k0[nx + m];
+    // lbda_t = vx_t + Vxx_t x_t (t >= 1; Vxx_t symmetric: element (c, i) read as (i, c) keeps
+    // the loads of neighbouring threads contiguous).  Runs on the warps pass 1 leaves idle.
+    const int lam0 = 32 * ((nr + 31) / 32);
+    const bool lam_overlap = T - lam0 >= 32;
+    auto lam_rows = [&](int tt, const double *x, int first, int step) {
+      const double *V = Vxx_b + (size_t)tt * nx * nx;
+      for (int i = first; i < nx; i += step) {
+        double s0 = vx_b[(size_t)tt * nx + i], s1 = 0.0;
+        int c = 0;
+        for (; c + 1 < nx; c += 2) {
+          s0 += V[(size_t)c * nx + i] * x[c];
+          s1 += V[(size_t)(c + 1) * nx + i] * x[c + 1];
+        }
+        if (c < nx)
+          s0 += V[(size_t)c * nx + i] * x[c];
+        lb_b[(size_t)(tt - 1) * nx + i] = s0 + s1;
+      }
+    };
     // Pass 1: x_{t+1} = a + Ahat x_t (and u, v): thread r owns gain row r (nr <= T).
     double gff = (tid < nr && N > 0) ? ff_b[tid] : 0.0;
     ctx.sync();
     for (int t = 0; t < N; ++t) {
-      const int s = t % RING;
-      if (bulk)
-        ctx.wait_copy(s);
-      const double *slot = ring + s * FS;
+      const int s_ = t % RING;
+      ctx.wait_copy(s_);
+      const double *slot = ring + s_ * FS + rec_shift(t);
       if (tid < nr) {
         const int r = tid;
         double s0 = gff, s1 = 0.0;
@@ -612,29 +665,22 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
           xs_b[(size_t)(t + 1) * nx + (r - nk)] = sv;
         }
         gff = (t + 1 < N) ? ff_b[(size_t)(t + 1) * nr + r] : 0.0;
+      } else if (lam_overlap && tid >= lam0 && t >= 1) {
+        lam_rows(t, xc, tid - lam0, T - lam0);
       }
       double *tmp = xc;
       xc = xnx;
       xnx = tmp;
       ctx.sync(); // x_{t+1} visible; everyone is done with x_t and with this slot
       if (t + RING < N)
-        fill_slot(s, t + RING);
+        fill_slot(s_, t + RING);
     }
-    // Pass 2: lbda_{t+1} = vx_{t+1} + Vxx_{t+1} x_{t+1}: independent over knots
-    // (Vxx_{t+1} is symmetric: row i = column i, contiguous).
-    for (int e = tid; e < N * nx; e += T) {
-      const int tt = e / nx, i = e % nx;
-      const double *vcol = Vxx_b + ((size_t)(tt + 1) * nx + i) * nx;
-      const double *xr = xs_b + (size_t)(tt + 1) * nx;
-      double s0 = vx_b[(size_t)(tt + 1) * nx + i], s1 = 0.0;
-      int c = 0;
-      for (; c + 1 < nx; c += 2) {
-        s0 += vcol[c] * xr[c];
-        s1 += vcol[c + 1] * xr[c + 1];
-      }
-      if (c < nx)
-        s0 += vcol[c] * xr[c];
-      lb_b[(size_t)tt * nx + i] = s0 + s1;
+    if (lam_overlap) {
+      if (N >= 1)
+        lam_rows(N, xc, tid, T);
+    } else {
+      for (int tt = 1; tt <= N; ++tt) // xs is in global memory, written by this CTA
+        lam_rows(tt, xs_b + (size_t)tt * nx, tid, T);
     }
     // terminal multipliers v_N = z + Z x_N
     for (int m = tid; m < nct; m += T) {

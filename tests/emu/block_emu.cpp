@@ -15,9 +15,11 @@ namespace {
 struct HostBlockCtx {
   int tid, nthreads, warp, lane, nwarps;
   std::barrier<> *cta;
+  std::barrier<> **sub; // sub[w-1]: barrier over the first w warps
   std::barrier<> *wbar;
   double *xa, *xb; // this warp's exchange slots
   void sync() { cta->arrive_and_wait(); }
+  void sync_sub(int nth) { sub[nth / 32 - 1]->arrive_and_wait(); }
   void mma(double (&d)[2], double a, double b) {
     xa[lane] = a;
     xb[lane] = b;
@@ -55,11 +57,17 @@ extern "C" int emu_block_sweep(int nx, int nu, int nc, int nwarps, const ab2::Sw
     std::vector<std::unique_ptr<std::barrier<>>> wb;
     for (int w = 0; w < nwarps; ++w)
       wb.emplace_back(new std::barrier<>(32));
+    std::vector<std::unique_ptr<std::barrier<>>> subs;
+    std::vector<std::barrier<> *> subp;
+    for (int w = 1; w <= nwarps; ++w) {
+      subs.emplace_back(new std::barrier<>(32 * w));
+      subp.push_back(subs.back().get());
+    }
     std::vector<double> xa(T), xb(T);
     std::vector<std::thread> th;
     for (int t = 0; t < T; ++t)
       th.emplace_back([&, t] {
-        HostBlockCtx ctx{t, T, t / 32, t % 32, nwarps, &cta, wb[t / 32].get(),
+        HostBlockCtx ctx{t, T, t / 32, t % 32, nwarps, &cta, subp.data(), wb[t / 32].get(),
                          xa.data() + 32 * (t / 32), xb.data() + 32 * (t / 32)};
         ab2::riccati_block_sweep(ctx, p, d, inst, sm.data());
       });
