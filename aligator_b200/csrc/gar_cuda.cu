@@ -207,6 +207,11 @@ int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
   p.lbd0 = s->out[AB2_OUT_LBD0];
   p.lbdas = s->out[AB2_OUT_LBDAS];
   p.status = s->status;
+  {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device);
+    p.num_sms = sms > 0 ? sms : 148;
+  }
   *out = s;
   return AB2_OK;
 }
@@ -234,7 +239,11 @@ int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t) {
     return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..9");
   if (t->variant == 9 && !ab2::block_supported(s->d.nx, s->d.nu, s->d.nc, s->d.nc0))
     return fail(AB2_ERR_UNSUPPORTED, "variant 9 (CTA per instance) does not fit this shape");
+  if (t->stagger_ns < 0 || t->stagger_ns > 100000 || t->ctas_per_sm < 0 || t->ctas_per_sm > 32)
+    return fail(AB2_ERR_INVALID, "stagger_ns must be in [0, 100000], ctas_per_sm in [0, 32]");
   s->variant = t->variant;
+  s->p.stagger_ns = t->stagger_ns;
+  s->p.ctas_per_sm = t->ctas_per_sm;
   return AB2_OK;
 }
 

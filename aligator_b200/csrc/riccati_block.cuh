@@ -163,17 +163,37 @@ template <class Ctx> struct CtaAsGroup {
 };
 
 // Per-thread solve of one right-hand-side column with the factor left by
-// bk_factor_group (run-time n; same sequence as bk_solve_column).
-// rhs/work/sol: column pointers, rows `stride` apart; the result is -(KKT^-1 rhs).
+// bk_factor_group (run-time n; same sequence as bk_solve_column: interchanges, unit-lower
+// solve, D^-1, unit-upper solve, inverse interchanges).  Both triangular solves run in
+// dot-product form -- x_i = b_i - sum_c L(i,c) x_c -- so the loads of one row pipeline
+// (no store in between) and the code stays small (a fully unrolled register version
+// stalls on instruction fetch).  rhs/work/sol: column pointers, rows `stride` apart; the
+// result is -(KKT^-1 rhs).
 AB2_D void bk_solve_column_rt(const double *a, const int n, const double *dd, const double *sd,
                               const int *perm, const int *kind, const double *rhs, double *work,
                               double *sol, const int stride) {
+  constexpr int CH = 8;
   for (int i = 0; i < n; ++i)
     work[i * stride] = rhs[perm[i] * stride];
-  for (int c = 0; c < n; ++c) {
-    const double xc = work[c * stride];
-    for (int i = c + 1; i < n; ++i)
-      work[i * stride] -= a[i + c * n] * xc;
+  for (int i = 1; i < n; ++i) { // forward: unit lower
+    double s0 = work[i * stride], s1 = 0.0;
+    for (int c0 = 0; c0 < i; c0 += CH) {
+      double l[CH], x[CH];
+      AB2_UNROLL
+      for (int u = 0; u < CH; ++u) {
+        const int c = (c0 + u < i) ? c0 + u : 0;
+        l[u] = a[i + c * n];
+        x[u] = work[c * stride];
+      }
+      AB2_UNROLL
+      for (int u = 0; u < CH; u += 2) {
+        if (c0 + u < i)
+          s0 -= l[u] * x[u];
+        if (c0 + u + 1 < i)
+          s1 -= l[u + 1] * x[u + 1];
+      }
+    }
+    work[i * stride] = s0 + s1;
   }
   for (int k = 0; k < n; ++k) {
     const int kd = kind[k];
@@ -185,63 +205,28 @@ AB2_D void bk_solve_column_rt(const double *a, const int n, const double *dd, co
       work[(k + 1) * stride] = xk1 * dd[k + 1] + xk * s;
     }
   }
-  for (int c = n - 1; c >= 0; --c) {
-    double xc = work[c * stride];
-    for (int i = c + 1; i < n; ++i)
-      xc -= a[i + c * n] * work[i * stride];
-    work[c * stride] = xc;
+  for (int c = n - 2; c >= 0; --c) { // backward: unit upper (L^T)
+    double s0 = work[c * stride], s1 = 0.0;
+    for (int i0 = c + 1; i0 < n; i0 += CH) {
+      double l[CH], x[CH];
+      AB2_UNROLL
+      for (int u = 0; u < CH; ++u) {
+        const int i = (i0 + u < n) ? i0 + u : n - 1;
+        l[u] = a[i + c * n];
+        x[u] = work[i * stride];
+      }
+      AB2_UNROLL
+      for (int u = 0; u < CH; u += 2) {
+        if (i0 + u < n)
+          s0 -= l[u] * x[u];
+        if (i0 + u + 1 < n)
+          s1 -= l[u + 1] * x[u + 1];
+      }
+    }
+    work[c * stride] = s0 + s1;
   }
   for (int i = 0; i < n; ++i)
     sol[perm[i] * stride] = -work[i * stride];
-}
-
-// The same solve with the column held in registers (n <= NMAX; every loop fully unrolled
-// and predicated on the run-time n): the loads of the factor are independent of the
-// arithmetic, so they pipeline instead of serialising on the shared-memory round trip.
-template <int NMAX>
-AB2_D void bk_solve_column_reg(const double *a, const int n, const double *dd, const double *sd,
-                               const int *perm, const int *kind, const double *rhs, double *sol,
-                               const int stride) {
-  double x[NMAX];
-  AB2_UNROLL
-  for (int i = 0; i < NMAX; ++i)
-    x[i] = (i < n) ? rhs[perm[i < n ? i : 0] * stride] : 0.0;
-  AB2_UNROLL
-  for (int c = 0; c < NMAX; ++c) {
-    if (c < n) {
-      AB2_UNROLL
-      for (int i = c + 1; i < NMAX; ++i)
-        if (i < n)
-          x[i] -= a[i + c * n] * x[c];
-    }
-  }
-  AB2_UNROLL
-  for (int k = 0; k < NMAX; ++k) {
-    if (k < n) {
-      const int kd = kind[k];
-      if (kd == 0) {
-        x[k] *= dd[k];
-      } else if (kd == 1 && k + 1 < NMAX) {
-        const int k1 = (k + 1 < NMAX) ? k + 1 : k;
-        const double xk = x[k], xk1 = x[k1], s = sd[k];
-        x[k] = xk * dd[k] + xk1 * s;
-        x[k1] = xk1 * dd[k1] + xk * s;
-      }
-    }
-  }
-  AB2_UNROLL
-  for (int c = NMAX - 1; c >= 0; --c) {
-    if (c < n) {
-      AB2_UNROLL
-      for (int i = c + 1; i < NMAX; ++i)
-        if (i < n)
-          x[c] -= a[i + c * n] * x[i];
-    }
-  }
-  AB2_UNROLL
-  for (int i = 0; i < NMAX; ++i)
-    if (i < n)
-      sol[perm[i] * stride] = -x[i];
 }
 
 constexpr int BLK_CH = 4; // n-tiles accumulated together by one warp (one work item)
@@ -455,18 +440,11 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
         ctx.issue_copy(1, rec + d.split, src + d.split, d.srec_pad - d.split);
       }
       if (tid < bk_threads) // the other warps go straight to the CTA barrier below
-        if (!bk_factor_group<8>(grp, kkt, nk, nk, dd, sd, perm, kind))
+        if (!bk_factor_group<16>(grp, kkt, nk, nk, dd, sd, perm, kind))
           st |= ST_STAGE_FACTOR_FAILED;
       ctx.sync();
       if (tid <= nx) { // column tid of [K k; Z z] = -KKT^-1 X[:, tid]
-        if (nk <= 8)
-          bk_solve_column_reg<8>(kkt, nk, dd, sd, perm, kind, X + tid, KKs + tid, d.sx);
-        else if (nk <= 16)
-          bk_solve_column_reg<16>(kkt, nk, dd, sd, perm, kind, X + tid, KKs + tid, d.sx);
-        else if (nk <= 32)
-          bk_solve_column_reg<32>(kkt, nk, dd, sd, perm, kind, X + tid, KKs + tid, d.sx);
-        else
-          bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, X + tid, Ys + tid, KKs + tid, d.sx);
+        bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, X + tid, Ys + tid, KKs + tid, d.sx);
       }
       ctx.sync();
       for (int e = tid; e < nk * nx; e += T) // gains K, Z (row-major nk x nx)

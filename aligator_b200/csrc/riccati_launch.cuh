@@ -135,6 +135,10 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
   ctx.lane = lane32 % C::G;
   ctx.mask = (C::G == 32) ? 0xffffffffu : (((1u << C::G) - 1u) << (gsub * C::G));
   ctx.init(bars);
+  if (p.stagger_ns > 0) { // resident slot of this warp on its SM (first wave: CTA b runs on SM b mod num_sms)
+    const int slot = (blockIdx.x / p.num_sms) * WARPS + warp;
+    __nanosleep((unsigned)(slot * p.stagger_ns));
+  }
   riccati_group_sweep<C>(ctx, p, inst, sm);
 }
 
@@ -152,7 +156,7 @@ template <class C, int WARPS, int MAXREG, bool TMA>
 inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int *info) {
   constexpr int IPW = 32 / C::G;
   const int groups = WARPS * IPW;
-  const size_t smem = (size_t)groups * gd * sizeof(double) + (size_t)groups * 8 * NBAR + (size_t)C::LUT_INTS * 4;
+  size_t smem = (size_t)groups * gd * sizeof(double) + (size_t)groups * 8 * NBAR + (size_t)C::LUT_INTS * 4;
   auto kern = riccati_sweep_kernel<C, WARPS, MAXREG, TMA>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
@@ -163,6 +167,40 @@ inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int
   if (e != cudaSuccess)
     return e;
   const int grid = (p.batch + groups - 1) / groups;
+  // Residency.  The SM saturates below its maximum residency (C2: 12-14 warps), so extra
+  // resident CTAs only slow each other down; what costs is a partly filled LAST round.
+  // Keep the smallest residency that still needs the minimum number of rounds (C2: 7
+  // CTAs/SM -> 4096 instances = two full rounds of 2072 instead of 2368 + 1728), enforced
+  // by padding the dynamic shared-memory request (the system reserves 1 KB per CTA).
+  // p.ctas_per_sm > 0 overrides, < 0 keeps the maximum.
+  {
+    static thread_local size_t cached_smem = 0; // per kernel instantiation
+    static thread_local int cached_cmax = 0;
+    if (cached_smem != smem) {
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_cmax, kern, WARPS * 32, smem);
+      if (e != cudaSuccess)
+        return e;
+      cached_smem = smem;
+    }
+    const int cmax = cached_cmax;
+    int want = p.ctas_per_sm;
+    if (want == 0 && cmax > 1) {
+      const int sms = p.num_sms > 0 ? p.num_sms : 148;
+      auto rounds = [&](int c) { return (grid + sms * c - 1) / (sms * c); };
+      want = cmax;
+      while ((want - 1) * WARPS >= 12 && rounds(want - 1) == rounds(cmax))
+        --want; // (never below 12 resident warps: under that the SM is not saturated)
+    }
+    if (want > 0 && want < cmax) {
+      const size_t pad = (((size_t)227 * 1024 / want) - 1024) & ~(size_t)15;
+      if (pad > smem) {
+        smem = pad;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+          return e;
+      }
+    }
+  }
   if (info) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, kern);

@@ -30,7 +30,7 @@ class GarDims(C.Structure):
 
 
 class GarTuning(C.Structure):
-    _fields_ = [("variant", C.c_int)]
+    _fields_ = [("variant", C.c_int), ("stagger_ns", C.c_int), ("ctas_per_sm", C.c_int)]
 
 
 class GarError(RuntimeError):
@@ -112,12 +112,13 @@ class CudaRiccatiBatch:
     """Thin owner of an ``ab2_gar_solver`` handle: `batch` independent LQ problems of
     identical dimensions (stage knots (nx,nu,nc), terminal knot (nx,0,nct))."""
 
-    def __init__(self, nx, nu, nc, nct, nc0, horizon, batch, device=0, variant=-1):
+    def __init__(self, nx, nu, nc, nct, nc0, horizon, batch, device=0, variant=-1, stagger_ns=0,
+                 ctas_per_sm=0):
         self.dims = GarDims(nx, nu, nc, nct, nc0, horizon, batch, device)
         self.h = C.c_void_p()
         _check(lib().ab2_gar_create(C.byref(self.dims), C.byref(self.h)))
-        if variant >= 0:
-            _check(lib().ab2_gar_set_tuning(self.h, C.byref(GarTuning(variant))))
+        if variant >= 0 or stagger_ns or ctas_per_sm:
+            _check(lib().ab2_gar_set_tuning(self.h, C.byref(GarTuning(variant, stagger_ns, ctas_per_sm))))
         self.srec = stage_record_doubles(nx, nu, nc)
         self.trec = term_record_doubles(nx, nct)
         self._keep = None

@@ -93,6 +93,8 @@ typedef struct ab2_gar_dims {
  * see csrc/riccati_launch.cuh; 9 forces the CTA-per-instance kernel (csrc/riccati_block.cuh). */
 typedef struct ab2_gar_tuning {
   int variant;
+  int stagger_ns;  /* > 0: start-up delay per resident warp slot (de-phases the warps of an SM) */
+  int ctas_per_sm; /* > 0: cap on resident CTAs per SM (e.g. 7 -> 4096 instances = two full rounds) */
 } ab2_gar_tuning;
 
 /* Doubles in one stage / terminal record (stage includes the pad to even).

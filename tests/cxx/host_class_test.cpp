@@ -106,10 +106,11 @@ int main() {
   rc |= check_one(6, 3, 0, 100, 1e-8, 2);
   rc |= check_one(12, 6, 0, 100, 1e-11, 3);
   rc |= check_one(4, 2, 2, 50, 1e-3, 4);
+  rc |= check_one(40, 3, 0, 6, 1e-8, 5); // no compile-time instantiation: CTA-per-instance kernel
   // error convention: unsupported dims throw like the reference's RuntimeError
   try {
     std::mt19937 rng(9);
-    ab::LqrProblem big = random_problem(rng, 40, 3, 0, 2);
+    ab::LqrProblem big = random_problem(rng, 150, 60, 0, 2); // exceeds one CTA's shared memory
     ab::CudaRiccatiSolver s(big);
     rc |= 64;
   } catch (const aligator_b200::RuntimeError &e) {

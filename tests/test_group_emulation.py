@@ -23,7 +23,8 @@ class SweepParams(C.Structure):
                 ("mueq", C.c_double), ("do_bwd", C.c_int), ("do_fwd", C.c_int)] + \
                [(n, _dp) for n in ("stage", "term", "G0", "g0", "ff", "fb", "Vxx", "vx", "ffT",
                                    "fbT", "kkt0", "xs", "us", "vs", "vsT", "lbd0", "lbdas")] + \
-               [("status", C.POINTER(C.c_int))]
+               [("status", C.POINTER(C.c_int)), ("stagger_ns", C.c_int), ("num_sms", C.c_int),
+                ("ctas_per_sm", C.c_int)]
 
 
 def _lib():
