@@ -86,6 +86,11 @@ struct ab2_gar_solver {
   long launches = 0;
   int variant = -1;
   int group_doubles[3] = {0, 0, 0};
+  // ab2_gar_sweep_host: internal streams, one event per stream + a fork event
+  static constexpr int kPipeStreams = 4;
+  cudaStream_t pipe_stream[kPipeStreams] = {};
+  cudaEvent_t pipe_done[kPipeStreams] = {};
+  cudaEvent_t pipe_fork = nullptr;
 };
 
 static size_t stage_total(const ab2_gar_solver *s) {
@@ -228,6 +233,14 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
   for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0})
     if (q)
       cudaFree(q);
+  for (int i = 0; i < ab2_gar_solver::kPipeStreams; ++i) {
+    if (s->pipe_done[i])
+      cudaEventDestroy(s->pipe_done[i]);
+    if (s->pipe_stream[i])
+      cudaStreamDestroy(s->pipe_stream[i]);
+  }
+  if (s->pipe_fork)
+    cudaEventDestroy(s->pipe_fork);
   delete s;
   return AB2_OK;
 }
@@ -293,6 +306,35 @@ int ab2_gar_set_problem(ab2_gar_solver *s, const double *stage, const double *te
   return AB2_OK;
 }
 
+// SweepParams of the instances [b0, b0 + nb): every array leads with the batch index.
+static ab2::SweepParams slice_params(const ab2_gar_solver *s, int b0, int nb) {
+  ab2::SweepParams q = s->p;
+  const size_t b = (size_t)b0;
+  const int N = s->d.horizon, nx = s->d.nx;
+  q.batch = nb;
+  q.stage += b * N * s->srec;
+  q.term += b * s->trec;
+  if (q.G0)
+    q.G0 += b * s->d.nc0 * nx;
+  if (q.g0)
+    q.g0 += b * s->d.nc0;
+  q.ff += b * s->out_knots[AB2_OUT_FF] * s->out_rec[AB2_OUT_FF];
+  q.fb += b * s->out_knots[AB2_OUT_FB] * s->out_rec[AB2_OUT_FB];
+  q.Vxx += b * s->out_knots[AB2_OUT_VXX] * s->out_rec[AB2_OUT_VXX];
+  q.vx += b * s->out_knots[AB2_OUT_VX] * s->out_rec[AB2_OUT_VX];
+  q.ffT += b * s->out_rec[AB2_OUT_FFT];
+  q.fbT += b * s->out_rec[AB2_OUT_FBT];
+  q.kkt0 += b * s->out_rec[AB2_OUT_KKT0];
+  q.xs += b * s->out_knots[AB2_OUT_XS] * s->out_rec[AB2_OUT_XS];
+  q.us += b * s->out_knots[AB2_OUT_US] * s->out_rec[AB2_OUT_US];
+  q.vs += b * s->out_knots[AB2_OUT_VS] * s->out_rec[AB2_OUT_VS];
+  q.vsT += b * s->out_rec[AB2_OUT_VST];
+  q.lbd0 += b * s->out_rec[AB2_OUT_LBD0];
+  q.lbdas += b * s->out_knots[AB2_OUT_LBDAS] * s->out_rec[AB2_OUT_LBDAS];
+  q.status += b;
+  return q;
+}
+
 static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream) {
   if (!s)
     return fail(AB2_ERR_INVALID, "null solver");
@@ -319,6 +361,93 @@ static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream
 int ab2_gar_backward(ab2_gar_solver *s, double mueq, void *stream) { return launch(s, mueq, 1, 0, stream); }
 int ab2_gar_forward(ab2_gar_solver *s, void *stream) { return launch(s, s ? s->p.mueq : 0.0, 0, 1, stream); }
 int ab2_gar_sweep(ab2_gar_solver *s, double mueq, void *stream) { return launch(s, mueq, 1, 1, stream); }
+
+int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *term, const double *G0,
+                       const double *g0, double mueq, int nchunks, const int *whats,
+                       double *const *dsts, int nwhat, void *stream) {
+  if (!s || !stage || !term || (s->d.nc0 > 0 && (!G0 || !g0)) || nwhat < 0 || (nwhat > 0 && (!whats || !dsts)))
+    return fail(AB2_ERR_INVALID, "bad argument");
+  for (int i = 0; i < nwhat; ++i)
+    if (whats[i] < 0 || whats[i] >= AB2_OUT_COUNT || !dsts[i])
+      return fail(AB2_ERR_INVALID, "bad output selector");
+  if (!(mueq > 0.0) && (s->d.nc > 0 || s->d.nct > 0))
+    return fail(AB2_ERR_INVALID, "mueq must be > 0 when constraints are present");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  const int B = s->d.batch, N = s->d.horizon, nx = s->d.nx, nc0 = s->d.nc0;
+  constexpr int NS = ab2_gar_solver::kPipeStreams;
+  if (!s->pipe_fork) {
+    CUDA_TRY(cudaEventCreateWithFlags(&s->pipe_fork, cudaEventDisableTiming));
+    for (int i = 0; i < NS; ++i) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&s->pipe_stream[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&s->pipe_done[i], cudaEventDisableTiming));
+    }
+  }
+  auto own = [&](double *&buf, size_t n) -> int {
+    if (!buf)
+      CUDA_TRY(cudaMalloc(&buf, (n > 0 ? n : 1) * sizeof(double)));
+    return AB2_OK;
+  };
+  int rc;
+  if ((rc = own(s->own_stage, stage_total(s))) != AB2_OK || (rc = own(s->own_term, (size_t)B * s->trec)) != AB2_OK ||
+      (rc = own(s->own_G0, (size_t)B * nc0 * nx)) != AB2_OK || (rc = own(s->own_g0, (size_t)B * nc0)) != AB2_OK)
+    return rc;
+  s->p.stage = s->own_stage;
+  s->p.term = s->own_term;
+  s->p.G0 = s->own_G0;
+  s->p.g0 = s->own_g0;
+  s->have_problem = true;
+  s->p.mueq = mueq;
+  s->p.do_bwd = 1;
+  s->p.do_fwd = 1;
+  if (nchunks <= 0) { // enough slices to hide the first upload / last download, each still one full wave
+    nchunks = B / 512;
+    if (nchunks > 16)
+      nchunks = 16;
+  }
+  if (nchunks < 1)
+    nchunks = 1;
+  if (nchunks > B)
+    nchunks = B;
+  cudaStream_t user = (cudaStream_t)stream;
+  CUDA_TRY(cudaEventRecord(s->pipe_fork, user));
+  for (int i = 0; i < NS && i < nchunks; ++i)
+    CUDA_TRY(cudaStreamWaitEvent(s->pipe_stream[i], s->pipe_fork, 0));
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = (int)((long long)B * c / nchunks), b1 = (int)((long long)B * (c + 1) / nchunks);
+    const int nb = b1 - b0;
+    if (nb <= 0)
+      continue;
+    cudaStream_t st = s->pipe_stream[c % NS];
+    auto up = [&](double *dev, const double *host, size_t per_inst) -> int {
+      if (per_inst)
+        CUDA_TRY(cudaMemcpyAsync(dev + (size_t)b0 * per_inst, host + (size_t)b0 * per_inst,
+                                 (size_t)nb * per_inst * sizeof(double), cudaMemcpyHostToDevice, st));
+      return AB2_OK;
+    };
+    if ((rc = up(s->own_stage, stage, (size_t)N * s->srec)) != AB2_OK || (rc = up(s->own_term, term, s->trec)) != AB2_OK ||
+        (rc = up(s->own_G0, G0, (size_t)nc0 * nx)) != AB2_OK || (rc = up(s->own_g0, g0, nc0)) != AB2_OK)
+      return rc;
+    const ab2::SweepParams q = slice_params(s, b0, nb);
+    if (s->k && s->variant != 9)
+      CUDA_TRY(s->k->launch(q, s->variant, s->group_doubles, st, nullptr));
+    else
+      CUDA_TRY(ab2::launch_block(q, s->d.nx, s->d.nu, s->d.nc, st, nullptr));
+    s->launches += 1;
+    for (int i = 0; i < nwhat; ++i) {
+      const int w = whats[i];
+      const size_t per_inst = (size_t)s->out_knots[w] * s->out_rec[w];
+      if (per_inst)
+        CUDA_TRY(cudaMemcpyAsync(dsts[i] + (size_t)b0 * per_inst, s->out[w] + (size_t)b0 * per_inst,
+                                 (size_t)nb * per_inst * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+  }
+  for (int i = 0; i < NS && i < nchunks; ++i) {
+    CUDA_TRY(cudaEventRecord(s->pipe_done[i], s->pipe_stream[i]));
+    CUDA_TRY(cudaStreamWaitEvent(user, s->pipe_done[i], 0));
+  }
+  s->have_backward = true;
+  return AB2_OK;
+}
 
 size_t ab2_gar_output_doubles(const ab2_gar_solver *s, int what) {
   if (!s || what < 0 || what >= AB2_OUT_COUNT)

@@ -64,6 +64,9 @@ def lib():
         L.ab2_gar_backward.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.ab2_gar_forward.argtypes = [C.c_void_p, C.c_void_p]
         L.ab2_gar_sweep.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.ab2_gar_sweep_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_double, C.c_int, C.POINTER(C.c_int),
+                                         C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
         L.ab2_gar_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_get_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_int, C.c_void_p]
@@ -158,6 +161,18 @@ class CudaRiccatiBatch:
 
     def synchronize(self, stream=0):
         _check(lib().ab2_gar_synchronize(self.h, C.c_void_p(stream)))
+
+    def sweep_host(self, stage, term, G0, g0, mueq, outputs, nchunks=0, stream=0):
+        """Upload + sweep + download in one pipelined call (``ab2_gar_sweep_host``): the batch
+        travels in slices on internal streams so uploads, sweeps and downloads overlap.
+        ``outputs``: {OUT_*: host array of the full output size}; pinned arrays make the
+        copies asynchronous.  Asynchronous w.r.t. the host: call ``synchronize(stream)``."""
+        whats = (C.c_int * len(outputs))(*outputs.keys())
+        dsts = (C.c_void_p * len(outputs))(*[_ptr(a).value for a in outputs.values()])
+        self._keep = (stage, term, G0, g0, outputs)
+        _check(lib().ab2_gar_sweep_host(self.h, _ptr(stage), _ptr(term), _ptr(G0), _ptr(g0),
+                                        C.c_double(mueq), int(nchunks), whats, dsts, len(outputs),
+                                        C.c_void_p(stream)))
 
     # ---- results ------------------------------------------------------------
     def out_shape(self, what):

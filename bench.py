@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="slices of the pipelined e2e call (0 = auto)")
     ap.add_argument("--stagger-ns", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -292,11 +293,10 @@ def main():
                                   stagger_ns=args.stagger_ns, ctas_per_sm=args.ctas_per_sm)
 
         def e2e_step():
-            s2.set_problem(hs[0].numpy(), hs[1].numpy(), hs[2].numpy(), hs[3].numpy(),
-                           memspace=gar.AB2_HOST, stream=stream)
-            s2.sweep(MUEQ, stream=stream)
-            for w, h in zip(outs, hout):
-                s2.get_into(w, h, gar.AB2_HOST, stream=stream)
+            # one call of the public host-buffer API: upload, sweep and download pipelined
+            # over slices of the batch (PCIe full duplex: max(H2D, D2H) instead of the sum)
+            s2.sweep_host(hs[0], hs[1], hs[2], hs[3], MUEQ, dict(zip(outs, hout)),
+                          nchunks=args.e2e_chunks, stream=stream)
             s2.synchronize(stream)
 
         e2e_step()
@@ -314,7 +314,8 @@ def main():
         d2h = sum(int(np.prod(solver.out_shape(w))) for w in outs) * 8
         e2e = {"value": knots / dt, "unit": "knots/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-               "reads": "xs,us,lbdas,lbd0,ff,fb (what solver-proxddp.hxx:610-632 consumes)"}
+               "reads": "xs,us,lbdas,lbd0,ff,fb (what solver-proxddp.hxx:610-632 consumes)",
+               "api": "ab2_gar_sweep_host: upload/sweep/download pipelined over batch slices"}
         s2.close()
 
     if rank != 0:

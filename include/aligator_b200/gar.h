@@ -131,6 +131,18 @@ int ab2_gar_forward(ab2_gar_solver *s, void *stream);
 /* backward + forward in ONE persistent launch: the loop body of
  * bench/gar-riccati.cpp:46-49 and solver-proxddp.hxx:608-611. */
 int ab2_gar_sweep(ab2_gar_solver *s, double mueq, void *stream);
+/* One whole iteration of the caller's loop with HOST buffers, pipelined over the batch:
+ * upload the problem (what updateLQSubproblem rewrote, solver-proxddp.hxx:734-805), sweep,
+ * and download `nwhat` result arrays (`whats[i]` -> `dsts[i]`, full-size host arrays laid out
+ * like ab2_gar_get's; what solver-proxddp.hxx:610-632 reads back).  The batch is cut into
+ * `nchunks` slices (0 = automatic) that travel on internal streams, so the upload of slice
+ * i+1, the sweep of slice i and the download of slice i-1 overlap; PCIe is full duplex, so the
+ * step costs max(upload, download) instead of their sum.  Host buffers should be pinned
+ * (page-locked); pageable memory works but serialises.  Ordered after prior work on `stream`;
+ * work enqueued on `stream` afterwards waits for it.  Results also stay on the device. */
+int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *term, const double *G0,
+                       const double *g0, double mueq, int nchunks, const int *whats,
+                       double *const *dsts, int nwhat, void *stream);
 
 /* Replaces: getFeedforward(i)/getFeedback(i) (riccati-base.hpp:33-34), the public
  * `datas[i].vm` / `kkt0` members (proximal-riccati.hpp:40-43) and the caller-owned

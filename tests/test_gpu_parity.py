@@ -369,3 +369,32 @@ def test_shape_too_large_for_one_cta_is_refused(gar):
     assert gar.supported(120, 40, 0, 120) == 0
     with pytest.raises(gar.GarError):
         gar.CudaRiccatiBatch(120, 40, 0, 0, 120, 4, 2)
+
+
+@pytest.mark.parametrize("shape,chunks", [((12, 6, 0, 0, 20, 37, 1e-8), 5), ((4, 2, 2, 3, 10, 64, 1e-3), 0),
+                                          ((9, 5, 3, 0, 6, 11, 1e-3), 3), ((12, 6, 0, 0, 8, 3, 1e-8), 16)])
+def test_pipelined_host_sweep_equals_plain_calls(gar, shape, chunks):
+    """ab2_gar_sweep_host (upload / sweep / download pipelined over batch slices on internal
+    streams) returns bit for bit what set_problem + sweep + get return."""
+    import torch
+    nx, nu, nc, nct, N, B, mueq = shape
+    probs = gen.generate_batch(5, B, N, nx, nu, nc, nct)
+    plain, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq)
+    s = gar.CudaRiccatiBatch(nx, nu, nc, nct, probs[0].nc0, N, B)
+    pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in packed]
+    whats = dict(fb=gar.OUT_FB, ff=gar.OUT_FF, xs=gar.OUT_XS, us=gar.OUT_US, lbdas=gar.OUT_LBDAS,
+                 Vxx=gar.OUT_VXX, vsT=gar.OUT_VST)
+    outs = {w: torch.full((max(int(np.prod(s.out_shape(w))), 1),), np.nan, dtype=torch.float64).pin_memory()
+            for w in whats.values()}
+    for _ in range(2):  # twice: the internal streams/events are reused
+        s.sweep_host(pin[0], pin[1], pin[2], pin[3], mueq, outs, nchunks=chunks)
+        s.synchronize()
+    for k, w in whats.items():
+        got = outs[w].numpy()[:int(np.prod(s.out_shape(w)))].reshape(s.out_shape(w))
+        if k == "Vxx":
+            got = got.transpose(0, 1, 3, 2)
+        assert np.array_equal(got, plain[k]), k
+    assert np.all(s.status() == 0)
+    # the results also stay on the device: a plain get sees them
+    assert np.array_equal(s.get(gar.OUT_XS), plain["xs"])
+    s.close()
