@@ -33,6 +33,16 @@ __global__ void shift_left_kernel(double *base, long inst_stride, int nrec, int 
       b[(size_t)(nrec - 1) * rec + i] = 0.0;
 }
 
+// [K_0 | k_0] of every instance -> dst [batch][nu][nx+1]
+__global__ void first_step_policy_kernel(const double *__restrict__ fb, const double *__restrict__ ff,
+                                         double *__restrict__ dst, int batch, int N, int nr, int nu, int nx) {
+  const int per = nu * (nx + 1);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)batch * per; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per), e = (int)(i % per), r = e / (nx + 1), c = e % (nx + 1);
+    dst[i] = (c < nx) ? fb[((size_t)b * N * nr + r) * nx + c] : ff[(size_t)b * N * nr + r];
+  }
+}
+
 // one KernelEntry per compile-time shape, each defined in its own object file
 // (kernel_inst.cu compiled with -DAB2_NX=.. -DAB2_NU=.. -DAB2_NC=.. -DAB2_G=..)
 #define X(NX, NU, NC, G) extern const KernelEntry kEntry_##NX##_##NU##_##NC;
@@ -483,6 +493,26 @@ int ab2_gar_get_range(ab2_gar_solver *s, int what, int b0, int nb, int t0, int n
                              (size_t)nt * rec * sizeof(double), (size_t)nb,
                              memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                              (cudaStream_t)stream));
+  return AB2_OK;
+}
+
+int ab2_gar_first_step_policy(ab2_gar_solver *s, double *dst, void *stream) {
+  if (!s || !dst)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  if (s->d.horizon < 1)
+    return fail(AB2_ERR_INVALID, "first_step_policy needs horizon >= 1");
+  if (!s->have_backward)
+    return fail(AB2_ERR_STATE, "first_step_policy before backward()");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  const long total = (long)s->d.batch * s->d.nu * (s->d.nx + 1);
+  const int threads = 256;
+  long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 8)
+    blocks = 148 * 8;
+  ab2::first_step_policy_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(
+      s->out[AB2_OUT_FB], s->out[AB2_OUT_FF], dst, s->d.batch, s->d.horizon, s->nr, s->d.nu, s->d.nx);
+  CUDA_TRY(cudaGetLastError());
+  s->launches += 1;
   return AB2_OK;
 }
 

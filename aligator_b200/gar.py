@@ -70,6 +70,7 @@ def lib():
         L.ab2_gar_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_get_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_first_step_policy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ab2_gar_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ab2_gar_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_cycle_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -209,6 +210,10 @@ class CudaRiccatiBatch:
     def get_range_into(self, what, b0, nb, t0, nt, dst, memspace, stream=0):
         _check(lib().ab2_gar_get_range(self.h, what, b0, nb, t0, nt, _ptr(dst), memspace,
                                        C.c_void_p(stream)))
+
+    def first_step_policy_into(self, dst, stream=0):
+        """[K_0 | k_0] of every instance -> device buffer dst [batch][nu][nx+1]."""
+        _check(lib().ab2_gar_first_step_policy(self.h, _ptr(dst), C.c_void_p(stream)))
 
     def device_ptr(self, what):
         p = C.c_void_p()

@@ -233,21 +233,36 @@ def main():
                                   stagger_ns=args.stagger_ns, ctas_per_sm=args.ctas_per_sm)
     stream = torch.cuda.current_stream().cuda_stream
     solver.set_problem(stage, term, G0, g0, memspace=gar.AB2_DEVICE, stream=stream)
-    # first-step policy [K0; k0] per instance: the one all-gather when the batch shards
-    pol = torch.empty(B, NU, NX + 1, dtype=torch.float64, device=dev)
-    pol_all = torch.empty(world * B, NU, NX + 1, dtype=torch.float64, device=dev) if world > 1 else None
-    ff0 = torch.empty(B, NU + NX, dtype=torch.float64, device=dev)
-    fb0 = torch.empty(B, NU + NX, NX, dtype=torch.float64, device=dev)
+    # first-step policy [K0 | k0] per instance: the one all-gather when the batch shards.
+    # The gather of sweep i runs on a side stream and overlaps sweep i+1 (two buffers).
+    pol = [torch.empty(B, NU, NX + 1, dtype=torch.float64, device=dev) for _ in range(2)]
+    pol_all = [torch.empty(world * B, NU, NX + 1, dtype=torch.float64, device=dev) for _ in range(2)] \
+        if world > 1 else None
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream() if world > 1 else None
+    gathered = [None, None]
+    step_no = [0]
 
     from aligator_b200 import sharding
 
     def step():
         solver.sweep(MUEQ, stream=stream)
         if world > 1:  # the one exchange: all-gather of the first-step policy [K0 | k0]
-            solver.get_range_into(gar.OUT_FB, 0, B, 0, 1, fb0, gar.AB2_DEVICE, stream=stream)
-            solver.get_range_into(gar.OUT_FF, 0, B, 0, 1, ff0, gar.AB2_DEVICE, stream=stream)
-            sharding.pack_first_step_policy(torch, fb0, ff0, NU, NX, out=pol)
-            sharding.all_gather_policy(torch, dist, pol, world, out=pol_all)
+            i = step_no[0] & 1
+            step_no[0] += 1
+            if gathered[i] is not None:
+                main.wait_event(gathered[i])  # the gather that last read pol[i] is done
+            solver.first_step_policy_into(pol[i], stream=stream)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                sharding.all_gather_policy(torch, dist, pol[i], world, out=pol_all[i])
+                ev = torch.cuda.Event()
+                ev.record(side)
+            gathered[i] = ev
+
+    def join():  # every gather issued so far has completed before the timer stops
+        if side is not None:
+            main.wait_stream(side)
 
     def barrier():
         if world > 1:
@@ -267,6 +282,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    join()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)

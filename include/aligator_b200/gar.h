@@ -153,6 +153,11 @@ int ab2_gar_get(ab2_gar_solver *s, int what, double *dst, int memspace, void *st
 int ab2_gar_get_range(ab2_gar_solver *s, int what, int b0, int nb, int t0, int nt,
                       double *dst, int memspace, void *stream);
 /* Device-resident consumers: raw device pointer of an output array. */
+/* First-step policy of every instance, packed [batch][nu][nx+1] = [K_0 | k_0] (row-major) into
+ * the DEVICE buffer `dst` by one small kernel: what a receding-horizon consumer applies
+ * (results_.gains_[0], solver-proxddp.hxx:619-626) and the payload of the one all-gather when
+ * the batch is sharded across GPUs. */
+int ab2_gar_first_step_policy(ab2_gar_solver *s, double *dst, void *stream);
 int ab2_gar_device_ptr(ab2_gar_solver *s, int what, double **out);
 /* Per-instance status words (layout above). */
 int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream);

@@ -398,3 +398,22 @@ def test_pipelined_host_sweep_equals_plain_calls(gar, shape, chunks):
     # the results also stay on the device: a plain get sees them
     assert np.array_equal(s.get(gar.OUT_XS), plain["xs"])
     s.close()
+
+
+def test_first_step_policy_kernel(gar):
+    """ab2_gar_first_step_policy packs [K_0 | k_0] exactly as the host-side reference packing
+    of knot 0 of OUT_FB / OUT_FF (aligator_b200.sharding.pack_first_step_policy)."""
+    import torch
+    from aligator_b200 import sharding
+    nx, nu, nc, nct, N, B, mueq = 12, 6, 0, 0, 10, 9, 1e-8
+    probs = gen.generate_batch(3, B, N, nx, nu, nc, nct)
+    s = gar.CudaRiccatiBatch(nx, nu, nc, nct, nx, N, B)
+    s.set_problem(*gar.pack_problems(probs))
+    s.sweep(mueq)
+    pol = torch.full((B, nu, nx + 1), float("nan"), dtype=torch.float64, device="cuda")
+    s.first_step_policy_into(pol)
+    s.synchronize()
+    fb, ff = s.get(gar.OUT_FB), s.get(gar.OUT_FF)
+    want = sharding.pack_first_step_policy(torch, torch.from_numpy(fb[:, 0]), torch.from_numpy(ff[:, 0]), nu, nx)
+    assert torch.equal(pol.cpu(), want)
+    s.close()
