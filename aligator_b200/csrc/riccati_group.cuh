@@ -144,7 +144,10 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   static constexpr int RS = ev(NX + 1);      // row stride of rhs0 / sol
   // shared-memory layout of one group (doubles); every region starts 16-byte aligned
   static constexpr int S_REC = 0;
-  static constexpr int S_VN = S_REC + (DB ? 2 : 1) * SREC_PAD; // V' (symmetric, full)
+  // tensor-core step: two zero doubles behind each record buffer -- the entry every
+  // structural zero of H0 points at (no compare/select when the accumulators are loaded)
+  static constexpr int RSTRIDE = SREC_PAD + (MMA ? 2 : 0);
+  static constexpr int S_VN = S_REC + (DB ? 2 : 1) * RSTRIDE; // V' (symmetric, full)
   static constexpr int S_VXN = S_VN + ev(VROWS * VS);          // vx'
   static constexpr int S_KKT = S_VXN + ev(NX);                 // NK*NK column-major
   static constexpr int S_RHS = S_KKT + ev(NK * NK);            // NK x RS, unsolved rhs
@@ -579,11 +582,14 @@ template <int N> struct FastFactor {
     for (int k = 0; k < N; ++k) {
       const double akk = a[k][k];
       const double abs_akk = fabs(akk);
-      double colmax = 0.0;
+      // |akk| >= alpha * colmax  <=>  |akk| >= alpha * |a_ik| for every i (rounding is
+      // monotone), and a zero pivot fails one of the two tests of the general algorithm
+      // either way: one multiply + one compare per entry instead of an fp64 max
+      // (which costs a compare and two selects).
+      good = good && (abs_akk > 0.0);
       AB2_UNROLL
       for (int i = k + 1; i < N; ++i)
-        colmax = fmax(colmax, fabs(a[i][k]));
-      good = good && (abs_akk >= colmax * alpha) && (fmax(abs_akk, colmax) != 0.0);
+        good = good && (fabs(a[i][k]) * alpha <= abs_akk);
       const double d11 = rcp_fast(akk);
       d[k] = d11;
       AB2_UNROLL
@@ -917,18 +923,22 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     for (int nt = 0; nt < NT; ++nt) {
       const int o0 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q);
       const int o1 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q + 1);
-      lut[(NT + mt * NT + nt) * 32 + lane] = (int)((unsigned)(o0 & 0xffff) | ((unsigned)(o1 & 0xffff) << 16));
+      const unsigned u0 = o0 < 0 ? (unsigned)C::SREC_PAD : (unsigned)o0; // structural zero -> the zero slot
+      const unsigned u1 = o1 < 0 ? (unsigned)C::SREC_PAD : (unsigned)o1;
+      lut[(NT + mt * NT + nt) * 32 + lane] = (int)(u0 | (u1 << 16));
     }
   }
+  if (lane < 4)
+    sm[C::S_REC + (lane >> 1) * C::RSTRIDE + C::SREC_PAD + (lane & 1)] = 0.0;
   ctx.sync();
 
   const bool colS = lane <= NX; // this lane solves right-hand-side column `lane` ([K | k])
   int cur = 0;
   for (int t = N - 1; t >= 0; --t) {
     ctx.wait_copy(cur);
-    double *rec = sm + C::S_REC + cur * C::SREC_PAD;
+    double *rec = sm + C::S_REC + cur * C::RSTRIDE;
     if (t > 0) // stream the next knot into the other buffer during this step
-      ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::SREC_PAD,
+      ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::RSTRIDE,
                      AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
     cur ^= 1;
     if (t >= 4) { // and pull the record of 4 knots ahead into L2 (one 128-byte line per lane)
@@ -991,7 +1001,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
         AB2_UNROLL
         for (int e = 0; e < 2; ++e) {
           const unsigned o = ((unsigned)lut[(NT + mt * NT + nt) * 32 + lane] >> (16 * e)) & 0xffffu;
-          H[mt][nt][e] = (o != 0xffffu) ? rec[o != 0xffffu ? o : 0] : 0.0;
+          H[mt][nt][e] = rec[o];
         }
       }
     }
@@ -1084,9 +1094,11 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
         for (int nt = 0; nt < NT2; ++nt) {
           AB2_UNROLL
           for (int e = 0; e < 2; ++e) {
+            // rows i >= NX and columns jj > NX of the accumulator are never stored: any
+            // finite value will do there, so no select
             const int jj = 8 * nt + 2 * q + e;
-            const double v = rec[C::col_offset(jj <= NX ? jj : 0) + ic];
-            EA[mt][nt][e] = (i < NX && jj <= NX) ? v : 0.0;
+            const int off = (jj < NX) ? jj * NX : ((jj == NX) ? C::OFF_F : 0);
+            EA[mt][nt][e] = rec[off + ic];
           }
         }
         AB2_UNROLL
@@ -1304,9 +1316,9 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     for (int t = N - 1; t >= 0; --t) {
       if (C::DB) {
         ctx.wait_copy(cur);
-        rec = sm + C::S_REC + cur * C::SREC_PAD;
+        rec = sm + C::S_REC + cur * C::RSTRIDE;
         if (t > 0) // stream the next knot into the other buffer during this step
-          ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::SREC_PAD,
+          ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::RSTRIDE,
                          stage_b + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
         cur ^= 1;
       } else {
