@@ -198,12 +198,19 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   }
 
   // forward rollout: slots of the fb ring (as many as the stage area can hold, at most 8)
-  static constexpr int FWD_RING_RAW = (S_STAGE_END - 2 * ev(NX)) / ev(NR * NX);
-  static constexpr int FWD_RING = FWD_RING_RAW > 8 ? 8 : (FWD_RING_RAW < 1 ? 1 : FWD_RING_RAW);
   static constexpr bool FB_BULK = ((NR * NX) % 2) == 0; // 16-byte granularity for bulk copies
-  static constexpr int FWD_SLOT = ev(NR * NX);           // doubles per ring slot
+  // Fused forward (tensor-core builds): the ring slot of knot t also carries Vxx_t and vx_t
+  // -- laid out behind the gain rows as NX more "rows" plus their bias -- so the lanes that
+  // pass 1 leaves idle compute lbda_t = vx_t + Vxx_t x_t in the same iteration: no second
+  // pass, no register-staged global loads.
+  static constexpr bool FWD_FUSED = MMA && FB_BULK && (NX % 2 == 0);
+  static constexpr int FWD_ROWS = FWD_FUSED ? NR + NX : NR;
+  static constexpr int FWD_SLOT = FWD_FUSED ? (NR + NX) * NX + NX : ev(NR * NX); // doubles per ring slot
+  static constexpr int FWD_RING_RAW = (S_STAGE_END - 2 * ev(NX)) / FWD_SLOT;
+  static constexpr int FWD_RING_MIN = FWD_FUSED ? 4 : 1; // (the fused ring may outgrow the stage area)
+  static constexpr int FWD_RING = FWD_RING_RAW > 8 ? 8 : (FWD_RING_RAW < FWD_RING_MIN ? FWD_RING_MIN : FWD_RING_RAW);
   static constexpr int NXE = ev(NX);
-  static_assert(FWD_RING * ev(NR * NX) + 2 * ev(NX) <= S_STAGE_END, "forward ring does not fit");
+  static constexpr int FWD_END = FWD_RING * FWD_SLOT + 2 * ev(NX);
   static_assert(NU >= 1, "stage knots need nu >= 1");
   static_assert(NCOL <= G, "lane-per-column mapping needs nx+nu+1 <= G");
   static_assert(NK <= G, "cooperative Bunch-Kaufman needs nu+nc <= G");
@@ -214,6 +221,7 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
     const int n0 = NX + nc0;
     const int k0 = n0 * n0 + 6 * n0 + 2; // K0, b, x, dd, sd, out, 2*n0 ints
     int m = S_STAGE_END > k0 ? S_STAGE_END : k0;
+    m = m > FWD_END ? m : FWD_END;
     return (m + 1) & ~1;
   }
   static AB2_HD int term_rec(int nct) { return NX * NX + NX + nct * NX + nct; }
@@ -930,6 +938,8 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
   }
   if (lane < 4)
     sm[C::S_REC + (lane >> 1) * C::RSTRIDE + C::SREC_PAD + (lane & 1)] = 0.0;
+  for (int i = lane; i < C::S_MMA_END - C::S_WSM; i += 32)
+    Wsm[i] = 0.0; // W / X / KK share this space; its padding entries must be finite
   ctx.sync();
 
   const bool colS = lane <= NX; // this lane solves right-hand-side column `lane` ([K | k])
@@ -1070,15 +1080,15 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
       }
     }
     ctx.sync();
-    // fragments of KK = [K k] (rows >= NK are zero)
+    // fragments of KK = [K k].  No predicates: rows >= NK meet the structural zeros of the
+    // other operand (they only have to be finite -- the buffer was zeroed once and is
+    // shared with W), columns > NX feed accumulator entries nobody stores.
     double KKf[KT2][NT2];
     AB2_UNROLL
     for (int k2 = 0; k2 < KT2; ++k2) {
       AB2_UNROLL
       for (int nt = 0; nt < NT2; ++nt)
-        KKf[k2][nt] = (4 * k2 + q < NK && 8 * nt + g <= NX)
-                          ? KKs[(4 * k2 + q < NK ? 4 * k2 + q : 0) * SX + (8 * nt + g <= NX ? 8 * nt + g : 0)]
-                          : 0.0; // padding of the fragment: structural zeros
+        KKf[k2][nt] = KKs[(4 * k2 + q) * SX + 8 * nt + g];
     }
     // (4) [Ahat a] = [A f] + B KK   (:266-267)   and
     // (5) [Vxx vx] = [Qhat qhat] + Shat KK, with Shat[i][c] = X[c][i]   (:270-277)
@@ -1104,10 +1114,11 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
         AB2_UNROLL
         for (int k2 = 0; k2 < KT2; ++k2) {
           const int c = 4 * k2 + q;
+          // (rows i >= NX of both accumulators are never stored: no row predicate)
           const double bv = rec[C::OFF_B + (c < NU ? c : 0) * NX + ic];
-          Bf[mt][k2] = (c < NU && i < NX) ? bv : 0.0;
-          const double xv = X[(c < NK ? c : 0) * SX + (i <= NX ? i : 0)];
-          Xf[mt][k2] = (c < NK && i <= NX) ? xv : 0.0;
+          Bf[mt][k2] = (c < NU) ? bv : 0.0;
+          const double xv = X[c * SX + i];
+          Xf[mt][k2] = (c < NK) ? xv : 0.0;
         }
       }
       AB2_UNROLL
@@ -1624,7 +1635,10 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     // cover HBM latency); ff travels in a register pipeline of the same depth.
     constexpr int RING = C::FWD_RING;
     constexpr int FS = C::FWD_SLOT;
-    constexpr int RPL = (NR + C::G - 1) / C::G; // gain rows per lane
+    constexpr bool FUSED = C::FWD_FUSED;
+    constexpr int ROWS = C::FWD_ROWS;             // gain rows (+ NX lambda rows when fused)
+    constexpr int RPL = (ROWS + C::G - 1) / C::G; // rows per lane
+    const int NIT = FUSED ? N + 1 : N;            // the fused loop has one more iteration: lbda_N
     constexpr bool EVF = C::EVEN;
     double *ring = sm;                 // RING x FS doubles (the backward's buffers are dead)
     double *xc = sm + RING * FS;       // x_t
@@ -1632,7 +1646,13 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     (void)xv;
     ctx.sync();
     auto fill_slot = [&](int d, int t) { // fb record of knot t -> ring slot d
-      if (C::FB_BULK) {
+      if (FUSED) { // [K; Z; Ahat]_t | Vxx_t (symmetric for t >= 1: row i = column i) | vx_t
+        ctx.copy_expect(d, (t < N ? NR * NX : 0) + NX * NX + NX);
+        if (t < N)
+          ctx.copy_add(d, ring + d * FS, fb_b + (size_t)t * NR * NX, NR * NX);
+        ctx.copy_add(d, ring + d * FS + NR * NX, Vxx_b + (size_t)t * NX * NX, NX * NX);
+        ctx.copy_add(d, ring + d * FS + (NR + NX) * NX, vx_b + (size_t)t * NX, NX);
+      } else if (C::FB_BULK) {
         ctx.issue_copy(d, ring + d * FS, fb_b + (size_t)t * NR * NX, NR * NX);
       } else { // odd record size: no 16-byte granularity, plain cooperative copy
         for (int i2 = lane; i2 < NR * NX; i2 += C::G)
@@ -1641,7 +1661,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     };
     AB2_UNROLL
     for (int d = 0; d < RING; ++d)
-      if (d < N)
+      if (d < NIT)
         fill_slot(d, d);
     if (lane < NX) {
       const double v = k0[lane];
@@ -1660,19 +1680,22 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       }
     }
     ctx.sync();
-    for (int t0 = 0; t0 < N; t0 += RING) {
+    for (int t0 = 0; t0 < NIT; t0 += RING) {
       AB2_UNROLL
       for (int d = 0; d < RING; ++d) {
         const int t = t0 + d;
-        if (t < N) {
+        if (t < NIT) {
           if (C::FB_BULK)
             ctx.wait_copy(d);
           const double *slot = ring + d * FS;
           AB2_UNROLL
           for (int q = 0; q < RPL; ++q) {
             const int r = lane + q * C::G;
-            if (r < NR) {
+            // gain rows exist for t < N; lambda rows (fused) for t >= 1
+            if (FUSED ? ((r < NR && t < N) || (r >= NR && r < ROWS && t >= 1)) : (r < NR)) {
               double s0 = gff[d][q], s1 = 0.0; // two chains halve the dependent-FMA latency
+              if (FUSED && r >= NR)
+                s0 = slot[(NR + NX) * NX + (r - NR)]; // vx_t
               if (EVF) {
                 AB2_UNROLL
                 for (int c = 0; c < NX; c += 2) {
@@ -1691,18 +1714,23 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
                 us_b[(size_t)t * NU + r] = s;
               else if (r < NK)
                 vs_b[(size_t)t * NC + (r - NU)] = s;
-              else {
+              else if (!FUSED || r < NR) {
                 xnx[r - NK] = s;
                 xs_b[(size_t)(t + 1) * NX + (r - NK)] = s;
+              } else {
+                lb_b[(size_t)(t - 1) * NX + (r - NR)] = s; // lbda_t = vx_t + Vxx_t x_t
               }
-              gff[d][q] = (t + RING < N) ? ff_b[(size_t)(t + RING) * NR + r] : 0.0;
+              if (!FUSED || r < NR)
+                gff[d][q] = (t + RING < N) ? ff_b[(size_t)(t + RING) * NR + r] : 0.0;
             }
           }
-          double *tmp = xc;
-          xc = xnx;
-          xnx = tmp;
+          if (t < N) {
+            double *tmp = xc;
+            xc = xnx;
+            xnx = tmp;
+          }
           ctx.sync(); // x_{t+1} visible; every lane is done with x_t and with this slot
-          if (t + RING < N)
+          if (t + RING < NIT)
             fill_slot(d, t + RING);
         }
       }
@@ -1710,7 +1738,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     // Pass 2 -- the parallel part: lbda_{t+1} = vx_{t+1} + Vxx_{t+1} x_{t+1} has no
     // dependence between knots: G/NX knots per iteration, two iterations batched so that
     // all their loads are in flight together; no synchronisation.
-    {
+    if (!FUSED) {
       constexpr int KPI = (C::G / NX) > 0 ? (C::G / NX) : 1; // knots per iteration
       constexpr int U = 2;
       const int sub = lane / NX, i = lane % NX;

@@ -73,6 +73,32 @@ template <int G, bool TMA> struct DevCtx {
     }
   }
 
+  // Several bulk copies completing on ONE barrier phase: announce the total, then add the pieces.
+  __device__ __forceinline__ void copy_expect(int part, int nd_total) {
+    if (TMA) {
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * part),
+                     "r"((uint32_t)nd_total * 8u)
+                     : "memory");
+    }
+  }
+  __device__ __forceinline__ void copy_add(int part, double *dst, const double *src, int nd) {
+    if (TMA) {
+      if (lane == 0)
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(dst)),
+            "l"(src), "r"((uint32_t)nd * 8u), "r"(bar0 + 8 * part)
+            : "memory");
+    } else {
+      const uint32_t d = smem_u32(dst);
+      for (int c = lane; c < nd / 2; c += G)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * c), "l"(src + 2 * c)
+                     : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+
   // Every lane that wrote (through the generic proxy) shared memory a bulk store will read
   // calls this BEFORE the group synchronisation that precedes bulk_store().
   __device__ __forceinline__ void async_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
