@@ -205,9 +205,13 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   // pass, no register-staged global loads.
   static constexpr bool FWD_FUSED = MMA && FB_BULK && (NX % 2 == 0);
   static constexpr int FWD_ROWS = FWD_FUSED ? NR + NX : NR;
-  static constexpr int FWD_SLOT = FWD_FUSED ? (NR + NX) * NX + NX : ev(NR * NX); // doubles per ring slot
+  static constexpr bool FWD_FF = FWD_FUSED && (NR % 2 == 0); // ff_t rides in the slot too (no LDG in pass 1)
+  static constexpr int FWD_SLOT =
+      FWD_FUSED ? (NR + NX) * NX + NX + (FWD_FF ? NR : 0) : ev(NR * NX); // doubles per ring slot
   static constexpr int FWD_RING_RAW = (S_STAGE_END - 2 * ev(NX)) / FWD_SLOT;
-  static constexpr int FWD_RING_MIN = FWD_FUSED ? 4 : 1; // (the fused ring may outgrow the stage area)
+  // the fused ring may outgrow the stage area: at least 4 slots, 5 when that costs < 12 %
+  static constexpr int FWD_RING_MIN =
+      FWD_FUSED ? ((5 * FWD_SLOT + 2 * ev(NX)) * 100 <= S_STAGE_END * 112 ? 5 : 4) : 1;
   static constexpr int FWD_RING = FWD_RING_RAW > 8 ? 8 : (FWD_RING_RAW < FWD_RING_MIN ? FWD_RING_MIN : FWD_RING_RAW);
   static constexpr int NXE = ev(NX);
   static constexpr int FWD_END = FWD_RING * FWD_SLOT + 2 * ev(NX);
@@ -1647,9 +1651,12 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     ctx.sync();
     auto fill_slot = [&](int d, int t) { // fb record of knot t -> ring slot d
       if (FUSED) { // [K; Z; Ahat]_t | Vxx_t (symmetric for t >= 1: row i = column i) | vx_t
-        ctx.copy_expect(d, (t < N ? NR * NX : 0) + NX * NX + NX);
-        if (t < N)
+        ctx.copy_expect(d, (t < N ? NR * NX + (C::FWD_FF ? NR : 0) : 0) + NX * NX + NX);
+        if (t < N) {
           ctx.copy_add(d, ring + d * FS, fb_b + (size_t)t * NR * NX, NR * NX);
+          if (C::FWD_FF)
+            ctx.copy_add(d, ring + d * FS + (NR + NX) * NX + NX, ff_b + (size_t)t * NR, NR);
+        }
         ctx.copy_add(d, ring + d * FS + NR * NX, Vxx_b + (size_t)t * NX * NX, NX * NX);
         ctx.copy_add(d, ring + d * FS + (NR + NX) * NX, vx_b + (size_t)t * NX, NX);
       } else if (C::FB_BULK) {
@@ -1676,7 +1683,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       AB2_UNROLL
       for (int q = 0; q < RPL; ++q) {
         const int r = lane + q * C::G;
-        gff[d][q] = (r < NR && d < N) ? ff_b[(size_t)d * NR + r] : 0.0;
+        gff[d][q] = (!C::FWD_FF && r < NR && d < N) ? ff_b[(size_t)d * NR + r] : 0.0;
       }
     }
     ctx.sync();
@@ -1694,8 +1701,8 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
             // gain rows exist for t < N; lambda rows (fused) for t >= 1
             if (FUSED ? ((r < NR && t < N) || (r >= NR && r < ROWS && t >= 1)) : (r < NR)) {
               double s0 = gff[d][q], s1 = 0.0; // two chains halve the dependent-FMA latency
-              if (FUSED && r >= NR)
-                s0 = slot[(NR + NX) * NX + (r - NR)]; // vx_t
+              if (FUSED && (C::FWD_FF || r >= NR)) // ff_t sits right behind vx_t: one bias vector
+                s0 = slot[(NR + NX) * NX + (r >= NR ? r - NR : NX + r)];
               if (EVF) {
                 AB2_UNROLL
                 for (int c = 0; c < NX; c += 2) {
@@ -1720,7 +1727,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
               } else {
                 lb_b[(size_t)(t - 1) * NX + (r - NR)] = s; // lbda_t = vx_t + Vxx_t x_t
               }
-              if (!FUSED || r < NR)
+              if (!C::FWD_FF && (!FUSED || r < NR))
                 gff[d][q] = (t + RING < N) ? ff_b[(size_t)(t + RING) * NR + r] : 0.0;
             }
           }
