@@ -95,7 +95,7 @@ struct ab2_gar_solver {
   bool have_problem = false, have_backward = false;
   long launches = 0;
   int variant = -1;
-  int group_doubles[3] = {0, 0, 0};
+  int group_doubles[4] = {0, 0, 0, 0};
   // ab2_gar_sweep_host: internal streams, one event per stream + a fork event
   static constexpr int kPipeStreams = 4;
   cudaStream_t pipe_stream[kPipeStreams] = {};
@@ -258,8 +258,8 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
 int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t) {
   if (!s || !t)
     return fail(AB2_ERR_INVALID, "null argument");
-  if (t->variant < -1 || t->variant > 9)
-    return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..9");
+  if (t->variant < -1 || t->variant > 10)
+    return fail(AB2_ERR_INVALID, "variant must be -1 (default) or 0..10");
   if (t->variant == 9 && !ab2::block_supported(s->d.nx, s->d.nu, s->d.nc, s->d.nc0))
     return fail(AB2_ERR_UNSUPPORTED, "variant 9 (CTA per instance) does not fit this shape");
   if (t->stagger_ns < 0 || t->stagger_ns > 100000 || t->ctas_per_sm < 0 || t->ctas_per_sm > 32)

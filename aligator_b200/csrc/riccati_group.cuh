@@ -164,8 +164,8 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   static constexpr int S_MMA_END = S_WSM + (ev(WROWS * SW) > 2 * ev(XROWS * SX) ? ev(WROWS * SW) : 2 * ev(XROWS * SX));
   static constexpr int S_STAGE_END = S_MMA_END;
   static_assert(!MMA || SREC_PAD < 0xffff, "record offsets are packed in 16 bits");
-  static_assert(!MMA || (DB_ && G_ == 32 && NC_ == 0 && (NX_ % 2 == 0)),
-                "the tensor-core step needs double-buffered records, a full warp, nc = 0, even nx");
+  static_assert(!MMA || (G_ == 32 && NC_ == 0 && (NX_ % 2 == 0)),
+                "the tensor-core step needs a full warp, nc = 0, even nx");
 
   // rec offset of logical column jp of [A | f | B] (padding columns alias column 0)
   static AB2_HD int col_offset(int jp) {
@@ -203,7 +203,8 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   // -- laid out behind the gain rows as NX more "rows" plus their bias -- so the lanes that
   // pass 1 leaves idle compute lbda_t = vx_t + Vxx_t x_t in the same iteration: no second
   // pass, no register-staged global loads.
-  static constexpr bool FWD_FUSED = MMA && FB_BULK && (NX % 2 == 0);
+  // (only when the lambda rows find idle lanes: nu + nc + 2 nx <= G)
+  static constexpr bool FWD_FUSED = MMA && FB_BULK && (NX % 2 == 0) && (NR + NX <= G);
   static constexpr int FWD_ROWS = FWD_FUSED ? NR + NX : NR;
   static constexpr bool FWD_FF = FWD_FUSED && (NR % 2 == 0); // ff_t rides in the slot too (no LDG in pass 1)
   static constexpr int FWD_SLOT =
@@ -940,7 +941,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
       lut[(NT + mt * NT + nt) * 32 + lane] = (int)(u0 | (u1 << 16));
     }
   }
-  if (lane < 4)
+  if (lane < (C::DB ? 4 : 2))
     sm[C::S_REC + (lane >> 1) * C::RSTRIDE + C::SREC_PAD + (lane & 1)] = 0.0;
   for (int i = lane; i < C::S_MMA_END - C::S_WSM; i += 32)
     Wsm[i] = 0.0; // W / X / KK share this space; its padding entries must be finite
@@ -949,12 +950,17 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
   const bool colS = lane <= NX; // this lane solves right-hand-side column `lane` ([K | k])
   int cur = 0;
   for (int t = N - 1; t >= 0; --t) {
-    ctx.wait_copy(cur);
-    double *rec = sm + C::S_REC + cur * C::RSTRIDE;
-    if (t > 0) // stream the next knot into the other buffer during this step
-      ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::RSTRIDE,
-                     AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
-    cur ^= 1;
+    // DB: the record of knot t-1 streams into the other buffer during this step.
+    // Single buffer (smaller footprint -> more resident CTAs): the record is refilled in two
+    // parts as soon as each is consumed -- the cost blocks after (2), [A|B|f] after (5).
+    ctx.wait_copy(C::DB ? cur : 0);
+    double *rec = sm + C::S_REC + (C::DB ? cur : 0) * C::RSTRIDE;
+    if (C::DB) {
+      if (t > 0)
+        ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::RSTRIDE,
+                       AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
+      cur ^= 1;
+    }
     if (t >= 4) { // and pull the record of 4 knots ahead into L2 (one 128-byte line per lane)
       const char *nxt = reinterpret_cast<const char *>(AB2_STAGE_B + (size_t)(t - 4) * C::SREC_PAD);
       for (int o = lane * 128; o < C::SREC_PAD * 8; o += C::G * 128)
@@ -1007,6 +1013,8 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     }
     ctx.sync();
     // (2) H = H0 + M^T W
+    if (!C::DB)
+      ctx.wait_copy(1); // the cost blocks of this knot
     double H[NT][NT][2];
     AB2_UNROLL
     for (int mt = 0; mt < NT; ++mt) {
@@ -1032,6 +1040,9 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     }
     // (3) control rows of H: [Shat^T | rhat] -> X, Rhat -> KKT matrix (:232-257)
     ctx.sync(); // every lane has its W fragments: the storage becomes X / KK
+    if (!C::DB && t > 0) // ... and its H0 entries: the cost blocks of knot t-1 may land
+      ctx.issue_copy(1, rec + C::SPLIT, AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD + C::SPLIT,
+                     C::SREC_PAD - C::SPLIT);
     AB2_UNROLL
     for (int mt = 0; mt < NT; ++mt) {
       const int c = 8 * mt + g - NX - 1;
@@ -1186,6 +1197,8 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     if (C::VXX_BULK && t > 0)
       ctx.async_fence(); // this lane's writes to V' become visible to the TMA store below
     ctx.sync();
+    if (!C::DB && t > 0) // [A|B|f] of this knot is consumed (the closing products hold it in registers)
+      ctx.issue_copy(0, rec, AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD, C::SPLIT);
     if (t > 0) { // symmetric Vxx_t, as the next step of the reference leaves it
       double *Vt = AB2_VXX_B + (size_t)t * NX * NX;
       if (C::VXX_BULK) { // V' is dense in shared memory: one TMA bulk store, no LDS/STG

@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
 struct KernelEntry {
   int nx, nu, nc, G;
   int srec_pad;
-  void (*group_doubles)(int nc0, int gd[3]);
-  cudaError_t (*launch)(const SweepParams &, int variant, const int gd[3], cudaStream_t, int *info);
+  void (*group_doubles)(int nc0, int gd[4]);
+  cudaError_t (*launch)(const SweepParams &, int variant, const int gd[4], cudaStream_t, int *info);
 };
 
 template <class C, int WARPS, int MAXREG, bool TMA>
@@ -256,18 +256,38 @@ inline cudaError_t launch_one(const SweepParams &p, int gd, cudaStream_t st, int
 //   6: as 0 capped at 128 registers (8 CTAs = 16 warps per SM)
 //   7: stage step on the FP64 tensor cores (DMMA m8n8k4), 128 registers, 16 warps per SM
 //   8: as 7 with 168 registers (12 warps per SM, no spills)
+//  10: as 7 with a single record buffer refilled in two parts (smallest shared-memory footprint)
 template <int NX, int NU, int NC, int G>
-inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[3], cudaStream_t st, int *info) {
+inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[4], cudaStream_t st, int *info) {
   using CS = Cfg<NX, NU, NC, G, false>;
   using CD = Cfg<NX, NU, NC, G, true>;
   if (variant < 0) {
     variant = 6;
     if constexpr (G == 32 && NC == 0 && NX % 2 == 0) {
-      // 16 warps/SM (128 registers) needs <= 27 KB of shared memory per 2-warp CTA;
-      // larger states run the 168-register build (12 warps/SM, no spills).
-      const size_t smem2 = (size_t)2 * gd[2] * sizeof(double) + 2 * 8 * NBAR +
-                           (size_t)Cfg<NX, NU, NC, G, true, true, true>::LUT_INTS * 4;
-      variant = (smem2 + 1024) * 8 <= 227 * 1024 ? 7 : 8;
+      // Tensor-core builds.  What decides is the number of ROUNDS the batch needs:
+      //   7: double-buffered records, 128 registers (<= 8 CTAs/SM)
+      //   8: double-buffered records, 168 registers, no spills (<= 6 CTAs/SM)
+      //  10: single record buffer, 128 registers: the smallest footprint (<= 8 CTAs/SM)
+      // fewest rounds wins; ties go to 7 when it reaches 8 CTAs/SM, else 8, else 10.
+      using CM = Cfg<NX, NU, NC, G, true, true, true>;
+      const int sms = p.num_sms > 0 ? p.num_sms : 148;
+      const int grid = (p.batch + 1) / 2;
+      auto ctas = [&](int gdw, int cap) {
+        const size_t smem = (size_t)2 * gdw * sizeof(double) + 2 * 8 * NBAR + (size_t)CM::LUT_INTS * 4;
+        const int c = (int)((size_t)227 * 1024 / (smem + 1024));
+        return c < cap ? (c < 1 ? 1 : c) : cap;
+      };
+      auto rounds = [&](int c) { return (grid + sms * c - 1) / (sms * c); };
+      const int c7 = ctas(gd[2], 8), c8 = ctas(gd[2], 6), c10 = ctas(gd[3], 8);
+      const int r7 = rounds(c7), r8 = rounds(c8), r10 = rounds(c10);
+      if (c7 == 8 && r7 <= r8 && r7 <= r10)
+        variant = 7;
+      else if (r8 <= r7 && r8 <= r10)
+        variant = 8;
+      else if (r10 < r7)
+        variant = 10;
+      else
+        variant = 7;
     }
   }
   if (variant == 1)
@@ -286,17 +306,22 @@ inline cudaError_t launch_cfg(const SweepParams &p, int variant, const int gd[3]
     using CM = Cfg<NX, NU, NC, G, true, true, true>;
     if (variant == 7) // stage step on the FP64 tensor cores (DMMA), 2 warps/CTA
       return launch_one<CM, 2, 128, true>(p, gd[2], st, info);
-    if (variant == 8) // same, 4 warps/CTA
+    if (variant == 8) // same, 168 registers
       return launch_one<CM, 2, 168, true>(p, gd[2], st, info);
+    if (variant == 10) // same as 7 with a single record buffer refilled in two parts
+      return launch_one<Cfg<NX, NU, NC, G, false, true, true>, 2, 128, true>(p, gd[3], st, info);
   }
   return launch_one<CD, 2, 144, true>(p, gd[1], st, info);
 }
-template <int NX, int NU, int NC, int G> inline void group_doubles_cfg(int nc0, int gd[3]) {
+template <int NX, int NU, int NC, int G> inline void group_doubles_cfg(int nc0, int gd[4]) {
   gd[0] = Cfg<NX, NU, NC, G, false>::group_doubles(nc0);
   gd[1] = Cfg<NX, NU, NC, G, true>::group_doubles(nc0);
   gd[2] = gd[1];
-  if constexpr (G == 32 && NC == 0 && NX % 2 == 0)
+  gd[3] = gd[0];
+  if constexpr (G == 32 && NC == 0 && NX % 2 == 0) {
     gd[2] = Cfg<NX, NU, NC, G, true, true, true>::group_doubles(nc0);
+    gd[3] = Cfg<NX, NU, NC, G, false, true, true>::group_doubles(nc0);
+  }
 }
 
 } // namespace ab2

@@ -89,7 +89,7 @@ typedef struct ab2_gar_dims {
 
 /* launch tuning.  variant: -1 = automatic (the FP64 tensor-core formulation where the
  * shape allows it, else the lane-per-column one; the CTA-per-instance kernel for shapes
- * without a compile-time instantiation); 0..8 select a specific warp-per-instance build,
+ * without a compile-time instantiation); 0..8 and 10 select a specific warp-per-instance build,
  * see csrc/riccati_launch.cuh; 9 forces the CTA-per-instance kernel (csrc/riccati_block.cuh). */
 typedef struct ab2_gar_tuning {
   int variant;

@@ -81,6 +81,12 @@ template <int NX, int NU, int NC, int G> int dispatch(int mode, const ab2::Sweep
     else
       return 3;
   }
+  if (mode == 3) { // tensor-core formulation, single record buffer
+    if constexpr (G == 32 && NC == 0 && NX % 2 == 0)
+      return run<ab2::Cfg<NX, NU, NC, G, false, true, true>>(p);
+    else
+      return 3;
+  }
   return mode ? run<ab2::Cfg<NX, NU, NC, G, true>>(p) : run<ab2::Cfg<NX, NU, NC, G, false>>(p);
 }
 

@@ -306,11 +306,12 @@ def test_unconstrained_knots_that_need_interchanges(gar, shape, variant):
     compare(got, ref, nu, nc, N, 1e-8, tol=1e-9)
 
 
-@pytest.mark.parametrize("variant", [7, 8])
+@pytest.mark.parametrize("variant", [7, 8, 10])
 @pytest.mark.parametrize("shape", [(12, 6, 0, 0, 100, 41, 1e-11), (14, 7, 0, 0, 200, 9, 1e-8),
                                    (10, 4, 0, 0, 50, 7, 1e-8), (12, 6, 0, 2, 10, 5, 1e-2)])
 def test_tensor_core_variants(gar, shape, variant):
-    """Variants 7/8: the stage step on the FP64 tensor cores (DMMA m8n8k4)."""
+    """Variants 7/8/10: the stage step on the FP64 tensor cores (DMMA m8n8k4); 10 = single
+    record buffer."""
     nx, nu, nc, nct, N, B, mueq = shape
     probs = gen.generate_batch(55 + nx, B, N, nx, nu, nc, nct)
     got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, variant=variant)

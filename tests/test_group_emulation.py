@@ -174,19 +174,22 @@ def test_emulated_kernel_unconstrained_with_interchanges(shape, db):
     check_against_oracle(nx, nu, nc, nct, N, B=2, mueq=1e-8, seed=31, db=db, pivoting=True, tol=1e-9)
 
 
+@pytest.mark.parametrize("db", [2, 3])
 @pytest.mark.parametrize("shape", [(12, 6, 0, 0, 10), (14, 7, 0, 0, 5), (10, 4, 0, 0, 6)])
-def test_emulated_tensor_core_step(shape):
+def test_emulated_tensor_core_step(shape, db):
     """db=2: the DMMA (mma.sync m8n8k4 f64) formulation of the stage step, with the mma
-    emulated by a fragment exchange between the 32 lane-threads."""
+    emulated by a fragment exchange between the 32 lane-threads; db=3: the same with a
+    single record buffer refilled in two parts."""
     nx, nu, nc, nct, N = shape
-    check_against_oracle(nx, nu, nc, nct, N, B=2, mueq=1e-8, seed=17 + nx, db=2)
+    check_against_oracle(nx, nu, nc, nct, N, B=2, mueq=1e-8, seed=17 + nx, db=db)
 
 
 def test_emulated_tensor_core_step_with_interchanges():
     check_against_oracle(12, 6, 0, 0, 8, B=2, mueq=1e-8, seed=31, db=2, pivoting=True, tol=1e-9)
 
 
-def test_emulated_tensor_core_step_edge_horizons():
-    check_against_oracle(12, 6, 0, 0, 0, B=1, mueq=1e-8, seed=3, db=2)
-    check_against_oracle(12, 6, 0, 0, 1, B=1, mueq=1e-8, seed=4, db=2)
-    check_against_oracle(12, 6, 0, 2, 4, B=1, mueq=1e-2, seed=5, db=2, tol=1e-9)
+@pytest.mark.parametrize("db", [2, 3])
+def test_emulated_tensor_core_step_edge_horizons(db):
+    check_against_oracle(12, 6, 0, 0, 0, B=1, mueq=1e-8, seed=3, db=db)
+    check_against_oracle(12, 6, 0, 0, 1, B=1, mueq=1e-8, seed=4, db=db)
+    check_against_oracle(12, 6, 0, 2, 4, B=1, mueq=1e-2, seed=5, db=db, tol=1e-9)
