@@ -199,12 +199,12 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
 
   // forward rollout: slots of the fb ring (as many as the stage area can hold, at most 8)
   static constexpr bool FB_BULK = ((NR * NX) % 2) == 0; // 16-byte granularity for bulk copies
-  // Fused forward (tensor-core builds): the ring slot of knot t also carries Vxx_t and vx_t
+  // Fused forward: the ring slot of knot t also carries Vxx_t and vx_t
   // -- laid out behind the gain rows as NX more "rows" plus their bias -- so the lanes that
   // pass 1 leaves idle compute lbda_t = vx_t + Vxx_t x_t in the same iteration: no second
   // pass, no register-staged global loads.
   // (only when the lambda rows find idle lanes: nu + nc + 2 nx <= G)
-  static constexpr bool FWD_FUSED = MMA && FB_BULK && (NX % 2 == 0) && (NR + NX <= G);
+  static constexpr bool FWD_FUSED = FB_BULK && (NX % 2 == 0) && (NR + NX <= G);
   static constexpr int FWD_ROWS = FWD_FUSED ? NR + NX : NR;
   static constexpr bool FWD_FF = FWD_FUSED && (NR % 2 == 0); // ff_t rides in the slot too (no LDG in pass 1)
   static constexpr int FWD_SLOT =
