@@ -159,9 +159,14 @@ def run_reference(args, rank, world):
     for _ in range(max(args.warmup, 1)):
         t1 = min(t1, bo.sweep(MUEQ, reps=1))
     if args.ref_seconds > 0:  # bounded sample sized in seconds (used for cpu_baseline)
-        t5 = bo.sweep(MUEQ, reps=5) / 5.0  # sustained pace (a lone sweep runs well above it)
-        args.steps = max(1, int(args.ref_seconds / max(t5, t1, 1e-5)))
-    t = bo.sweep(MUEQ, reps=args.steps)
+        t, steps = 0.0, 0
+        chunk = max(1, int(1.0 / max(t1, 1e-5)))  # about a second of sweeps at a time
+        while t < args.ref_seconds:  # (the sustained pace is well below a lone sweep's)
+            t += bo.sweep(MUEQ, reps=chunk)
+            steps += chunk
+        args.steps = steps
+    else:
+        t = bo.sweep(MUEQ, reps=args.steps)
     knots = nb * (HORIZON + 1) * args.steps
     v = knots / t
     line = {"metric": "riccati_knots_per_sec", "value": v, "unit": "knots/s", "n_gpus": args.gpus,
