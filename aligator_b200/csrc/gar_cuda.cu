@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/aligator_b200/gar.h"
+#include "lq_assemble.h"
 #include "riccati_block_launch.h"
 #include "riccati_configs.h"
 #include "riccati_launch.cuh"
@@ -371,6 +372,64 @@ static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream
 int ab2_gar_backward(ab2_gar_solver *s, double mueq, void *stream) { return launch(s, mueq, 1, 0, stream); }
 int ab2_gar_forward(ab2_gar_solver *s, void *stream) { return launch(s, s ? s->p.mueq : 0.0, 0, 1, stream); }
 int ab2_gar_sweep(ab2_gar_solver *s, double mueq, void *stream) { return launch(s, mueq, 1, 1, stream); }
+
+int ab2_gar_assemble(ab2_gar_solver *s, const ab2_lq_inputs *in, void *stream) {
+  if (!s || !in)
+    return fail(AB2_ERR_INVALID, "null argument");
+  const ab2_gar_dims &d = s->d;
+  const bool stage_ok = d.horizon == 0 || (in->Jx && in->Ju && in->slack && in->Lxx && in->Lxu && in->Luu &&
+                                           in->Lx && in->Lu);
+  const bool cstr_ok = d.nc == 0 || d.horizon == 0 || (in->cJx && in->cJu && in->Lv && in->shifted && in->lo && in->hi);
+  const bool hess_ok = (!in->Hxx && !in->Hxu && !in->Huu) || (in->Hxx && in->Hxu && in->Huu);
+  const bool term_ok = in->Lxx_N && in->Lx_N &&
+                       (d.nct == 0 || (in->cJx_N && in->Lv_N && in->shifted_N && in->loN && in->hiN));
+  const bool init_ok = d.nc0 == 0 || (in->G0 && in->g0);
+  if (!stage_ok || !cstr_ok || !hess_ok || !term_ok || !init_ok)
+    return fail(AB2_ERR_INVALID, "ab2_lq_inputs: a required array is NULL for these dimensions");
+  CUDA_TRY(cudaSetDevice(d.device));
+  auto own = [&](double *&buf, size_t n) -> int {
+    if (!buf)
+      CUDA_TRY(cudaMalloc(&buf, (n > 0 ? n : 1) * sizeof(double)));
+    return AB2_OK;
+  };
+  int rc;
+  if ((rc = own(s->own_stage, stage_total(s))) != AB2_OK || (rc = own(s->own_term, (size_t)d.batch * s->trec)) != AB2_OK ||
+      (rc = own(s->own_G0, (size_t)d.batch * d.nc0 * d.nx)) != AB2_OK || (rc = own(s->own_g0, (size_t)d.batch * d.nc0)) != AB2_OK)
+    return rc;
+  CUDA_TRY(ab2::launch_lq_assemble(*in, s->own_stage, s->own_term, s->own_G0, s->own_g0, d.batch, d.horizon, d.nx,
+                                   d.nu, d.nc, d.nct, d.nc0, s->srec, s->trec, (cudaStream_t)stream));
+  s->launches += d.horizon > 0 ? 2 : 1;
+  s->p.stage = s->own_stage;
+  s->p.term = s->own_term;
+  s->p.G0 = s->own_G0;
+  s->p.g0 = s->own_g0;
+  s->have_problem = true;
+  return AB2_OK;
+}
+
+int ab2_gar_problem_ptr(ab2_gar_solver *s, int what, const double **out) {
+  if (!s || !out || what < 0 || what > 3)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  const double *ptrs[4] = {s->p.stage, s->p.term, s->p.G0, s->p.g0};
+  *out = ptrs[what];
+  return AB2_OK;
+}
+
+int ab2_gar_get_problem(ab2_gar_solver *s, int what, double *dst, int memspace, void *stream) {
+  if (!s || !dst || what < 0 || what > 3)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  if (!s->have_problem)
+    return fail(AB2_ERR_STATE, "no problem set");
+  const double *ptrs[4] = {s->p.stage, s->p.term, s->p.G0, s->p.g0};
+  const size_t n[4] = {stage_total(s), (size_t)s->d.batch * s->trec, (size_t)s->d.batch * s->d.nc0 * s->d.nx,
+                       (size_t)s->d.batch * s->d.nc0};
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  if (n[what])
+    CUDA_TRY(cudaMemcpyAsync(dst, ptrs[what], n[what] * sizeof(double),
+                             memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+  return AB2_OK;
+}
 
 int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *term, const double *G0,
                        const double *g0, double mueq, int nchunks, const int *whats,

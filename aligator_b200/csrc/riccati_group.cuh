@@ -1627,7 +1627,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
         b0[NX + m] = -g0[m];
       }
       ctx.sync();
-      if (!bk_factor_group(ctx, K0, n0, n0, dd0, sd0, perm0, kind0))
+      if (!bk_factor_group<4>(ctx, K0, n0, n0, dd0, sd0, perm0, kind0))
         st |= ST_INIT_FACTOR_FAILED;
       bk_solve_vec_group(ctx, K0, n0, n0, dd0, sd0, perm0, kind0, b0, x0w, o0);
       for (int i = lane; i < n0; i += C::G)

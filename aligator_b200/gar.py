@@ -29,6 +29,15 @@ class GarDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("nx", "nu", "nc", "nct", "nc0", "horizon", "batch", "device")]
 
 
+_LQ_PTRS = ("Jx", "Ju", "slack", "Lxx", "Lxu", "Luu", "Lx", "Lu", "Hxx", "Hxu", "Huu", "cJx", "cJu", "Lv",
+            "shifted", "lo", "hi", "Lxx_N", "Lx_N", "cJx_N", "Lv_N", "shifted_N", "loN", "hiN", "G0", "g0", "Hxx0")
+
+
+class LqInputs(C.Structure):
+    """``ab2_lq_inputs``: device pointers to the derivative buffers of updateLQSubproblem."""
+    _fields_ = [(n, C.c_void_p) for n in _LQ_PTRS] + [("preg", C.c_double), ("mu_inv", C.c_double)]
+
+
 class GarTuning(C.Structure):
     _fields_ = [("variant", C.c_int), ("stagger_ns", C.c_int), ("ctas_per_sm", C.c_int)]
 
@@ -70,6 +79,9 @@ def lib():
         L.ab2_gar_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_get_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_assemble.argtypes = [C.c_void_p, C.POINTER(LqInputs), C.c_void_p]
+        L.ab2_gar_get_problem.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_problem_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ab2_gar_first_step_policy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ab2_gar_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ab2_gar_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -210,6 +222,36 @@ class CudaRiccatiBatch:
     def get_range_into(self, what, b0, nb, t0, nt, dst, memspace, stream=0):
         _check(lib().ab2_gar_get_range(self.h, what, b0, nb, t0, nt, _ptr(dst), memspace,
                                        C.c_void_p(stream)))
+
+    def assemble(self, arrays, preg, mu_inv, stream=0):
+        """updateLQSubproblem + computeProjectedJacobians on the device (``ab2_gar_assemble``).
+        ``arrays``: {field of ab2_lq_inputs: device tensor / device address}; missing fields
+        are NULL.  The assembled problem becomes the solver's current problem."""
+        inp = LqInputs()
+        for n in _LQ_PTRS:
+            a = arrays.get(n)
+            setattr(inp, n, None if a is None else _ptr(a).value)
+        inp.preg, inp.mu_inv = float(preg), float(mu_inv)
+        self._keep = (arrays,)
+        _check(lib().ab2_gar_assemble(self.h, C.byref(inp), C.c_void_p(stream)))
+
+    def get_problem(self, what, stream=0):
+        """Host copy of the current packed problem: what = 0 stage, 1 term, 2 G0, 3 g0."""
+        d = self.dims
+        n = [d.batch * d.horizon * self.srec, d.batch * self.trec, d.batch * d.nc0 * d.nx, d.batch * d.nc0][what]
+        buf = np.empty(max(n, 1), dtype=np.float64)
+        _check(lib().ab2_gar_get_problem(self.h, what, _ptr(buf), AB2_HOST, C.c_void_p(stream)))
+        self.synchronize(stream)
+        return buf[:n]
+
+    def problem_device_ptrs(self):
+        """Device addresses of the solver-owned packed problem (stage, term, G0, g0)."""
+        out = []
+        for w in range(4):
+            p = C.c_void_p()
+            _check(lib().ab2_gar_problem_ptr(self.h, w, C.byref(p)))
+            out.append(p.value)
+        return out
 
     def first_step_policy_into(self, dst, stream=0):
         """[K_0 | k_0] of every instance -> device buffer dst [batch][nu][nx+1]."""

@@ -131,6 +131,38 @@ int ab2_gar_forward(ab2_gar_solver *s, void *stream);
 /* backward + forward in ONE persistent launch: the loop body of
  * bench/gar-riccati.cpp:46-49 and solver-proxddp.hxx:608-611. */
 int ab2_gar_sweep(ab2_gar_solver *s, double mueq, void *stream);
+/* Inputs of the batched LQ assembly: the derivative buffers SolverProxDDP::updateLQSubproblem
+ * (solvers/proxddp/solver-proxddp.hxx:734-805) and computeProjectedJacobians (:25-69) read.
+ * DEVICE pointers; stage arrays are [batch][N][block], terminal / initial arrays [batch][block],
+ * blocks column-major like the reference's Eigen matrices.  Constraint sets are given per row
+ * by bounds: a row is ACTIVE (kept by applyNormalConeProjectionJacobian, core/constraint-set.hxx:
+ * 25-37) iff shifted > hi or shifted < lo -- equality rows: lo = +inf; negative orthant: lo = -inf,
+ * hi = 0; box: its limits (computeActiveSet of equality-constraint.hpp:52, negative-orthant.hpp:30,
+ * box-constraint.hpp:39). */
+typedef struct ab2_lq_inputs {
+  const double *Jx, *Ju, *slack;   /* dd.Jx() -> A, dd.Ju() -> B, dyn_slacks[t+1] -> f        (:755-757) */
+  const double *Lxx, *Lxu, *Luu;   /* cd.Lxx_, Lxu_, Luu_ -> Q, S, R (+ preg on the diagonals) (:759-768) */
+  const double *Lx, *Lu;           /* workspace Lxs[t], Lus[t] -> q, r                          (:764-765) */
+  const double *Hxx, *Hxu, *Huu;   /* dd.Hxx_, Hxu_, Huu_ (HessianApprox::EXACT) or NULL        (:770-774) */
+  const double *cJx, *cJu;         /* constraint Jacobians before projection [nc x nx], [nc x nu] (:40-41) */
+  const double *Lv, *shifted;      /* workspace Lvs[t] -> d; shifted_constraints[t]              (:46,49,780) */
+  const double *lo, *hi;           /* [nc] bounds of the stage constraint rows (shared by all knots) */
+  const double *Lxx_N, *Lx_N;      /* terminal cost                                               (:787-790) */
+  const double *cJx_N, *Lv_N, *shifted_N, *loN, *hiN; /* terminal constraints [nct ...]          (:55-68,791-794) */
+  const double *G0, *g0;           /* init_data Jx(), value_                                      (:798-800) */
+  const double *Hxx0;              /* init_data Hxx_ (added to stage 0's Q) or NULL               (:803-804) */
+  double preg, mu_inv;
+} ab2_lq_inputs;
+/* updateLQSubproblem + computeProjectedJacobians for every instance and knot in one pass over
+ * HBM: writes the solver-owned packed problem (the same bytes ab2_gar_set_problem uploads) and
+ * makes it the current problem.  A device-resident caller never moves the knots over PCIe. */
+int ab2_gar_assemble(ab2_gar_solver *s, const ab2_lq_inputs *in, void *stream);
+/* Device address of the current packed problem: what = 0 stage, 1 term, 2 G0, 3 g0
+ * (the bytes workspace_.lqr_problem holds after updateLQSubproblem). */
+int ab2_gar_problem_ptr(ab2_gar_solver *s, int what, const double **out);
+/* Copy of it (whole array) to `dst` in host or device memory. */
+int ab2_gar_get_problem(ab2_gar_solver *s, int what, double *dst, int memspace, void *stream);
+
 /* One whole iteration of the caller's loop with HOST buffers, pipelined over the batch:
  * upload the problem (what updateLQSubproblem rewrote, solver-proxddp.hxx:734-805), sweep,
  * and download `nwhat` result arrays (`whats[i]` -> `dsts[i]`, full-size host arrays laid out
