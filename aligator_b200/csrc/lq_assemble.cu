@@ -19,86 +19,81 @@ namespace ab2 {
 // negative-orthant.hpp:30-33, box-constraint.hpp:39-43 expressed as one test on [lo, hi])
 __device__ __forceinline__ bool row_active(double z, double lo, double hi) { return z > hi || z < lo; }
 
-// One element of the stage record of (instance, knot) `rec`: e indexes
-// [A | B | f | Q | S | R | q | r | C | D | d | pad].
-__device__ __forceinline__ double stage_element(const ab2_lq_inputs &in, long rec, int t, long inst, int e,
-                                                int nx, int nu, int nc) {
-  const int nxx = nx * nx, nxu = nx * nu, nuu = nu * nu;
-  if (e < nxx) // knot.A = dd.Jx()  (:755)
-    return in.Jx[rec * nxx + e];
-  e -= nxx;
-  if (e < nxu) // knot.B = dd.Ju()
-    return in.Ju[rec * nxu + e];
-  e -= nxu;
-  if (e < nx) // knot.f = dyn_slacks[t+1]
-    return in.slack[rec * nx + e];
-  e -= nx;
-  if (e < nxx) { // knot.Q = Lxx; diag += preg; (+= Hxx, EXACT :770-774) (; += id.Hxx_ on stage 0, :803-804)
-    double v = in.Lxx[rec * nxx + e];
-    if (e % (nx + 1) == 0)
-      v += in.preg;
-    if (in.Hxx)
-      v += in.Hxx[rec * nxx + e];
-    if (t == 0 && in.Hxx0)
-      v += in.Hxx0[inst * nxx + e];
-    return v;
-  }
-  e -= nxx;
-  if (e < nxu) {
-    double v = in.Lxu[rec * nxu + e];
-    if (in.Hxu)
-      v += in.Hxu[rec * nxu + e];
-    return v;
-  }
-  e -= nxu;
-  if (e < nuu) {
-    double v = in.Luu[rec * nuu + e];
-    if (e % (nu + 1) == 0)
-      v += in.preg;
-    if (in.Huu)
-      v += in.Huu[rec * nuu + e];
-    return v;
-  }
-  e -= nuu;
-  if (e < nx + nu) {
-    // q = Lxs[t] + cstr_lx_corr, r = Lus[t] + cstr_lu_corr (:764-765, 782-783) with
-    // corr = P^T lv - Ptilde^T lv, lv = Lvs * mu_inv: both products over ALL rows, then subtracted (:46-52)
-    const bool isx = e < nx;
-    const int jj = isx ? e : e - nx;
-    double full = 0.0, proj = 0.0;
-    if (nc > 0) {
-      const double *P = isx ? in.cJx + rec * nc * nx : in.cJu + rec * nc * nu;
-      for (int i = 0; i < nc; ++i) {
-        const double lv = in.Lv[rec * nc + i] * in.mu_inv;
-        const double pij = P[i + (long)jj * nc];
-        const double a = row_active(in.shifted[rec * nc + i], in.lo[i], in.hi[i]) ? 1.0 : 0.0;
-        full += pij * lv;
-        proj += (pij * a) * lv;
-      }
-    }
-    return (isx ? in.Lx[rec * nx + jj] : in.Lu[rec * nu + jj]) + (full - proj);
-  }
-  e -= nx + nu;
-  if (e < nc * nx) { // knot.C = projected Jx: rows of inactive constraints zeroed (:49-50, 778)
-    const int i = e % nc;
-    return row_active(in.shifted[rec * nc + i], in.lo[i], in.hi[i]) ? in.cJx[rec * nc * nx + e] : 0.0;
-  }
-  e -= nc * nx;
-  if (e < nc * nu) {
-    const int i = e % nc;
-    return row_active(in.shifted[rec * nc + i], in.lo[i], in.hi[i]) ? in.cJu[rec * nc * nu + e] : 0.0;
-  }
-  e -= nc * nu;
-  if (e < nc) // knot.d = Lvs[t]
-    return in.Lv[rec * nc + e];
-  return 0.0; // pad to even
-}
+// The map "element e of the record -> (source array, offset, what to do with it)" is the same
+// for every record, so each CTA builds it once in shared memory; per element the kernel then
+// spends one table look-up instead of an eleven-way block decode.
+enum : int { SRC_JX, SRC_JU, SRC_SLACK, SRC_LXX, SRC_LXU, SRC_LUU, SRC_LX, SRC_LU, SRC_CJX, SRC_CJU, SRC_LV, SRC_COUNT };
+enum : int { F_DIAG = 1, F_HESS = 2, F_H0 = 4, F_ROW = 8, F_CORR = 16, F_ZERO = 32 };
 
-// A warp per record (grid-stride), lanes stride over the record's elements, UNR elements per
-// lane in flight: unit-stride reads of every source block and unit-stride writes of the record.
-__global__ void __launch_bounds__(256)
+struct StageTables {
+  const double *src[SRC_COUNT];
+  const double *hess[SRC_COUNT]; // second operand (dynamics Hessians) of Lxx / Lxu / Luu
+  int blk[SRC_COUNT];            // doubles per record of each source
+};
+
+// A warp per record (grid-stride), lanes stride over the record's elements
+// [A | B | f | Q | S | R | q | r | C | D | d | pad], UNR elements per lane in flight:
+// unit-stride reads of every source block and unit-stride writes of the record.
+__global__ void __launch_bounds__(256, 4)
     lq_assemble_stage_kernel(const ab2_lq_inputs in, double *__restrict__ stage, long nrec, int N, int nx,
                              int nu, int nc, int srec) {
+  extern __shared__ int2 tab[]; // [srec]: x = source | flags << 8 | row << 16, y = offset in the source block
+  __shared__ StageTables T;
+  const int nxx = nx * nx, nxu = nx * nu, nuu = nu * nu;
+  if (threadIdx.x == 0) {
+    const double *srcs[SRC_COUNT] = {in.Jx, in.Ju, in.slack, in.Lxx, in.Lxu, in.Luu, in.Lx, in.Lu, in.cJx, in.cJu, in.Lv};
+    const int blks[SRC_COUNT] = {nxx, nxu, nx, nxx, nxu, nuu, nx, nu, nc * nx, nc * nu, nc};
+    for (int i = 0; i < SRC_COUNT; ++i) {
+      T.src[i] = srcs[i] ? srcs[i] : in.Jx;
+      T.hess[i] = nullptr;
+      T.blk[i] = blks[i];
+    }
+    T.hess[SRC_LXX] = in.Hxx;
+    T.hess[SRC_LXU] = in.Hxu;
+    T.hess[SRC_LUU] = in.Huu;
+  }
+  for (int e = threadIdx.x; e < srec; e += blockDim.x) {
+    int r = e, id, fl = 0, row = 0;
+    if (r < nxx) { // knot.A = dd.Jx()  (:755)
+      id = SRC_JX;
+    } else if ((r -= nxx) < nxu) { // knot.B = dd.Ju()
+      id = SRC_JU;
+    } else if ((r -= nxu) < nx) { // knot.f = dyn_slacks[t+1]
+      id = SRC_SLACK;
+    } else if ((r -= nx) < nxx) { // knot.Q = Lxx; diag += preg; += Hxx (EXACT, :770-774); += id.Hxx_ at t = 0 (:803-804)
+      id = SRC_LXX;
+      fl = ((r % (nx + 1) == 0) ? F_DIAG : 0) | (in.Hxx ? F_HESS : 0) | (in.Hxx0 ? F_H0 : 0);
+    } else if ((r -= nxx) < nxu) {
+      id = SRC_LXU;
+      fl = in.Hxu ? F_HESS : 0;
+    } else if ((r -= nxu) < nuu) {
+      id = SRC_LUU;
+      fl = ((r % (nu + 1) == 0) ? F_DIAG : 0) | (in.Huu ? F_HESS : 0);
+    } else if ((r -= nuu) < nx) { // q = Lxs[t] + cstr_lx_corr (:764, 782)
+      id = SRC_LX;
+      fl = nc > 0 ? F_CORR : 0;
+    } else if ((r -= nx) < nu) { // r = Lus[t] + cstr_lu_corr (:765, 783)
+      id = SRC_LU;
+      fl = nc > 0 ? F_CORR : 0;
+    } else if ((r -= nu) < nc * nx) { // knot.C = projected Jx: rows of inactive constraints zeroed (:49-50, 778)
+      id = SRC_CJX;
+      fl = F_ROW;
+      row = r % nc;
+    } else if ((r -= nc * nx) < nc * nu) {
+      id = SRC_CJU;
+      fl = F_ROW;
+      row = r % nc;
+    } else if ((r -= nc * nu) < nc) { // knot.d = Lvs[t]
+      id = SRC_LV;
+    } else { // pad to even
+      id = SRC_JX;
+      fl = F_ZERO;
+      r = 0;
+    }
+    tab[e] = make_int2(id | (fl << 8) | (row << 16), r);
+  }
+  __syncthreads();
+
   constexpr int UNR = 4;
   const int lane = threadIdx.x & 31;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -108,11 +103,49 @@ __global__ void __launch_bounds__(256)
     const long inst = rec / N;
     double *dst = stage + rec * srec;
     for (int e0 = 0; e0 < srec; e0 += 32 * UNR) {
-      double v[UNR];
+      double v[UNR], h[UNR];
+      int2 ent[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) { // every streaming operand of the pass is requested here
+        const int e = e0 + 32 * u + lane;
+        ent[u] = tab[e < srec ? e : 0];
+        const int id = ent[u].x & 0xff;
+        const long o = rec * T.blk[id] + ent[u].y;
+        v[u] = T.src[id][o];
+        h[u] = (ent[u].x & (F_HESS << 8)) ? T.hess[id][o] : 0.0;
+      }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
-        const int e = e0 + 32 * u + lane;
-        v[u] = (e < srec) ? stage_element(in, rec, t, inst, e, nx, nu, nc) : 0.0;
+        const int id = ent[u].x & 0xff, fl = (ent[u].x >> 8) & 0xff;
+        if (fl == 0)
+          continue;
+        if (fl & F_ZERO)
+          v[u] = 0.0;
+        if (fl & F_DIAG)
+          v[u] += in.preg;
+        if (fl & F_HESS)
+          v[u] += h[u];
+        if ((fl & F_H0) && t == 0)
+          v[u] += in.Hxx0[inst * nxx + ent[u].y];
+        if (fl & F_ROW) {
+          const int i = ent[u].x >> 16;
+          v[u] = row_active(in.shifted[rec * nc + i], in.lo[i], in.hi[i]) ? v[u] : 0.0;
+        }
+        if (fl & F_CORR) {
+          // corr = P^T lv - Ptilde^T lv, lv = Lvs * mu_inv: both products over ALL rows, then
+          // subtracted (:46-52)
+          const double *P = (id == SRC_LX) ? in.cJx + rec * nc * nx : in.cJu + rec * nc * nu;
+          const int jj = ent[u].y;
+          double full = 0.0, proj = 0.0;
+          for (int i = 0; i < nc; ++i) {
+            const double lv = in.Lv[rec * nc + i] * in.mu_inv;
+            const double pij = P[i + (long)jj * nc];
+            const double a = row_active(in.shifted[rec * nc + i], in.lo[i], in.hi[i]) ? 1.0 : 0.0;
+            full += pij * lv;
+            proj += (pij * a) * lv;
+          }
+          v[u] += full - proj;
+        }
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
@@ -173,7 +206,12 @@ cudaError_t launch_lq_assemble(const ab2_lq_inputs &in, double *stage, double *t
     long grid = (nrec + 7) / 8; // 8 warps per CTA
     if (grid > full)
       grid = full;
-    lq_assemble_stage_kernel<<<(int)grid, 256, 0, st>>>(in, stage, nrec, N, nx, nu, nc, srec);
+    const size_t tab_bytes = (size_t)srec * sizeof(int2);
+    cudaError_t e0 = cudaFuncSetAttribute(lq_assemble_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)tab_bytes);
+    if (e0 != cudaSuccess)
+      return e0;
+    lq_assemble_stage_kernel<<<(int)grid, 256, tab_bytes, st>>>(in, stage, nrec, N, nx, nu, nc, srec);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
       return e;
