@@ -18,6 +18,9 @@ struct BlockDevCtx {
   __device__ __forceinline__ void sync() { __syncthreads(); }
   // barrier over the first `nth` threads (whole warps) of the CTA: named barrier 1
   __device__ __forceinline__ void sync_sub(int nth) { asm volatile("bar.sync 1, %0;" ::"r"(nth) : "memory"); }
+  __device__ __forceinline__ void wsync() { __syncwarp(); }
+  __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ __forceinline__ bool all(bool p) { return __all_sync(0xffffffffu, p); }
   __device__ __forceinline__ void mma(double (&d)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d[0]), "+d"(d[1])

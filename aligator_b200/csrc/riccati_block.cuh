@@ -172,27 +172,23 @@ template <class Ctx> struct CtaAsGroup {
 AB2_D void bk_solve_column_rt(const double *a, const int n, const double *dd, const double *sd,
                               const int *perm, const int *kind, const double *rhs, double *work,
                               double *sol, const int stride) {
-  constexpr int CH = 8;
   for (int i = 0; i < n; ++i)
     work[i * stride] = rhs[perm[i] * stride];
-  for (int i = 1; i < n; ++i) { // forward: unit lower
+  for (int i = 1; i < n; ++i) { // forward: unit lower, row i of L against x_0..x_{i-1}
     double s0 = work[i * stride], s1 = 0.0;
-    for (int c0 = 0; c0 < i; c0 += CH) {
-      double l[CH], x[CH];
-      AB2_UNROLL
-      for (int u = 0; u < CH; ++u) {
-        const int c = (c0 + u < i) ? c0 + u : 0;
-        l[u] = a[i + c * n];
-        x[u] = work[c * stride];
-      }
-      AB2_UNROLL
-      for (int u = 0; u < CH; u += 2) {
-        if (c0 + u < i)
-          s0 -= l[u] * x[u];
-        if (c0 + u + 1 < i)
-          s1 -= l[u + 1] * x[u + 1];
-      }
+    const double *li = a + i;   // L(i, c) = li[c * n]
+    int c = 0;
+    for (; c + 4 <= i; c += 4) { // four loads of each operand in flight, two accumulation chains
+      const double l0 = li[c * n], l1 = li[(c + 1) * n], l2 = li[(c + 2) * n], l3 = li[(c + 3) * n];
+      const double x0 = work[c * stride], x1 = work[(c + 1) * stride], x2 = work[(c + 2) * stride],
+                   x3 = work[(c + 3) * stride];
+      s0 -= l0 * x0;
+      s1 -= l1 * x1;
+      s0 -= l2 * x2;
+      s1 -= l3 * x3;
     }
+    for (; c < i; ++c)
+      s0 -= li[c * n] * work[c * stride];
     work[i * stride] = s0 + s1;
   }
   for (int k = 0; k < n; ++k) {
@@ -205,28 +201,82 @@ AB2_D void bk_solve_column_rt(const double *a, const int n, const double *dd, co
       work[(k + 1) * stride] = xk1 * dd[k + 1] + xk * s;
     }
   }
-  for (int c = n - 2; c >= 0; --c) { // backward: unit upper (L^T)
+  for (int c = n - 2; c >= 0; --c) { // backward: unit upper (L^T), column c of L against x_{c+1}..x_{n-1}
     double s0 = work[c * stride], s1 = 0.0;
-    for (int i0 = c + 1; i0 < n; i0 += CH) {
-      double l[CH], x[CH];
-      AB2_UNROLL
-      for (int u = 0; u < CH; ++u) {
-        const int i = (i0 + u < n) ? i0 + u : n - 1;
-        l[u] = a[i + c * n];
-        x[u] = work[i * stride];
-      }
-      AB2_UNROLL
-      for (int u = 0; u < CH; u += 2) {
-        if (i0 + u < n)
-          s0 -= l[u] * x[u];
-        if (i0 + u + 1 < n)
-          s1 -= l[u + 1] * x[u + 1];
-      }
+    const double *lc = a + c * n; // L(i, c) = lc[i]
+    int i = c + 1;
+    for (; i + 4 <= n; i += 4) {
+      const double l0 = lc[i], l1 = lc[i + 1], l2 = lc[i + 2], l3 = lc[i + 3];
+      const double x0 = work[i * stride], x1 = work[(i + 1) * stride], x2 = work[(i + 2) * stride],
+                   x3 = work[(i + 3) * stride];
+      s0 -= l0 * x0;
+      s1 -= l1 * x1;
+      s0 -= l2 * x2;
+      s1 -= l3 * x3;
     }
+    for (; i < n; ++i)
+      s0 -= lc[i] * work[i * stride];
     work[c * stride] = s0 + s1;
   }
   for (int i = 0; i < n; ++i)
     sol[perm[i] * stride] = -work[i * stride];
+}
+
+// LDL^T of a matrix on which every pivot test of the Bunch-Kaufman algorithm picks the 1x1
+// pivot in place (|a_kk| >= alpha * colmax, core/bunchkaufman.hpp:61; the SPD Rhat of an
+// unconstrained knot) -- the same arithmetic as the general algorithm on that path (and as
+// FastFactor of the warp-per-instance kernel), run by ONE warp with lane = row: the column
+// test is a vote, the pivot row travels by shuffle, no scan, no barrier between warps.
+// Leaves the factor in the format of bk_factor_group (identity interchanges).  Returns false
+// at the first pivot test that fails; the matrix is then partly overwritten (the caller
+// restores its copy and runs the general algorithm).
+template <class Ctx>
+AB2_D bool ldlt_fast_warp(Ctx &ctx, double *a, const int n, double *dd, double *sd, int *perm, int *kind) {
+  const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
+  const int lane = ctx.lane;
+  for (int k = 0; k < n; ++k) {
+    ctx.wsync(); // column k is final
+    const double akk = a[k + k * n];
+    const bool below = lane > k && lane < n;
+    const double my = below ? a[lane + k * n] : 0.0;
+    const bool ok = (fabs(my) * alpha <= fabs(akk)) && (fabs(akk) > 0.0);
+    if (!ctx.all(ok))
+      return false;
+    const double d = 1.0 / akk;
+    if (lane == k) {
+      dd[k] = d;
+      sd[k] = 0.0;
+      kind[k] = 0;
+      perm[k] = k;
+    }
+    // trailing rows: a_ij -= (a_jk d) a_ik, i >= j.  Four columns per round: the shuffles and
+    // the loads of a round are independent, so a lone warp overlaps their latencies.
+    int j = k + 1;
+    for (; j + 4 <= n; j += 4) {
+      const double m0 = ctx.shfl(my, j), m1 = ctx.shfl(my, j + 1), m2 = ctx.shfl(my, j + 2),
+                   m3 = ctx.shfl(my, j + 3);
+      const bool in = lane < n;
+      double *p = a + lane + j * n;
+      const double r0 = in ? p[0] : 0.0, r1 = in ? p[n] : 0.0, r2 = in ? p[2 * n] : 0.0, r3 = in ? p[3 * n] : 0.0;
+      if (in && lane >= j)
+        p[0] = r0 - (m0 * d) * my;
+      if (in && lane >= j + 1)
+        p[n] = r1 - (m1 * d) * my;
+      if (in && lane >= j + 2)
+        p[2 * n] = r2 - (m2 * d) * my;
+      if (in && lane >= j + 3)
+        p[3 * n] = r3 - (m3 * d) * my;
+    }
+    for (; j < n; ++j) {
+      const double mj = ctx.shfl(my, j);
+      if (lane >= j && lane < n)
+        a[lane + j * n] -= (mj * d) * my;
+    }
+    if (below)
+      a[lane + k * n] = my * d;
+  }
+  ctx.wsync();
+  return true;
 }
 
 constexpr int BLK_CH = 4; // n-tiles accumulated together by one warp (one work item)
@@ -439,13 +489,30 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &
         const double *src = stage_b + (size_t)(t - 1) * d.srec_pad;
         ctx.issue_copy(1, rec + d.split, src + d.split, d.srec_pad - d.split);
       }
-      if (tid < bk_threads) // the other warps go straight to the CTA barrier below
-        if (!bk_factor_group<16>(grp, kkt, nk, nk, dd, sd, perm, kind))
+      // Unconstrained knots (SPD Rhat): the branch-free warp LDL^T; anything that needs an
+      // interchange or a 2x2 pivot falls back to the general cooperative algorithm on a copy.
+      const bool try_fast = nc == 0 && nk <= 32 && nk * nk <= d.xrows * d.sx;
+      if (try_fast)
+        for (int e = tid; e < nk * nk; e += T)
+          Ys[e] = kkt[e]; // Y is free until the solves
+      if (try_fast)
+        ctx.sync();
+      if (tid < bk_threads) { // the other warps go straight to the CTA barrier below
+        bool done = false;
+        if (try_fast) { // (bk_threads == 32: warp 0)
+          done = ldlt_fast_warp(ctx, kkt, nk, dd, sd, perm, kind);
+          if (!done)
+            for (int e = lane; e < nk * nk; e += 32)
+              kkt[e] = Ys[e];
+        }
+        if (!done && !bk_factor_group<16>(grp, kkt, nk, nk, dd, sd, perm, kind))
           st |= ST_STAGE_FACTOR_FAILED;
-      ctx.sync();
-      if (tid <= nx) { // column tid of [K k; Z z] = -KKT^-1 X[:, tid]
-        bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, X + tid, Ys + tid, KKs + tid, d.sx);
       }
+      ctx.sync();
+      // column tid of [K k; Z z] = -KKT^-1 X[:, tid].  (Four lanes per column with butterfly
+      // reductions was measured: more instructions, no shorter -- the chains are latency-bound.)
+      if (tid <= nx)
+        bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, X + tid, Ys + tid, KKs + tid, d.sx);
       ctx.sync();
       for (int e = tid; e < nk * nx; e += T) // gains K, Z (row-major nk x nx)
         fbt[e] = KKs[(e / nx) * d.sx + (e % nx)];

@@ -33,6 +33,23 @@ struct HostBlockCtx {
     }
     wbar->arrive_and_wait();
   }
+  void wsync() { wbar->arrive_and_wait(); }
+  double shfl(double v, int src) {
+    xa[lane] = v;
+    wbar->arrive_and_wait();
+    const double r = xa[src & 31];
+    wbar->arrive_and_wait();
+    return r;
+  }
+  bool all(bool p) {
+    xb[lane] = p ? 1.0 : 0.0;
+    wbar->arrive_and_wait();
+    bool r = true;
+    for (int i = 0; i < 32; ++i)
+      r = r && (xb[i] != 0.0);
+    wbar->arrive_and_wait();
+    return r;
+  }
   void issue_copy(int, double *dst, const double *src, int nd) {
     if (tid == 0)
       std::memcpy(dst, src, sizeof(double) * (size_t)nd);
