@@ -72,9 +72,9 @@ struct BlockDevCtx {
 
 // MAXREG 128: two or more CTAs per SM for the shapes whose buffers allow it; 255: the
 // large shapes, which own the SM anyway.
-template <int MAXREG>
+template <int MAXREG, class D>
 __global__ void __launch_bounds__(256) __maxnreg__(MAXREG)
-    riccati_block_kernel(const SweepParams p, const BlockDims d) {
+    riccati_block_kernel(const SweepParams p, const D d) {
   extern __shared__ __align__(16) double smem[];
   BlockDevCtx ctx;
   ctx.tid = threadIdx.x;
@@ -119,10 +119,10 @@ bool block_supported(int nx, int nu, int nc, int nc0) {
   return block_threads(nx, nu, nc, nc0) > 0 && block_smem_bytes(nx, nu, nc, nc0) <= (size_t)227 * 1024;
 }
 
-template <int MAXREG>
-static cudaError_t launch_block_t(const SweepParams &p, const BlockDims &d, int threads, size_t smem,
+template <int MAXREG, class D>
+static cudaError_t launch_block_t(const SweepParams &p, const D &d, int threads, size_t smem,
                                   cudaStream_t st, int *info) {
-  auto kern = riccati_block_kernel<MAXREG>;
+  auto kern = riccati_block_kernel<MAXREG, D>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
     return e;
@@ -159,6 +159,10 @@ cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStrea
   const BlockDims d = make_block_dims(nx, nu, nc, p.nc0);
   const int threads = block_threads(nx, nu, nc, p.nc0);
   const size_t smem = block_smem_bytes(nx, nu, nc, p.nc0);
+  // BASELINE config 5 (Talos whole-body walk, nx 57 nu 28, initial condition on the full state):
+  // the same code specialised at compile time
+  if (nx == 57 && nu == 28 && nc == 0 && p.nc0 == 57)
+    return launch_block_t<255>(p, StaticBlockDims<57, 28, 0, 57>{}, threads, smem, st, info);
   // one CTA per SM anyway (shared memory): let it use the whole register file
   if (2 * (smem + 1024) > (size_t)227 * 1024)
     return launch_block_t<255>(p, d, threads, smem, st, info);

@@ -31,14 +31,14 @@ struct BlockDims {
   int fwd_ring, fwd_slot, slack;
 };
 
-AB2_HD int blk_ev(int x) { return (x + 1) & ~1; }
-AB2_HD int blk_fstride(int n) { // smallest stride >= n that is 4 or 12 mod 16
+AB2_HD constexpr int blk_ev(int x) { return (x + 1) & ~1; }
+AB2_HD constexpr int blk_fstride(int n) { // smallest stride >= n that is 4 or 12 mod 16
   int s = n;
   while (s % 16 != 4 && s % 16 != 12)
     ++s;
   return s;
 }
-AB2_HD int blk_s8(int n) { // smallest stride >= n that is 8 mod 16
+AB2_HD constexpr int blk_s8(int n) { // smallest stride >= n that is 8 mod 16
   int s = n;
   while (s % 16 != 8)
     ++s;
@@ -46,8 +46,8 @@ AB2_HD int blk_s8(int n) { // smallest stride >= n that is 8 mod 16
 }
 
 // Layout shared by the host (sizing the launch) and the device.
-AB2_HD BlockDims make_block_dims(int nx, int nu, int nc, int nc0) {
-  BlockDims d;
+AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0) {
+  BlockDims d{};
   d.nx = nx;
   d.nu = nu;
   d.nc = nc;
@@ -124,7 +124,21 @@ AB2_HD BlockDims make_block_dims(int nx, int nu, int nc, int nc0) {
   return d;
 }
 
-AB2_D int blk_col_offset(const BlockDims &d, int jp) { // logical column jp of [A | f | B]
+// The same layout with every field a compile-time constant: a specialisation of the kernel
+// for one shape (loops unroll, addresses fold) behind the same code.
+template <int NX, int NU, int NC, int NC0> struct StaticBlockDims {
+  static constexpr BlockDims v = make_block_dims(NX, NU, NC, NC0);
+#define AB2_SD(f) static constexpr int f = v.f;
+  AB2_SD(nx) AB2_SD(nu) AB2_SD(nc) AB2_SD(nk) AB2_SD(nr) AB2_SD(nj) AB2_SD(mtx) AB2_SD(kt) AB2_SD(nt) AB2_SD(nt2)
+  AB2_SD(kt2) AB2_SD(njp) AB2_SD(off_b) AB2_SD(off_f) AB2_SD(off_q) AB2_SD(off_s) AB2_SD(off_r) AB2_SD(off_qv)
+  AB2_SD(off_rv) AB2_SD(off_c) AB2_SD(off_d) AB2_SD(off_dv) AB2_SD(srec_pad) AB2_SD(split) AB2_SD(vs) AB2_SD(vrows)
+  AB2_SD(sw) AB2_SD(wrows) AB2_SD(sh) AB2_SD(sx) AB2_SD(xrows) AB2_SD(s_rec) AB2_SD(s_vn) AB2_SD(s_vxn) AB2_SD(s_w)
+  AB2_SD(s_x) AB2_SD(s_kk) AB2_SD(s_y) AB2_SD(s_h) AB2_SD(s_kkt) AB2_SD(s_dd) AB2_SD(s_sd) AB2_SD(s_int) AB2_SD(s_end)
+  AB2_SD(fwd_ring) AB2_SD(fwd_slot) AB2_SD(slack)
+#undef AB2_SD
+};
+
+template <class D> AB2_D int blk_col_offset(const D &d, int jp) { // logical column jp of [A | f | B]
   if (jp < d.nx)
     return jp * d.nx;
   if (jp == d.nx)
@@ -133,7 +147,7 @@ AB2_D int blk_col_offset(const BlockDims &d, int jp) { // logical column jp of [
     return d.off_b + (jp - d.nx - 1) * d.nx;
   return d.srec_pad; // padding column: the zeroed slack behind the record
 }
-AB2_D int blk_h0_offset(const BlockDims &d, int ip, int jp) { // -1 = structural zero
+template <class D> AB2_D int blk_h0_offset(const D &d, int ip, int jp) { // -1 = structural zero
   const int nx = d.nx, nu = d.nu;
   const int ti = ip < nx ? 0 : (ip == nx ? 1 : (ip <= nx + nu ? 2 : 3));
   const int tj = jp < nx ? 0 : (jp == nx ? 1 : (jp <= nx + nu ? 2 : 3));
@@ -284,8 +298,8 @@ constexpr int BLK_CH = 4; // n-tiles accumulated together by one warp (one work 
 // ---------------------------------------------------------------------------
 // The sweep of one instance by one CTA.
 // ---------------------------------------------------------------------------
-template <class Ctx>
-AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const BlockDims &d, const int inst,
+template <class Ctx, class D>
+AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const int inst,
                                double *__restrict__ sm) {
   const int nx = d.nx, nu = d.nu, nc = d.nc, nk = d.nk, nr = d.nr;
   const int tid = ctx.tid, T = ctx.nthreads, warp = ctx.warp, lane = ctx.lane, NW = ctx.nwarps;
