@@ -293,6 +293,13 @@ AB2_D bool ldlt_fast_warp(Ctx &ctx, double *a, const int n, double *dd, double *
   return true;
 }
 
+template <class D> struct dims_static {
+  static constexpr bool value = false;
+};
+template <int NX, int NU, int NC, int NC0> struct dims_static<StaticBlockDims<NX, NU, NC, NC0>> {
+  static constexpr bool value = true;
+};
+
 constexpr int BLK_CH = 4; // n-tiles accumulated together by one warp (one work item)
 
 // ---------------------------------------------------------------------------
@@ -523,8 +530,9 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
           st |= ST_STAGE_FACTOR_FAILED;
       }
       ctx.sync();
-      // column tid of [K k; Z z] = -KKT^-1 X[:, tid].  (Four lanes per column with butterfly
-      // reductions was measured: more instructions, no shorter -- the chains are latency-bound.)
+      // column tid of [K k; Z z] = -KKT^-1 X[:, tid]
+      // (four lanes per column with butterfly reductions was measured, with run-time and with
+      // compile-time dimensions: more instructions, no shorter -- the chains are latency-bound)
       if (tid <= nx)
         bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, X + tid, Ys + tid, KKs + tid, d.sx);
       ctx.sync();

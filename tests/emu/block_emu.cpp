@@ -62,9 +62,24 @@ extern "C" int emu_block_stage_record(int nx, int nu, int nc) {
   return ab2::make_block_dims(nx, nu, nc, 0).srec_pad;
 }
 
+template <class D> static int run_block(const D &d, int nwarps, const ab2::SweepParams &p);
+
+// the compile-time specialisation (StaticBlockDims) of two small shapes, to execute that
+// instantiation of the code on the CPU
+extern "C" int emu_block_sweep_static(int nx, int nu, int nc, int nwarps, const ab2::SweepParams *pp) {
+  if (nx == 7 && nu == 3 && nc == 0 && pp->nc0 == 7)
+    return run_block(ab2::StaticBlockDims<7, 3, 0, 7>{}, nwarps, *pp);
+  if (nx == 9 && nu == 5 && nc == 3 && pp->nc0 == 9)
+    return run_block(ab2::StaticBlockDims<9, 5, 3, 9>{}, nwarps, *pp);
+  return 1;
+}
+
 extern "C" int emu_block_sweep(int nx, int nu, int nc, int nwarps, const ab2::SweepParams *pp) {
-  const ab2::SweepParams &p = *pp;
-  const ab2::BlockDims d = ab2::make_block_dims(nx, nu, nc, p.nc0);
+  return run_block(ab2::make_block_dims(nx, nu, nc, pp->nc0), nwarps, *pp);
+}
+
+template <class D> static int run_block(const D &d, int nwarps, const ab2::SweepParams &p) {
+  const int nx = d.nx;
   const int T = 32 * nwarps;
   if (nx + 1 > T || d.nk > T || nx + p.nc0 > T || d.nr > T)
     return 2;

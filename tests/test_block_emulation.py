@@ -32,3 +32,11 @@ def test_block_wide_kkt_more_than_one_warp_of_rows():
     """nu + nc = 40 > 32 rows in the reduced KKT matrix, nx + nc0 = 48 rows in the
     initial-stage system: one THREAD per row over two warps."""
     check_against_oracle(24, 20, 20, 0, 2, B=1, mueq=1e-3, seed=5, block=2, tol=1e-9)
+
+
+def test_block_compile_time_specialisation():
+    """The same block program instantiated with compile-time dimensions (what BASELINE config 5
+    runs on the GPU): block < 0 selects it."""
+    check_against_oracle(7, 3, 0, 0, 6, B=2, mueq=1e-8, seed=40, block=-2)
+    check_against_oracle(9, 5, 3, 0, 5, B=2, mueq=1e-3, seed=41, block=-2, tol=1e-9)
+    check_against_oracle(7, 3, 0, 0, 5, B=1, mueq=1e-8, seed=31, block=-1, pivoting=True, tol=1e-9)

@@ -76,7 +76,9 @@ def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0, block=0):
     for k, v in keep.items():
         setattr(p, k, v.ctypes.data_as(_dp))
     p.status = status.ctypes.data_as(C.POINTER(C.c_int))
-    if block:
+    if block < 0:  # compile-time specialisation of the block program (StaticBlockDims)
+        rc = lib.emu_block_sweep_static(nx, nu, nc, int(-block), C.byref(p))
+    elif block:
         rc = lib.emu_block_sweep(nx, nu, nc, int(block), C.byref(p))
     else:
         rc = lib.emu_sweep(nx, nu, nc, int(db), C.byref(p))
