@@ -44,6 +44,17 @@ __global__ void first_step_policy_kernel(const double *__restrict__ fb, const do
   }
 }
 
+// row-major fb [nr][nx] + ff [nr]  ->  column-major [nr][nx+1] with column 0 = ff, per (instance, knot)
+__global__ void gains_kernel(const double *__restrict__ fb, const double *__restrict__ ff, double *__restrict__ dst,
+                             long nrec, int nr, int nx) {
+  const int per = nr * (nx + 1);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nrec * per; i += (long)gridDim.x * blockDim.x) {
+    const long rec = i / per;
+    const int e = (int)(i % per), c = e / nr, r = e % nr; // destination is column-major
+    dst[i] = (c == 0) ? ff[rec * nr + r] : fb[(rec * nr + r) * nx + (c - 1)];
+  }
+}
+
 // one KernelEntry per compile-time shape, each defined in its own object file
 // (kernel_inst.cu compiled with -DAB2_NX=.. -DAB2_NU=.. -DAB2_NC=.. -DAB2_G=..)
 #define X(NX, NU, NC, G) extern const KernelEntry kEntry_##NX##_##NU##_##NC;
@@ -88,6 +99,7 @@ struct ab2_gar_solver {
   ab2::SweepParams p;
   // owned device storage
   double *own_stage = nullptr, *own_term = nullptr, *own_G0 = nullptr, *own_g0 = nullptr;
+  double *gains_tmp = nullptr;
   double *out[AB2_OUT_COUNT] = {};
   size_t out_doubles[AB2_OUT_COUNT] = {};
   size_t out_rec[AB2_OUT_COUNT] = {};  // doubles per knot (or per instance)
@@ -241,7 +253,7 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
       cudaFree(s->out[w]);
   if (s->status)
     cudaFree(s->status);
-  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0})
+  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp})
     if (q)
       cudaFree(q);
   for (int i = 0; i < ab2_gar_solver::kPipeStreams; ++i) {
@@ -572,6 +584,34 @@ int ab2_gar_first_step_policy(ab2_gar_solver *s, double *dst, void *stream) {
       s->out[AB2_OUT_FB], s->out[AB2_OUT_FF], dst, s->d.batch, s->d.horizon, s->nr, s->d.nu, s->d.nx);
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;
+  return AB2_OK;
+}
+
+int ab2_gar_get_gains(ab2_gar_solver *s, double *dst, int memspace, void *stream) {
+  if (!s || !dst)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  if (!s->have_backward)
+    return fail(AB2_ERR_STATE, "get_gains before backward()");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  const long nrec = (long)s->d.batch * s->d.horizon;
+  const size_t total = (size_t)nrec * s->nr * (s->d.nx + 1);
+  if (total == 0)
+    return AB2_OK;
+  double *out = dst;
+  if (memspace != AB2_DEVICE) { // stage on the device, then one copy
+    if (!s->gains_tmp)
+      CUDA_TRY(cudaMalloc(&s->gains_tmp, total * sizeof(double)));
+    out = s->gains_tmp;
+  }
+  long blocks = ((long)total + 255) / 256;
+  if (blocks > 148 * 8)
+    blocks = 148 * 8;
+  ab2::gains_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(s->out[AB2_OUT_FB], s->out[AB2_OUT_FF], out, nrec,
+                                                                    s->nr, s->d.nx);
+  CUDA_TRY(cudaGetLastError());
+  s->launches += 1;
+  if (memspace != AB2_DEVICE)
+    CUDA_TRY(cudaMemcpyAsync(dst, out, total * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return AB2_OK;
 }
 

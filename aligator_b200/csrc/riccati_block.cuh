@@ -293,13 +293,6 @@ AB2_D bool ldlt_fast_warp(Ctx &ctx, double *a, const int n, double *dd, double *
   return true;
 }
 
-template <class D> struct dims_static {
-  static constexpr bool value = false;
-};
-template <int NX, int NU, int NC, int NC0> struct dims_static<StaticBlockDims<NX, NU, NC, NC0>> {
-  static constexpr bool value = true;
-};
-
 constexpr int BLK_CH = 4; // n-tiles accumulated together by one warp (one work item)
 
 // ---------------------------------------------------------------------------

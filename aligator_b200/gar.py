@@ -82,6 +82,7 @@ def lib():
         L.ab2_gar_assemble.argtypes = [C.c_void_p, C.POINTER(LqInputs), C.c_void_p]
         L.ab2_gar_get_problem.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_problem_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.ab2_gar_get_gains.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_first_step_policy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ab2_gar_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ab2_gar_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -252,6 +253,16 @@ class CudaRiccatiBatch:
             _check(lib().ab2_gar_problem_ptr(self.h, w, C.byref(p)))
             out.append(p.value)
         return out
+
+    def get_gains(self, stream=0):
+        """[batch][N][nx+1][nu+nc+nx] view of the column-major gain blocks ``[ff | fb]``
+        (results_.gains_ layout): ``g[b, t, 0]`` is the feedforward, ``g[b, t, 1 + j]`` column j."""
+        d = self.dims
+        nr = d.nu + d.nc + d.nx
+        buf = np.empty(max(d.batch * d.horizon * nr * (d.nx + 1), 1), dtype=np.float64)
+        _check(lib().ab2_gar_get_gains(self.h, _ptr(buf), AB2_HOST, C.c_void_p(stream)))
+        self.synchronize(stream)
+        return buf[:d.batch * d.horizon * nr * (d.nx + 1)].reshape(d.batch, d.horizon, d.nx + 1, nr)
 
     def first_step_policy_into(self, dst, stream=0):
         """[K_0 | k_0] of every instance -> device buffer dst [batch][nu][nx+1]."""

@@ -190,6 +190,12 @@ int ab2_gar_get_range(ab2_gar_solver *s, int what, int b0, int nb, int t0, int n
  * (results_.gains_[0], solver-proxddp.hxx:619-626) and the payload of the one all-gather when
  * the batch is sharded across GPUs. */
 int ab2_gar_first_step_policy(ab2_gar_solver *s, double *dst, void *stream);
+/* Gains in the layout of the caller's results: for every instance and stage knot a COLUMN-major
+ * (nu+nc+nx) x (nx+1) block whose column 0 is the feedforward [k; z; a] and columns 1..nx the
+ * feedback [K; Z; Ahat] -- what SolverProxDDP copies into results_.gains_[i] from
+ * getFeedforward(i) / getFeedback(i) (solver-proxddp.hxx:619-626, results.hxx:23-38).
+ * dst: [batch][N][(nu+nc+nx)*(nx+1)], host or device. */
+int ab2_gar_get_gains(ab2_gar_solver *s, double *dst, int memspace, void *stream);
 int ab2_gar_device_ptr(ab2_gar_solver *s, int what, double **out);
 /* Per-instance status words (layout above). */
 int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream);

@@ -418,3 +418,36 @@ def test_first_step_policy_kernel(gar):
     want = sharding.pack_first_step_policy(torch, torch.from_numpy(fb[:, 0]), torch.from_numpy(ff[:, 0]), nu, nx)
     assert torch.equal(pol.cpu(), want)
     s.close()
+
+
+def test_gains_in_results_layout(gar):
+    """ab2_gar_get_gains: column-major (nu+nc+nx) x (nx+1) blocks with column 0 = ff, the layout of
+    results_.gains_ (solver-proxddp.hxx:619-626)."""
+    nx, nu, nc, nct, N, B, mueq = 4, 2, 2, 0, 7, 5, 1e-3
+    probs = gen.generate_batch(8, B, N, nx, nu, nc, nct)
+    s = gar.CudaRiccatiBatch(nx, nu, nc, nct, nx, N, B)
+    s.set_problem(*gar.pack_problems(probs))
+    s.sweep(mueq)
+    g = s.get_gains()
+    fb, ff = s.get(gar.OUT_FB), s.get(gar.OUT_FF)
+    assert np.array_equal(g[:, :, 0, :], ff)
+    assert np.array_equal(g[:, :, 1:, :], fb.transpose(0, 1, 3, 2))
+    s.close()
+
+
+def test_cuda_matches_committed_fixture(gar):
+    """The CUDA path against the committed (oracle-generated) fixture tests/golden/oracle_regression.npz
+    -- no oracle code runs in this test."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ref = np.load(os.path.join(here, "golden", "oracle_regression.npz"))
+    for case, (nx, nu, nc, nct, N, mueq, seed) in mg.CASES.items():
+        probs = gen.generate_batch(seed, 2, N, nx, nu, nc, nct)
+        got, _ = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq)
+        tol = 1e-9 if (nc or nct) else TOL
+        for k in ("fb", "ff", "Vxx", "vx", "xs", "us", "lbdas"):
+            assert gen.rel_fro(got[k], ref["%s/%s" % (case, k)]) <= tol, (case, k)

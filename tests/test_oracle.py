@@ -437,3 +437,19 @@ def test_batched_driver_matches_serial_class():
             assert np.array_equal(out["lbdas"][b, t], lbdas[t + 1])
         assert np.array_equal(out["xs"][b, N], xs[N])
         assert np.array_equal(out["lbd0"][b], lbdas[0])
+
+
+def test_oracle_regression_fixture():
+    """tests/golden/oracle_regression.npz (oracle-generated, see the README there): the oracle
+    still produces these K, k, Vxx, vx, xs, us, lambdas (1e-12: compiler/FMA freedom only)."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ref = np.load(os.path.join(here, "golden", "oracle_regression.npz"))
+    for case in mg.CASES:
+        got = mg.solve(case)
+        for k in ("fb", "ff", "Vxx", "vx", "xs", "us", "lbdas"):
+            assert gen.rel_fro(got[k], ref["%s/%s" % (case, k)]) <= 1e-12, (case, k)
