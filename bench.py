@@ -154,19 +154,24 @@ def run_reference(args, rank, world):
     stage, term, G0, g0 = [a.numpy() for a in synth_batch_torch(torch, nb, HORIZON, NX, NU, "cpu", 1234, NC)]
     from oracle import gar_oracle as orc
     bo = orc.BatchedOracle(NX, NU, NC, NCT, NX, HORIZON, nb, stage, term, G0, g0)
-    threads = orc.num_threads()
-    t1 = 1e9
-    for _ in range(max(args.warmup, 1)):
-        t1 = min(t1, bo.sweep(MUEQ, reps=1))
+    # every host core (torchrun exports OMP_NUM_THREADS=1 to its workers: ask explicitly)
+    threads = max(orc.num_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity")
+                  else (os.cpu_count() or 1))
+    # warm-up: W sweeps and at least 1.5 s (the worker threads' first sweeps run far below the
+    # sustained pace: thread start-up, allocator arenas, first touch)
+    t1, tw, nw = 1e9, 0.0, 0
+    while nw < max(args.warmup, 1) or tw < 1.5:
+        dt = bo.sweep(MUEQ, reps=1, nthreads=threads)
+        t1, tw, nw = min(t1, dt), tw + dt, nw + 1
     if args.ref_seconds > 0:  # bounded sample sized in seconds (used for cpu_baseline)
         t, steps = 0.0, 0
         chunk = max(1, int(1.0 / max(t1, 1e-5)))  # about a second of sweeps at a time
         while t < args.ref_seconds:  # (the sustained pace is well below a lone sweep's)
-            t += bo.sweep(MUEQ, reps=chunk)
+            t += bo.sweep(MUEQ, reps=chunk, nthreads=threads)
             steps += chunk
         args.steps = steps
     else:
-        t = bo.sweep(MUEQ, reps=args.steps)
+        t = bo.sweep(MUEQ, reps=args.steps, nthreads=threads)
     knots = nb * (HORIZON + 1) * args.steps
     v = knots / t
     line = {"metric": "riccati_knots_per_sec", "value": v, "unit": "knots/s", "n_gpus": args.gpus,
