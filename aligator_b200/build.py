@@ -47,7 +47,7 @@ def build(verbose=False, force=False, ptxas_v=False):
     hdrs = [os.path.join(CSRC, f) for f in ("riccati_group.cuh", "riccati_launch.cuh", "riccati_configs.h")]
     hdrs.append(os.path.join(PKG, "..", "include", "aligator_b200", "gar.h"))
     hdrs_block = hdrs + [os.path.join(CSRC, f) for f in ("riccati_block.cuh", "riccati_block_launch.h",
-                                                          "lq_assemble.h")]
+                                                          "lq_assemble.h", "kkt_error.h")]
     extra = ["-Xptxas", "-v"] if ptxas_v else []
     jobs = []
     for (nx, nu, nc, g) in configs():
@@ -63,6 +63,9 @@ def build(verbose=False, force=False, ptxas_v=False):
     jobs.append((obj, [NVCC] + ARCH + FLAGS + ["-c", src, "-o", obj]))
     src = os.path.join(CSRC, "block_kernel.cu")
     obj = os.path.join(OBJ, "block_%s.o" % _digest(hdrs_block + [src], str(extra)))
+    jobs.append((obj, [NVCC] + ARCH + FLAGS + extra + ["-c", src, "-o", obj]))
+    src = os.path.join(CSRC, "kkt_error.cu")
+    obj = os.path.join(OBJ, "kkt_%s.o" % _digest([os.path.join(CSRC, "kkt_error.h"), src], str(extra)))
     jobs.append((obj, [NVCC] + ARCH + FLAGS + extra + ["-c", src, "-o", obj]))
     src = os.path.join(CSRC, "lq_assemble.cu")
     obj = os.path.join(OBJ, "assemble_%s.o" % _digest([hdrs[-1], os.path.join(CSRC, "lq_assemble.h"), src], str(extra)))

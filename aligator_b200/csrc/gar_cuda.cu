@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/aligator_b200/gar.h"
+#include "kkt_error.h"
 #include "lq_assemble.h"
 #include "riccati_block_launch.h"
 #include "riccati_configs.h"
@@ -99,7 +100,7 @@ struct ab2_gar_solver {
   ab2::SweepParams p;
   // owned device storage
   double *own_stage = nullptr, *own_term = nullptr, *own_G0 = nullptr, *own_g0 = nullptr;
-  double *gains_tmp = nullptr;
+  double *gains_tmp = nullptr, *kkt_tmp = nullptr;
   double *out[AB2_OUT_COUNT] = {};
   size_t out_doubles[AB2_OUT_COUNT] = {};
   size_t out_rec[AB2_OUT_COUNT] = {};  // doubles per knot (or per instance)
@@ -253,7 +254,7 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
       cudaFree(s->out[w]);
   if (s->status)
     cudaFree(s->status);
-  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp})
+  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp})
     if (q)
       cudaFree(q);
   for (int i = 0; i < ab2_gar_solver::kPipeStreams; ++i) {
@@ -612,6 +613,44 @@ int ab2_gar_get_gains(ab2_gar_solver *s, double *dst, int memspace, void *stream
   s->launches += 1;
   if (memspace != AB2_DEVICE)
     CUDA_TRY(cudaMemcpyAsync(dst, out, total * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return AB2_OK;
+}
+
+int ab2_gar_kkt_error(ab2_gar_solver *s, double mueq, double *dst, int memspace, void *stream) {
+  if (!s || !dst)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  if (!s->have_problem || !s->have_backward)
+    return fail(AB2_ERR_STATE, "kkt_error needs a problem and a completed sweep");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  if (!s->kkt_tmp)
+    CUDA_TRY(cudaMalloc(&s->kkt_tmp, (size_t)s->d.batch * 3 * sizeof(double)));
+  ab2::KktErrorArgs a;
+  a.batch = s->d.batch;
+  a.N = s->d.horizon;
+  a.nx = s->d.nx;
+  a.nu = s->d.nu;
+  a.nc = s->d.nc;
+  a.nct = s->d.nct;
+  a.nc0 = s->d.nc0;
+  a.srec = s->srec;
+  a.trec = s->trec;
+  a.mueq = mueq;
+  a.stage = s->p.stage;
+  a.term = s->p.term;
+  a.G0 = s->p.G0;
+  a.g0 = s->p.g0;
+  a.xs = s->out[AB2_OUT_XS];
+  a.us = s->out[AB2_OUT_US];
+  a.vs = s->out[AB2_OUT_VS];
+  a.vsT = s->out[AB2_OUT_VST];
+  a.lbd0 = s->out[AB2_OUT_LBD0];
+  a.lbdas = s->out[AB2_OUT_LBDAS];
+  a.out = (memspace == AB2_DEVICE) ? dst : s->kkt_tmp;
+  CUDA_TRY(ab2::launch_kkt_error(a, (cudaStream_t)stream));
+  s->launches += 1;
+  if (memspace != AB2_DEVICE)
+    CUDA_TRY(cudaMemcpyAsync(dst, s->kkt_tmp, (size_t)s->d.batch * 3 * sizeof(double), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
   return AB2_OK;
 }
 

@@ -82,6 +82,7 @@ def lib():
         L.ab2_gar_assemble.argtypes = [C.c_void_p, C.POINTER(LqInputs), C.c_void_p]
         L.ab2_gar_get_problem.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_problem_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.ab2_gar_kkt_error.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_get_gains.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_first_step_policy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ab2_gar_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -252,6 +253,14 @@ class CudaRiccatiBatch:
             p = C.c_void_p()
             _check(lib().ab2_gar_problem_ptr(self.h, w, C.byref(p)))
             out.append(p.value)
+        return out
+
+    def kkt_error(self, mueq, stream=0):
+        """[batch][3] = (dynamics, constraint, stationarity) infinity norms of lqrComputeKktError
+        (gar/utils.hxx:88-182) for the current problem and the last forward pass, computed on the device."""
+        out = np.empty((self.dims.batch, 3), dtype=np.float64)
+        _check(lib().ab2_gar_kkt_error(self.h, C.c_double(mueq), _ptr(out), AB2_HOST, C.c_void_p(stream)))
+        self.synchronize(stream)
         return out
 
     def get_gains(self, stream=0):

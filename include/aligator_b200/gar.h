@@ -196,6 +196,11 @@ int ab2_gar_first_step_policy(ab2_gar_solver *s, double *dst, void *stream);
  * getFeedforward(i) / getFeedback(i) (solver-proxddp.hxx:619-626, results.hxx:23-38).
  * dst: [batch][N][(nu+nc+nx)*(nx+1)], host or device. */
 int ab2_gar_get_gains(ab2_gar_solver *s, double *dst, int memspace, void *stream);
+/* lqrComputeKktError (gar/utils.hxx:88-182) of the current problem and the solution of the last
+ * forward pass, for every instance: dst[batch][3] = infinity norms of the dynamics (incl. the
+ * initial condition), constraint (C x + D u + d - mu v) and stationarity residuals.  Computed on
+ * the device (one warp per (instance, knot)); dst in host or device memory. */
+int ab2_gar_kkt_error(ab2_gar_solver *s, double mueq, double *dst, int memspace, void *stream);
 int ab2_gar_device_ptr(ab2_gar_solver *s, int what, double **out);
 /* Per-instance status words (layout above). */
 int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream);

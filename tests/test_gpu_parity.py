@@ -451,3 +451,43 @@ def test_cuda_matches_committed_fixture(gar):
         tol = 1e-9 if (nc or nct) else TOL
         for k in ("fb", "ff", "Vxx", "vx", "xs", "us", "lbdas"):
             assert gen.rel_fro(got[k], ref["%s/%s" % (case, k)]) <= tol, (case, k)
+
+
+@pytest.mark.parametrize("shape", [(12, 6, 0, 0, 20, 9, 1e-8), (4, 2, 2, 3, 12, 17, 1e-3), (9, 5, 3, 0, 6, 5, 1e-3)])
+def test_kkt_error_kernel_matches_oracle(gar, shape):
+    """ab2_gar_kkt_error (lqrComputeKktError on the device, gar/utils.hxx:88-182) against the oracle's
+    restatement evaluated on the SAME solution, instance by instance."""
+    nx, nu, nc, nct, N, B, mueq = shape
+    probs = gen.generate_batch(21, B, N, nx, nu, nc, nct)
+    s = gar.CudaRiccatiBatch(nx, nu, nc, nct, probs[0].nc0, N, B)
+    s.set_problem(*gar.pack_problems(probs))
+    s.sweep(mueq)
+    got = s.kkt_error(mueq)
+    xs, us, vs, vsT = s.get(gar.OUT_XS), s.get(gar.OUT_US), s.get(gar.OUT_VS), s.get(gar.OUT_VST)
+    lb, lb0 = s.get(gar.OUT_LBDAS), s.get(gar.OUT_LBD0)
+    for b in range(B):
+        op = orc.OracleProblem(probs[b])
+        sol = orc.OracleSolution(op)
+        sol.set(xs=[xs[b, t] for t in range(N + 1)], us=[us[b, t] for t in range(N)],
+                vs=[vs[b, t] for t in range(N)] + [vsT[b]], lbdas=[lb0[b]] + [lb[b, t] for t in range(N)])
+        ref = np.array(orc.kkt_error(op, sol, mueq))
+        assert np.allclose(got[b], ref, rtol=1e-9, atol=1e-13), (b, got[b], ref)
+    # and the residuals themselves are within the reference's test threshold (tests/gar/riccati.cpp:84)
+    assert got.max() <= 1e-8
+    s.close()
+
+
+def test_kkt_error_of_every_instance_at_full_size(gar):
+    """BASELINE config 2 at full size: the KKT residuals of ALL 4096 instances, computed on the device."""
+    import torch
+    sys_path_bench = __import__("bench")
+    nx, nu, N, B = 12, 6, 100, 4096
+    stage, term, G0, g0 = sys_path_bench.synth_batch_torch(torch, B, N, nx, nu, torch.device("cuda:0"), 7, 0)
+    s = gar.CudaRiccatiBatch(nx, nu, 0, 0, nx, N, B)
+    s.set_problem(stage, term, G0, g0, memspace=gar.AB2_DEVICE)
+    s.sweep(1e-11)
+    assert np.all(s.status() == 0)
+    e = s.kkt_error(1e-11)
+    assert e.shape == (B, 3) and np.all(np.isfinite(e))
+    assert e.max() <= 1e-8, e.max()
+    s.close()
