@@ -2,7 +2,8 @@
 // device: the infinity norms of the dynamics, constraint and stationarity residuals of the
 // solution the sweep just produced.  One warp per (instance, knot): lane = residual row (lanes
 // walk the columns of the column-major blocks with unit stride), the per-instance maxima meet
-// through atomicMax on the bit patterns (non-negative doubles order like unsigned integers).
+// through atomicMax on the bit patterns (non-negative doubles order like unsigned integers, and
+// a NaN sorts above every number: it survives).
 // Lets a caller -- and the tests -- check ALL instances of a full-size batch without a CPU solver.
 #include <cuda_runtime.h>
 
@@ -12,6 +13,13 @@ namespace ab2 {
 
 __device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
   atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// running infinity norm that keeps a NaN once it has seen one (fmax would drop it: a residual
+// that is not a number must not read as "converged")
+__device__ __forceinline__ double upd(double m, double s) {
+  const double v = fabs(s);
+  return (v > m || v != v) ? v : m;
 }
 
 __global__ void __launch_bounds__(256) kkt_error_kernel(const KktErrorArgs a) {
@@ -43,7 +51,7 @@ __global__ void __launch_bounds__(256) kkt_error_kernel(const KktErrorArgs a) {
         double s = a.g0[b * nc0 + i];
         for (int c = 0; c < nx; ++c)
           s += a.G0[b * nc0 * nx + i + (long)c * nc0] * x[c];
-        dynE = fmax(dynE, fabs(s));
+        dynE = upd(dynE, s);
       }
     for (int i = lane; i < ncc; i += 32) { // C x + D u + d - mu v (:110-116)
       double s = d[i] - a.mueq * v[i];
@@ -51,7 +59,7 @@ __global__ void __launch_bounds__(256) kkt_error_kernel(const KktErrorArgs a) {
         s += C[i + (long)c * ncc] * x[c];
       for (int c = 0; c < nuu; ++c)
         s += D[i + (long)c * ncc] * u[c];
-      cstE = fmax(cstE, fabs(s));
+      cstE = upd(cstE, s);
     }
     for (int i = lane; i < nx; i += 32) { // gx (:118-146)
       double s = q[i];
@@ -70,7 +78,7 @@ __global__ void __launch_bounds__(256) kkt_error_kernel(const KktErrorArgs a) {
       if (!term)
         for (int c = 0; c < nx; ++c)
           s += A[c + (long)i * nx] * lamn[c];
-      dualE = fmax(dualE, fabs(s));
+      dualE = upd(dualE, s);
     }
     for (int i = lane; i < nuu; i += 32) { // gu
       double s = r[i];
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(256) kkt_error_kernel(const KktErrorArgs a) {
         s += R[i + (long)c * nu] * u[c];
       for (int c = 0; c < nx; ++c)
         s += B[c + (long)i * nx] * lamn[c];
-      dualE = fmax(dualE, fabs(s));
+      dualE = upd(dualE, s);
     }
     if (!term)
       for (int i = lane; i < nx; i += 32) { // A x + B u + f - x+  (:148-151)
@@ -91,13 +99,13 @@ __global__ void __launch_bounds__(256) kkt_error_kernel(const KktErrorArgs a) {
           s += A[i + (long)c * nx] * x[c];
         for (int c = 0; c < nu; ++c)
           s += B[i + (long)c * nx] * u[c];
-        dynE = fmax(dynE, fabs(s));
+        dynE = upd(dynE, s);
       }
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
-      dynE = fmax(dynE, __shfl_xor_sync(0xffffffffu, dynE, m));
-      cstE = fmax(cstE, __shfl_xor_sync(0xffffffffu, cstE, m));
-      dualE = fmax(dualE, __shfl_xor_sync(0xffffffffu, dualE, m));
+      dynE = upd(dynE, __shfl_xor_sync(0xffffffffu, dynE, m));
+      cstE = upd(cstE, __shfl_xor_sync(0xffffffffu, cstE, m));
+      dualE = upd(dualE, __shfl_xor_sync(0xffffffffu, dualE, m));
     }
     if (lane == 0) {
       atomic_max_nonneg(a.out + b * 3 + 0, dynE);
