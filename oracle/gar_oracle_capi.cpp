@@ -378,17 +378,30 @@ double gar_oracle_batched_sweep(void *bv, double mueq, int reps, int nthreads,
 #else
   nthreads = 1;
 #endif
+  // One parallel region around ALL repetitions: instances are independent, so each thread
+  // sweeps its own instances `reps` times back to back -- no fork/join or barrier per sweep
+  // (with many threads and a passive wait policy that overhead dwarfs the work).
   auto t0 = std::chrono::steady_clock::now();
-  for (int r = 0; r < reps; ++r) {
 #ifdef _OPENMP
-#pragma omp parallel for num_threads(nthreads) schedule(static)
+#pragma omp parallel num_threads(nthreads)
 #endif
-    for (int i = 0; i < b->batch; ++i) {
-      bool ok = b->solvers[i]->backward(mueq);
-      ok = b->solvers[i]->forward(b->sols[i]) && ok;
-      if (status)
-        status[i] = ok ? 1 : 0;
-    }
+  {
+#ifdef _OPENMP
+    const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+#pragma omp barrier
+#pragma omp master
+    t0 = std::chrono::steady_clock::now();
+#pragma omp barrier
+#else
+    const int tid = 0, nt = 1;
+#endif
+    for (int r = 0; r < reps; ++r)
+      for (int i = tid; i < b->batch; i += nt) {
+        bool ok = b->solvers[i]->backward(mueq);
+        ok = b->solvers[i]->forward(b->sols[i]) && ok;
+        if (status)
+          status[i] = ok ? 1 : 0;
+      }
   }
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
