@@ -1147,6 +1147,12 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
           }
         }
       }
+      if (!C::DB && t > 0) {
+        // single buffer: [A|B|f] of this knot now lives in the accumulators and fragments of every
+        // lane (the products above consumed the loads): refill it while the results are stored
+        ctx.sync();
+        ctx.issue_copy(0, rec, AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD, C::SPLIT);
+      }
       if (C::VXX_BULK && t > 0)
         ctx.bulk_store_wait_read(); // the previous knot's Vxx store has finished reading V'
       AB2_UNROLL
@@ -1197,8 +1203,6 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     if (C::VXX_BULK && t > 0)
       ctx.async_fence(); // this lane's writes to V' become visible to the TMA store below
     ctx.sync();
-    if (!C::DB && t > 0) // [A|B|f] of this knot is consumed (the closing products hold it in registers)
-      ctx.issue_copy(0, rec, AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD, C::SPLIT);
     if (t > 0) { // symmetric Vxx_t, as the next step of the reference leaves it
       double *Vt = AB2_VXX_B + (size_t)t * NX * NX;
       if (C::VXX_BULK) { // V' is dense in shared memory: one TMA bulk store, no LDS/STG
