@@ -40,3 +40,24 @@ def test_block_compile_time_specialisation():
     check_against_oracle(7, 3, 0, 0, 6, B=2, mueq=1e-8, seed=40, block=-2)
     check_against_oracle(9, 5, 3, 0, 5, B=2, mueq=1e-3, seed=41, block=-2, tol=1e-9)
     check_against_oracle(7, 3, 0, 0, 5, B=1, mueq=1e-8, seed=31, block=-1, pivoting=True, tol=1e-9)
+
+
+def test_block_random_shapes():
+    """Seeded random sweep over run-time shapes (odd sizes, constrained and not, terminal constraints,
+    every warp count that fits): catches index arithmetic that only breaks off the beaten path."""
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    done = 0
+    while done < 16:
+        nx, nu = int(rng.integers(1, 15)), int(rng.integers(1, 9))
+        nc = int(rng.integers(0, 4)) if rng.random() < 0.5 else 0
+        nct = int(rng.integers(0, 3)) if rng.random() < 0.3 else 0
+        N = int(rng.integers(0, 6))
+        need = max(nx + 1, nu + nc, 2 * nx, nu + nc + nx)
+        nw = int(rng.integers((need + 31) // 32, 4))
+        if 32 * nw < need:
+            continue
+        mueq = 1e-3 if (nc or nct) else 1e-8
+        check_against_oracle(nx, nu, nc, nct, N, B=1, mueq=mueq, seed=300 + done, block=nw,
+                             tol=1e-9 if (nc or nct) else 1e-10)
+        done += 1
