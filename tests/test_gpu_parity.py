@@ -504,3 +504,47 @@ def test_kkt_error_of_every_instance_at_full_size(gar):
     assert e.shape == (B, 3) and np.all(np.isfinite(e))
     assert e.max() <= 1e-8, e.max()
     s.close()
+
+
+@pytest.mark.parametrize("shape", [(5, 2, 0, 0, 3, 6, 1e-8), (4, 3, 2, 0, 2, 5, 1e-3), (7, 3, 0, 2, 7, 4, 1e-2)])
+def test_parametric_problems(gar, shape):
+    """nth > 0 (riccati-kernel.hxx:185-192, 278-311; proximal-riccati.hxx:50-59; forward with theta)
+    through the Python mirror of ProximalRiccatiSolver, against the oracle."""
+    import test_block_parametric as tp
+    nx, nu, nc, nct, nth, N, mueq = shape
+    probs = [tp.make_problem(50 + b, N, nx, nu, nc, nct, nth) for b in range(3)]
+    solver = gar.ProximalRiccatiSolver(probs)
+    assert solver.backward(mueq)
+    thetas = np.random.default_rng(1).standard_normal((3, nth))
+    sols = [gar.lqr_initialize_solution(p) for p in probs] if hasattr(gar, "lqr_initialize_solution") else None
+    tol = 1e-9 if (nc or nct) else TOL
+    for b, p in enumerate(probs):
+        op = orc.OracleProblem(p)
+        ref = orc.ProximalRiccatiSolver(op)
+        assert ref.backward(mueq)
+        for t in range(N):
+            f = ref.factor(t)
+            assert gen.rel_fro(solver.getFeedback(t, b), f["fb"]) <= tol
+            assert gen.rel_fro(solver.getFeedbackTheta(t, b), f["fth"]) <= tol
+        k0 = ref.kkt0()
+        mine = solver.kkt0(b)
+        for key in ("ff", "fth", "thGrad", "thHess"):
+            assert gen.rel_fro(mine[key], k0[key]) <= tol, key
+        for t in range(N + 1):
+            f = ref.factor(t)
+            assert gen.rel_fro(solver._get(gar.OUT_VXT)[b, t], f["Vxt"]) <= tol
+            assert gen.rel_fro(solver._get(gar.OUT_VTT)[b, t], f["Vtt"]) <= tol
+            assert gen.rel_fro(solver._get(gar.OUT_VT)[b, t], f["vt"]) <= tol
+    # forward with theta
+    solver.batch.forward(theta=thetas)
+    X, U = solver.batch.get(gar.OUT_XS), solver.batch.get(gar.OUT_US)
+    L0, L = solver.batch.get(gar.OUT_LBD0), solver.batch.get(gar.OUT_LBDAS)
+    for b, p in enumerate(probs):
+        op = orc.OracleProblem(p)
+        ref = orc.ProximalRiccatiSolver(op)
+        ref.backward(mueq)
+        sol = orc.OracleSolution(op)
+        assert ref.forward(sol, thetas[b])
+        xs, us, vs, lb = sol.get()
+        assert gen.rel_fro(X[b], np.array(xs)) <= tol and gen.rel_fro(U[b], np.array(us[:N])) <= tol
+        assert gen.rel_fro(L0[b], lb[0]) <= tol and gen.rel_fro(L[b], np.array(lb[1:])) <= tol
