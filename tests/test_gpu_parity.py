@@ -548,3 +548,32 @@ def test_parametric_problems(gar, shape):
         xs, us, vs, lb = sol.get()
         assert gen.rel_fro(X[b], np.array(xs)) <= tol and gen.rel_fro(U[b], np.array(us[:N])) <= tol
         assert gen.rel_fro(L0[b], lb[0]) <= tol and gen.rel_fro(L[b], np.array(lb[1:])) <= tol
+
+
+@pytest.mark.parametrize("shape", [(4, 2, 0, 0, 11, 3), (6, 3, 0, 0, 20, 4), (4, 2, 2, 0, 13, 2)])
+def test_parallel_solver_mirror_on_gpu(gar, shape):
+    """ParallelRiccatiSolver mirror (aligator_b200/parallel.py) with the CUDA leg back end: the legs are
+    parametric problems on the CTA-per-instance kernel, the condensed system is solved on the host;
+    the rollout equals the serial oracle solution."""
+    import copy
+    from aligator_b200 import parallel as par
+    nx, nu, nc, nct, N, J1 = shape
+    mueq = 1e-3 if nc else 1e-8
+    p = gen.generate_batch(77, 1, N, nx, nu, nc, nct)[0]
+    ops = orc.OracleProblem(copy.deepcopy(p))
+    ser = orc.ProximalRiccatiSolver(ops)
+    ser.backward(mueq)
+    sol = orc.OracleSolution(ops)
+    ser.forward(sol)
+    xs_s, us_s, vs_s, ls_s = sol.get()
+    mine = par.ParallelRiccatiSolver(p, J1, par.CudaLegBackend())
+    assert mine.backward(mueq)
+    xs = [np.zeros(nx) for _ in range(N + 1)]
+    us = [np.zeros(nu) for _ in range(N)]
+    vs = [np.zeros(nc) for _ in range(N)] + [np.zeros(nct)]
+    lb = [np.zeros(p.nc0)] + [np.zeros(nx) for _ in range(N)]
+    mine.forward(xs, us, vs, lb)
+    tol = 1e-7 if nc else 1e-8
+    assert gen.rel_fro(np.array(xs), np.array(xs_s)) <= tol
+    assert gen.rel_fro(np.array(us), np.array(us_s[:N])) <= tol
+    assert gen.rel_fro(np.array(lb[1:]), np.array(ls_s[1:])) <= tol
