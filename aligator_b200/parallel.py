@@ -5,9 +5,10 @@ solves -- all legs of all instances in one batch per distinct leg length -- and 
 symmetric block-tridiagonal system that couples the leg heads (block-tridiagonal.hpp:52-182) is
 solved here, on the host, with the reference's Bunch-Kaufman pivoting (core/bunchkaufman.hpp).
 
-The leg back end is pluggable (``backend(problem_of_one_leg) -> LegResult``): the product back end
-is the CUDA batch (``CudaLegBackend``); the CPU tests plug the oracle in, which exercises every
-line of the orchestration without a GPU.
+The leg back end is pluggable (``backend(knots_of_one_leg, final, mueq) -> LegResult``): the product
+back end is the CUDA batch (``CudaLegBackend``; it needs the parametric kernels, which are not in
+this build yet -- it raises instead of falling back); the CPU tests plug the oracle in, which
+exercises every line of the orchestration without a GPU.
 """
 from __future__ import annotations
 
@@ -323,6 +324,9 @@ class CudaLegBackend:
 
     def __call__(self, stages, final, mueq):
         from . import gar
+        if not hasattr(gar.lib(), "ab2_gar_create_parametric"):
+            # no CPU fallback: the legs need the parametric kernels (branch `parametric`)
+            raise gar.GarError("this build of libaligator_b200_gar has no parametric (nth > 0) kernels")
         stages = list(stages)
         if final:
             knots, term = stages[:-1], stages[-1]
