@@ -92,3 +92,20 @@ def test_parametric_block_sweep(shape):
     assert gen.rel_fro(got["us"][0], np.array(us[:N])) <= tol
     assert gen.rel_fro(got["lbd0"][0], lb[0]) <= tol
     assert gen.rel_fro(got["lbdas"][0], np.array(lb[1:])) <= tol
+
+
+def test_parametric_random_shapes():
+    """Seeded random sweep: odd sizes, constrained / terminal-constrained, nth from 1 to nx."""
+    rng = np.random.default_rng(99)
+    done = 0
+    while done < 10:
+        nx, nu = int(rng.integers(1, 9)), int(rng.integers(1, 5))
+        nc = int(rng.integers(0, 3)) if rng.random() < 0.4 else 0
+        nct = int(rng.integers(0, 3)) if rng.random() < 0.3 else 0
+        nth = int(rng.integers(1, nx + 1))
+        N = int(rng.integers(0, 5))
+        need = max(nx + 1, nu + nc, 2 * nx, nu + nc + nx, nth)
+        nw = (need + 31) // 32
+        mueq = 1e-3 if (nc or nct) else 1e-8
+        test_parametric_block_sweep((nx, nu, nc, nct, nth, N, mueq, nw))
+        done += 1
