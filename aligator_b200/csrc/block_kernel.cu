@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256) __maxnreg__(MAXREG)
   }
 }
 
-int block_threads(int nx, int nu, int nc, int nc0) {
-  const BlockDims d = make_block_dims(nx, nu, nc, nc0);
+int block_threads(int nx, int nu, int nc, int nc0, int nth) {
+  const BlockDims d = make_block_dims(nx, nu, nc, nc0, nth);
   int need = nx + 1;
   if (d.nk > need)
     need = d.nk;
@@ -98,6 +98,8 @@ int block_threads(int nx, int nu, int nc, int nc0) {
     need = nx + nc0;
   if (d.nr > need)
     need = d.nr;
+  if (nth > need)
+    need = nth;
   if (need > 256)
     return 0;
   const int nchunk = (d.nt + BLK_CH - 1) / BLK_CH;
@@ -110,13 +112,13 @@ int block_threads(int nx, int nu, int nc, int nc0) {
   return 32 * warps;
 }
 
-size_t block_smem_bytes(int nx, int nu, int nc, int nc0) {
-  const BlockDims d = make_block_dims(nx, nu, nc, nc0);
+size_t block_smem_bytes(int nx, int nu, int nc, int nc0, int nth) {
+  const BlockDims d = make_block_dims(nx, nu, nc, nc0, nth);
   return (size_t)d.s_end * sizeof(double) + 8 * NBAR;
 }
 
-bool block_supported(int nx, int nu, int nc, int nc0) {
-  return block_threads(nx, nu, nc, nc0) > 0 && block_smem_bytes(nx, nu, nc, nc0) <= (size_t)227 * 1024;
+bool block_supported(int nx, int nu, int nc, int nc0, int nth) {
+  return block_threads(nx, nu, nc, nc0, nth) > 0 && block_smem_bytes(nx, nu, nc, nc0, nth) <= (size_t)227 * 1024;
 }
 
 template <int MAXREG, class D>
@@ -156,12 +158,12 @@ static cudaError_t launch_block_t(const SweepParams &p, const D &d, int threads,
 }
 
 cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st, int *info) {
-  const BlockDims d = make_block_dims(nx, nu, nc, p.nc0);
-  const int threads = block_threads(nx, nu, nc, p.nc0);
-  const size_t smem = block_smem_bytes(nx, nu, nc, p.nc0);
+  const BlockDims d = make_block_dims(nx, nu, nc, p.nc0, p.nth);
+  const int threads = block_threads(nx, nu, nc, p.nc0, p.nth);
+  const size_t smem = block_smem_bytes(nx, nu, nc, p.nc0, p.nth);
   // BASELINE config 5 (Talos whole-body walk, nx 57 nu 28, initial condition on the full state):
   // the same code specialised at compile time
-  if (nx == 57 && nu == 28 && nc == 0 && p.nc0 == 57)
+  if (nx == 57 && nu == 28 && nc == 0 && p.nc0 == 57 && p.nth == 0)
     return launch_block_t<255>(p, StaticBlockDims<57, 28, 0, 57>{}, threads, smem, st, info);
   // one CTA per SM anyway (shared memory): let it use the whole register file
   if (2 * (smem + 1024) > (size_t)227 * 1024)

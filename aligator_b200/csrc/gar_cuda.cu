@@ -100,7 +100,8 @@ struct ab2_gar_solver {
   ab2::SweepParams p;
   // owned device storage
   double *own_stage = nullptr, *own_term = nullptr, *own_G0 = nullptr, *own_g0 = nullptr;
-  double *gains_tmp = nullptr, *kkt_tmp = nullptr;
+  double *gains_tmp = nullptr, *kkt_tmp = nullptr, *theta_dev = nullptr;
+  int nth = 0;
   double *out[AB2_OUT_COUNT] = {};
   size_t out_doubles[AB2_OUT_COUNT] = {};
   size_t out_rec[AB2_OUT_COUNT] = {};  // doubles per knot (or per instance)
@@ -134,6 +135,14 @@ size_t ab2_gar_stage_record_doubles(int nx, int nu, int nc) {
 size_t ab2_gar_term_record_doubles(int nx, int nct) {
   return (size_t)nx * nx + nx + (size_t)nct * nx + nct;
 }
+size_t ab2_gar_stage_record_doubles_th(int nx, int nu, int nc, int nth) {
+  size_t n = 2 * (size_t)nx * nx + 2 * (size_t)nx * nu + (size_t)nu * nu + 2 * (size_t)nx + nu +
+             (size_t)nc * (nx + nu + 1) + (size_t)nth * (nx + nu + nc + nth + 1);
+  return (n + 1) & ~(size_t)1;
+}
+size_t ab2_gar_term_record_doubles_th(int nx, int nct, int nth) {
+  return ab2_gar_term_record_doubles(nx, nct) + (size_t)nth * (nx + nct + nth + 1);
+}
 int ab2_gar_supported(int nx, int nu, int nc, int nc0) {
   if (nx < 1 || nu < 1 || nc < 0 || nc0 < 0)
     return 0;
@@ -143,18 +152,20 @@ int ab2_gar_supported(int nx, int nu, int nc, int nc0) {
   return ab2::block_supported(nx, nu, nc, nc0) ? 2 : 0; // run-time shape, one CTA per instance
 }
 
-int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
+int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) { return ab2_gar_create_parametric(dims, 0, out); }
+
+int ab2_gar_create_parametric(const ab2_gar_dims *dims, int nth, ab2_gar_solver **out) {
   if (!dims || !out)
     return fail(AB2_ERR_INVALID, "null argument");
   const ab2_gar_dims &d = *dims;
-  if (d.nx < 1 || d.nu < 1 || d.nc < 0 || d.nct < 0 || d.nc0 < 0 || d.horizon < 0 || d.batch < 1)
+  if (d.nx < 1 || d.nu < 1 || d.nc < 0 || d.nct < 0 || d.nc0 < 0 || d.horizon < 0 || d.batch < 1 || nth < 0)
     return fail(AB2_ERR_INVALID, "bad dimensions");
   // compile-time shapes run one warp (or part of one) per instance; every other shape runs
   // the CTA-per-instance kernel with run-time dimensions (block_kernel.cu)
   const ab2::KernelEntry *k = ab2::find_kernel(d.nx, d.nu, d.nc);
-  if (k && d.nx + d.nc0 > k->G)
-    k = nullptr;
-  if (!k && !ab2::block_supported(d.nx, d.nu, d.nc, d.nc0))
+  if (k && (d.nx + d.nc0 > k->G || nth > 0))
+    k = nullptr; // parametric problems run the CTA-per-instance kernel
+  if (!k && !ab2::block_supported(d.nx, d.nu, d.nc, d.nc0, nth))
     return fail(AB2_ERR_UNSUPPORTED,
                 "(nx,nu,nc,nc0) = (" + std::to_string(d.nx) + "," + std::to_string(d.nu) + "," +
                     std::to_string(d.nc) + "," + std::to_string(d.nc0) +
@@ -167,12 +178,13 @@ int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
   auto *s = new ab2_gar_solver();
   s->d = d;
   s->k = k;
-  s->srec = (int)ab2_gar_stage_record_doubles(d.nx, d.nu, d.nc);
+  s->nth = nth;
+  s->srec = (int)ab2_gar_stage_record_doubles_th(d.nx, d.nu, d.nc, nth);
   if (k && k->srec_pad != s->srec) {
     delete s;
     return fail(AB2_ERR_INVALID, "internal: record size mismatch");
   }
-  s->trec = (int)ab2_gar_term_record_doubles(d.nx, d.nct);
+  s->trec = (int)ab2_gar_term_record_doubles_th(d.nx, d.nct, nth);
   s->nr = d.nu + d.nc + d.nx;
   if (k)
     k->group_doubles(d.nc0, s->group_doubles);
@@ -195,6 +207,13 @@ int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
   setup(AB2_OUT_VST, d.nct, 1);
   setup(AB2_OUT_LBD0, d.nc0, 1);
   setup(AB2_OUT_LBDAS, nx, N);
+  setup(AB2_OUT_FTH, (size_t)s->nr * nth, N);
+  setup(AB2_OUT_VXT, (size_t)nx * nth, N + 1);
+  setup(AB2_OUT_VTT, (size_t)nth * nth, N + 1);
+  setup(AB2_OUT_VT, nth, N + 1);
+  setup(AB2_OUT_KKT0FTH, (size_t)(nx + d.nc0) * nth, 1);
+  setup(AB2_OUT_THGRAD, nth, 1);
+  setup(AB2_OUT_THHESS, (size_t)nth * nth, 1);
   for (int w = 0; w < AB2_OUT_COUNT; ++w) {
     // (+2: the forward pass of the CTA-per-instance kernel fetches odd-sized gain records
     // with 16-byte granularity, up to one double past the end of the array)
@@ -236,6 +255,15 @@ int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) {
   p.lbd0 = s->out[AB2_OUT_LBD0];
   p.lbdas = s->out[AB2_OUT_LBDAS];
   p.status = s->status;
+  p.nth = nth;
+  p.theta = nullptr;
+  p.fth = s->out[AB2_OUT_FTH];
+  p.Vxt = s->out[AB2_OUT_VXT];
+  p.Vtt = s->out[AB2_OUT_VTT];
+  p.vt = s->out[AB2_OUT_VT];
+  p.kkt0fth = s->out[AB2_OUT_KKT0FTH];
+  p.thGrad = s->out[AB2_OUT_THGRAD];
+  p.thHess = s->out[AB2_OUT_THHESS];
   {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device);
@@ -254,7 +282,7 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
       cudaFree(s->out[w]);
   if (s->status)
     cudaFree(s->status);
-  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp})
+  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev})
     if (q)
       cudaFree(q);
   for (int i = 0; i < ab2_gar_solver::kPipeStreams; ++i) {
@@ -356,6 +384,17 @@ static ab2::SweepParams slice_params(const ab2_gar_solver *s, int b0, int nb) {
   q.lbd0 += b * s->out_rec[AB2_OUT_LBD0];
   q.lbdas += b * s->out_knots[AB2_OUT_LBDAS] * s->out_rec[AB2_OUT_LBDAS];
   q.status += b;
+  if (s->nth > 0) {
+    q.fth += b * s->out_knots[AB2_OUT_FTH] * s->out_rec[AB2_OUT_FTH];
+    q.Vxt += b * s->out_knots[AB2_OUT_VXT] * s->out_rec[AB2_OUT_VXT];
+    q.Vtt += b * s->out_knots[AB2_OUT_VTT] * s->out_rec[AB2_OUT_VTT];
+    q.vt += b * s->out_knots[AB2_OUT_VT] * s->out_rec[AB2_OUT_VT];
+    q.kkt0fth += b * s->out_rec[AB2_OUT_KKT0FTH];
+    q.thGrad += b * s->out_rec[AB2_OUT_THGRAD];
+    q.thHess += b * s->out_rec[AB2_OUT_THHESS];
+    if (q.theta)
+      q.theta += b * s->nth;
+  }
   return q;
 }
 
@@ -385,10 +424,34 @@ static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream
 int ab2_gar_backward(ab2_gar_solver *s, double mueq, void *stream) { return launch(s, mueq, 1, 0, stream); }
 int ab2_gar_forward(ab2_gar_solver *s, void *stream) { return launch(s, s ? s->p.mueq : 0.0, 0, 1, stream); }
 int ab2_gar_sweep(ab2_gar_solver *s, double mueq, void *stream) { return launch(s, mueq, 1, 1, stream); }
+int ab2_gar_forward_theta(ab2_gar_solver *s, const double *theta, int memspace, void *stream) {
+  if (!s)
+    return fail(AB2_ERR_INVALID, "null solver");
+  if (theta && s->nth == 0)
+    return fail(AB2_ERR_INVALID, "theta given to a solver without parameters (nth = 0)");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  s->p.theta = nullptr;
+  if (theta) {
+    if (memspace == AB2_DEVICE) {
+      s->p.theta = theta;
+    } else {
+      if (!s->theta_dev)
+        CUDA_TRY(cudaMalloc(&s->theta_dev, (size_t)s->d.batch * s->nth * sizeof(double)));
+      CUDA_TRY(cudaMemcpyAsync(s->theta_dev, theta, (size_t)s->d.batch * s->nth * sizeof(double),
+                               cudaMemcpyHostToDevice, (cudaStream_t)stream));
+      s->p.theta = s->theta_dev;
+    }
+  }
+  const int rc = launch(s, s->p.mueq, 0, 1, stream);
+  s->p.theta = nullptr;
+  return rc;
+}
 
 int ab2_gar_assemble(ab2_gar_solver *s, const ab2_lq_inputs *in, void *stream) {
   if (!s || !in)
     return fail(AB2_ERR_INVALID, "null argument");
+  if (s->nth > 0)
+    return fail(AB2_ERR_UNSUPPORTED, "assemble: parametric problems (nth > 0) are not supported");
   const ab2_gar_dims &d = s->d;
   const bool stage_ok = d.horizon == 0 || (in->Jx && in->Ju && in->slack && in->Lxx && in->Lxu && in->Luu &&
                                            in->Lx && in->Lu);
@@ -621,6 +684,8 @@ int ab2_gar_kkt_error(ab2_gar_solver *s, double mueq, double *dst, int memspace,
     return fail(AB2_ERR_INVALID, "bad argument");
   if (!s->have_problem || !s->have_backward)
     return fail(AB2_ERR_STATE, "kkt_error needs a problem and a completed sweep");
+  if (s->nth > 0)
+    return fail(AB2_ERR_UNSUPPORTED, "kkt_error: parametric problems (nth > 0) are not supported");
   CUDA_TRY(cudaSetDevice(s->d.device));
   if (!s->kkt_tmp)
     CUDA_TRY(cudaMalloc(&s->kkt_tmp, (size_t)s->d.batch * 3 * sizeof(double)));
@@ -677,6 +742,8 @@ int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace
   const int N = s->d.horizon, B = s->d.batch;
   if (N < 1)
     return fail(AB2_ERR_INVALID, "cycle_append needs horizon >= 1");
+  if (s->nth > 0)
+    return fail(AB2_ERR_UNSUPPORTED, "cycle_append: parametric problems (nth > 0) are not supported");
   CUDA_TRY(cudaSetDevice(s->d.device));
   cudaStream_t st = (cudaStream_t)stream;
   // factors: datas[0..N-1] rotate left, datas[N-1] re-created (zeros), terminal kept

@@ -29,6 +29,9 @@ struct BlockDims {
   int vs, vrows, sw, wrows, sh, sx, xrows;
   int s_rec, s_vn, s_vxn, s_w, s_x, s_kk, s_y, s_h, s_kkt, s_dd, s_sd, s_int, s_end; // doubles
   int fwd_ring, fwd_slot, slack;
+  // parametric terms (nth > 0): record offsets [Gx | Gu | Gv | Gth | gamma] and the theta workspace
+  int nth, off_gx, off_gu, off_gv, off_gth, off_gam;
+  int s_th; // start of the theta workspace (behind everything else, incl. the initial-stage overlay)
 };
 
 AB2_HD constexpr int blk_ev(int x) { return (x + 1) & ~1; }
@@ -46,8 +49,9 @@ AB2_HD constexpr int blk_s8(int n) { // smallest stride >= n that is 8 mod 16
 }
 
 // Layout shared by the host (sizing the launch) and the device.
-AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0) {
+AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0, int nth = 0) {
   BlockDims d{};
+  d.nth = nth;
   d.nx = nx;
   d.nu = nu;
   d.nc = nc;
@@ -70,8 +74,14 @@ AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0) {
   d.off_c = d.off_rv + nu;
   d.off_d = d.off_c + nc * nx;
   d.off_dv = d.off_d + nc * nu;
-  d.srec_pad = blk_ev(d.off_dv + nc);
-  d.split = (d.off_q % 2 == 0) ? d.off_q : d.srec_pad;
+  d.off_gx = d.off_dv + nc;
+  d.off_gu = d.off_gx + nx * nth;
+  d.off_gv = d.off_gu + nu * nth;
+  d.off_gth = d.off_gv + nc * nth;
+  d.off_gam = d.off_gth + nth * nth;
+  d.srec_pad = blk_ev(d.off_gam + nth);
+  // (parametric knots read [Gx .. gamma] at the end of the step: no early refill of the tail)
+  d.split = (d.off_q % 2 == 0 && nth == 0) ? d.off_q : d.srec_pad;
   d.vs = blk_fstride(4 * d.kt);
   d.vrows = 8 * d.mtx;
   d.sw = blk_s8(d.njp);
@@ -113,6 +123,12 @@ AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0) {
   const int n0 = nx + nc0;
   const int k0 = n0 * n0 + 6 * n0 + 2;
   d.s_end = blk_ev(o > k0 ? o : k0);
+  d.s_th = d.s_end;
+  if (nth > 0) { // see ThetaWork below
+    const int nk = nu + nc;
+    d.s_end += blk_ev(2 * nx * nth) + blk_ev(2 * nth * nth) + blk_ev(2 * nth) + blk_ev(nx * nx) + blk_ev(nx) +
+               blk_ev(nx * nth) + blk_ev(nu * nth) + 3 * blk_ev((nk > n0 ? nk : n0) * nth) + blk_ev(nx * nth);
+  }
   // forward: ring of fb records + two state vectors
   d.fwd_slot = blk_ev(d.nr * nx) + 2; // an odd-sized record is fetched from the aligned double before it
   int ring = (d.s_end - 2 * blk_ev(nx)) / d.fwd_slot;
@@ -134,7 +150,8 @@ template <int NX, int NU, int NC, int NC0> struct StaticBlockDims {
   AB2_SD(off_rv) AB2_SD(off_c) AB2_SD(off_d) AB2_SD(off_dv) AB2_SD(srec_pad) AB2_SD(split) AB2_SD(vs) AB2_SD(vrows)
   AB2_SD(sw) AB2_SD(wrows) AB2_SD(sh) AB2_SD(sx) AB2_SD(xrows) AB2_SD(s_rec) AB2_SD(s_vn) AB2_SD(s_vxn) AB2_SD(s_w)
   AB2_SD(s_x) AB2_SD(s_kk) AB2_SD(s_y) AB2_SD(s_h) AB2_SD(s_kkt) AB2_SD(s_dd) AB2_SD(s_sd) AB2_SD(s_int) AB2_SD(s_end)
-  AB2_SD(fwd_ring) AB2_SD(fwd_slot) AB2_SD(slack)
+  AB2_SD(fwd_ring) AB2_SD(fwd_slot) AB2_SD(slack) AB2_SD(nth) AB2_SD(off_gx) AB2_SD(off_gu) AB2_SD(off_gv)
+  AB2_SD(off_gth) AB2_SD(off_gam) AB2_SD(s_th)
 #undef AB2_SD
 };
 
@@ -328,6 +345,26 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
   double *vx_b = p.vx + (size_t)inst * (N + 1) * nx;
   const int bk_threads = 32 * ((nk + 31) / 32); // warps that own rows of the KKT matrix
   CtaAsGroup<Ctx> grp{ctx, tid, bk_threads};
+  // ---- parametric terms (nth > 0): workspace behind everything else ----
+  const int nth = d.nth;
+  double *th = sm + d.s_th;
+  double *vxt2 = th;                                  // [2][nx*nth]  Vxt' (current / next), column-major
+  double *vtt2 = vxt2 + blk_ev(2 * nx * nth);         // [2][nth*nth]
+  double *vtv2 = vtt2 + blk_ev(2 * nth * nth);        // [2][nth]
+  double *ahat = vtv2 + blk_ev(2 * nth);              // Ahat row-major [c*nx + i] (closed-loop rows)
+  double *aff = ahat + blk_ev(nx * nx);               // a (closed-loop feedforward rows)
+  double *gxh = aff + blk_ev(nx);                     // Gxhat nx x nth column-major
+  double *guh = gxh + blk_ev(nx * nth);               // Guhat nu x nth column-major
+  const int thn = (nk > nx + nc0 ? nk : nx + nc0) * nth;
+  double *trhs = guh + blk_ev(nu * nth);              // right-hand sides [row][nth]
+  double *twork = trhs + blk_ev(thn);
+  double *tsol = twork + blk_ev(thn);
+  double *yth = tsol + blk_ev(thn);                   // Yth nx x nth row-major
+  int thcur = 0;                                      // which half of vxt2 / vtt2 / vtv2 holds V'
+  double *fth_b = nth ? p.fth + (size_t)inst * N * nr * nth : nullptr;
+  double *Vxt_b = nth ? p.Vxt + (size_t)inst * (N + 1) * nx * nth : nullptr;
+  double *Vtt_b = nth ? p.Vtt + (size_t)inst * (N + 1) * nth * nth : nullptr;
+  double *vt_b = nth ? p.vt + (size_t)inst * (N + 1) * nth : nullptr;
   const bool two_parts = d.split < d.srec_pad;
 
   if (p.do_bwd) {
@@ -349,7 +386,8 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
     // ---------------- terminal knot (nu = 0): riccati-kernel.hxx:146-149,175-183
     {
       const int trec = nx * nx + nx + nct * nx + nct;
-      const double *tr = p.term + (size_t)inst * trec;
+      const int trec_th = trec + nx * nth + nct * nth + nth * nth + nth; // + [Gx | Gv | Gth | gamma]
+      const double *tr = p.term + (size_t)inst * trec_th;
       const double *Qt = tr, *qt = tr + nx * nx, *Ct = qt + nx, *dt = Ct + (size_t)nct * nx;
       double *VN = Vxx_b + (size_t)N * nx * nx;
       for (int m = tid; m < nct * nx; m += T) { // Z = C / mu (stored row-major nct x nx)
@@ -382,6 +420,22 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       if (N > 0) // symmetrised by the step N-1 of the reference (A1)
         for (int e = tid; e < nx * nx; e += T)
           VN[(e % nx) + (e / nx) * nx] = Vn[(e / nx) * d.vs + (e % nx)];
+      if (nth > 0) { // nu = 0: Vxt = Gx, Vtt = Gth, vt = gamma (:185-192); Zth = 0 (:146-149)
+        const double *Gx = tr + trec, *Gth = Gx + nx * nth + nct * nth, *gam = Gth + nth * nth;
+        for (int e = tid; e < nx * nth; e += T) {
+          vxt2[e] = Gx[e];
+          Vxt_b[(size_t)N * nx * nth + e] = Gx[e];
+        }
+        for (int e = tid; e < nth * nth; e += T) {
+          vtt2[e] = Gth[e];
+          Vtt_b[(size_t)N * nth * nth + e] = Gth[e];
+        }
+        for (int e = tid; e < nth; e += T) {
+          vtv2[e] = gam[e];
+          vt_b[(size_t)N * nth + e] = gam[e];
+        }
+        ctx.sync();
+      }
     }
 
     // ---------------- stage knots N-1 .. 0: riccati-kernel.hxx:210-277
@@ -580,6 +634,8 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
                 const int jj = 8 * (n0 + c) + 2 * q + e;
                 if (jj < nx) {
                   fbt[(nk + i) * nx + jj] = EA[c][e];
+                  if (nth > 0)
+                    ahat[i * nx + jj] = EA[c][e];
                   if (t == 0)
                     Vxx_b[i + jj * nx] = VV[c][e]; // datas[0].Vxx is left unsymmetrised (A1)
                   if (i >= jj) { // V' = lower triangle mirrored (:216 of the next step)
@@ -588,6 +644,8 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
                   }
                 } else if (jj == nx) {
                   fft[nk + i] = EA[c][e];
+                  if (nth > 0)
+                    aff[i] = EA[c][e];
                   vx_b[(size_t)t * nx + i] = VV[c][e];
                   vxn[i] = VV[c][e];
                 }
@@ -596,6 +654,83 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
         }
       }
       ctx.sync();
+      if (nth > 0) { // (8) parametric terms, riccati-kernel.hxx:278-311 -- plain thread-parallel loops
+        const double *Am = rec, *Bm = rec + d.off_b;
+        const double *Gx = rec + d.off_gx, *Gu = rec + d.off_gu, *Gv = rec + d.off_gv, *Gth = rec + d.off_gth,
+                     *gam = rec + d.off_gam;
+        const double *Vxtn = vxt2 + thcur * nx * nth, *Vttn = vtt2 + thcur * nth * nth, *vtn = vtv2 + thcur * nth;
+        double *Vxtc = vxt2 + (thcur ^ 1) * nx * nth, *Vttc = vtt2 + (thcur ^ 1) * nth * nth,
+               *vtc = vtv2 + (thcur ^ 1) * nth;
+        for (int e = tid; e < (nx + nu) * nth; e += T) { // Gxhat = Gx + A^T Vxt', Guhat = Gu + B^T Vxt'
+          const int j = e / (nx + nu), r = e % (nx + nu);
+          const bool isx = r < nx;
+          const int i = isx ? r : r - nx;
+          const double *Mc = isx ? Am + i * nx : Bm + i * nx; // column i of A / B
+          double acc = 0.0;
+          for (int c = 0; c < nx; ++c)
+            acc += Mc[c] * Vxtn[c + j * nx];
+          if (isx)
+            gxh[i + j * nx] = Gx[i + j * nx] + acc;
+          else
+            guh[i + j * nu] = Gu[i + j * nu] + acc;
+        }
+        ctx.sync();
+        for (int e = tid; e < nk * nth; e += T) { // right-hand sides [Guhat; Gv] (the solve negates)
+          const int r = e / nth, j = e % nth;
+          trhs[e] = (r < nu) ? guh[r + j * nu] : Gv[(r - nu) + j * nc];
+        }
+        ctx.sync();
+        if (tid < nth)
+          bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, trhs + tid, twork + tid, tsol + tid, nth);
+        ctx.sync();
+        double *ftt = fth_b + (size_t)t * nr * nth;
+        for (int e = tid; e < nk * nth; e += T) // fth rows [Kth; Zth]
+          ftt[e] = tsol[e];
+        for (int e = tid; e < nx * nth; e += T) { // Yth = B Kth
+          const int i = e / nth, j = e % nth;
+          double acc = 0.0;
+          for (int c = 0; c < nu; ++c)
+            acc += Bm[i + c * nx] * tsol[c * nth + j];
+          yth[e] = acc;
+          ftt[nk * nth + e] = acc;
+        }
+        for (int i = tid; i < nth; i += T) { // vt = (gamma + vt') + Gu^T k + Vxt'^T a
+          const double s0 = gam[i] + vtn[i];
+          double s1 = 0.0, s2 = 0.0;
+          for (int c = 0; c < nu; ++c)
+            s1 += Gu[c + i * nu] * KKs[c * d.sx + nx];
+          for (int c = 0; c < nx; ++c)
+            s2 += Vxtn[c + i * nx] * aff[c];
+          const double v = (s0 + s1) + s2;
+          vtc[i] = v;
+          vt_b[(size_t)t * nth + i] = v;
+        }
+        for (int e = tid; e < nx * nth; e += T) { // Vxt = (Gx + K^T Gu) + Ahat^T Vxt'
+          const int i = e % nx, j = e / nx;
+          double s1 = 0.0, s2 = 0.0;
+          for (int c = 0; c < nu; ++c)
+            s1 += KKs[c * d.sx + i] * Gu[c + j * nu];
+          for (int c = 0; c < nx; ++c)
+            s2 += ahat[c * nx + i] * Vxtn[c + j * nx];
+          const double v = (Gx[e] + s1) + s2;
+          Vxtc[e] = v;
+          Vxt_b[(size_t)t * nx * nth + e] = v;
+        }
+        ctx.sync(); // Yth complete
+        for (int e = tid; e < nth * nth; e += T) { // Vtt = ((Gth + Vtt') + Gu^T Kth) + Vxt'^T Yth
+          const int i = e % nth, j = e / nth;
+          double s1 = 0.0, s2 = 0.0;
+          for (int c = 0; c < nu; ++c)
+            s1 += Gu[c + i * nu] * tsol[c * nth + j];
+          for (int c = 0; c < nx; ++c)
+            s2 += Vxtn[c + i * nx] * yth[c * nth + j];
+          const double v = ((Gth[e] + Vttn[e]) + s1) + s2;
+          Vttc[e] = v;
+          Vtt_b[(size_t)t * nth * nth + e] = v;
+        }
+        thcur ^= 1;
+        ctx.sync();
+      }
       if (t > 0) {
         const double *src = stage_b + (size_t)(t - 1) * d.srec_pad;
         ctx.issue_copy(0, rec, src, d.split);
@@ -643,6 +778,33 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       for (int i = tid; i < n0; i += T)
         p.kkt0[(size_t)inst * n0 + i] = o0[i];
       ctx.sync();
+      if (nth > 0) { // fth = -K0^-1 [Vxt_0; 0], thGrad, thHess (proximal-riccati.hxx:50-59)
+        const double *Vxt0 = vxt2 + thcur * nx * nth, *Vtt0 = vtt2 + thcur * nth * nth, *vt0 = vtv2 + thcur * nth;
+        for (int e = tid; e < n0 * nth; e += T) {
+          const int r = e / nth, j = e % nth;
+          trhs[e] = (r < nx) ? Vxt0[r + j * nx] : 0.0;
+        }
+        ctx.sync();
+        if (tid < nth)
+          bk_solve_column_rt(K0, n0, dd0, sd0, perm0, kind0, trhs + tid, twork + tid, tsol + tid, nth);
+        ctx.sync();
+        for (int e = tid; e < n0 * nth; e += T)
+          p.kkt0fth[(size_t)inst * n0 * nth + e] = tsol[e];
+        for (int i = tid; i < nth; i += T) {
+          double acc = 0.0;
+          for (int c = 0; c < nx; ++c)
+            acc += Vxt0[c + i * nx] * o0[c];
+          p.thGrad[(size_t)inst * nth + i] = vt0[i] + acc;
+        }
+        for (int e = tid; e < nth * nth; e += T) {
+          const int i = e % nth, j = e / nth;
+          double acc = 0.0;
+          for (int c = 0; c < nx; ++c)
+            acc += Vxt0[c + i * nx] * tsol[c * nth + j];
+          p.thHess[(size_t)inst * nth * nth + e] = Vtt0[e] + acc;
+        }
+        ctx.sync();
+      }
     }
     if (tid == 0)
       p.status[inst] = st;
@@ -673,13 +835,32 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
     };
     for (int s_ = 0; s_ < RING && s_ < N; ++s_)
       fill_slot(s_, s_);
+    // theta terms of the rollout (riccati-kernel.hxx:196-207, 315-377): only when theta is given
+    const double *theta = (nth > 0 && p.theta) ? p.theta + (size_t)inst * nth : nullptr;
+    const double *f0th = theta ? p.kkt0fth + (size_t)inst * n0 * nth : nullptr;
+    const double *fthf = theta ? p.fth + (size_t)inst * N * nr * nth : nullptr;
+    const double *Vxtf = theta ? p.Vxt + (size_t)inst * (N + 1) * nx * nth : nullptr;
     for (int i = tid; i < nx; i += T) {
-      const double v = k0[i];
+      double v = k0[i];
+      if (theta) {
+        double acc = 0.0;
+        for (int c = 0; c < nth; ++c)
+          acc += f0th[i * nth + c] * theta[c];
+        v += acc;
+      }
       xc[i] = v;
       xs_b[i] = v;
     }
-    for (int m = tid; m < nc0; m += T)
-      p.lbd0[(size_t)inst * nc0 + m] = k0[nx + m];
+    for (int m = tid; m < nc0; m += T) {
+      double v = k0[nx + m];
+      if (theta) {
+        double acc = 0.0;
+        for (int c = 0; c < nth; ++c)
+          acc += f0th[(nx + m) * nth + c] * theta[c];
+        v += acc;
+      }
+      p.lbd0[(size_t)inst * nc0 + m] = v;
+    }
     // lbda_t = vx_t + Vxx_t x_t (t >= 1; Vxx_t symmetric: element (c, i) read as (i, c) keeps
     // the loads of neighbouring threads contiguous).  Runs on the warps pass 1 leaves idle.
     const int lam0 = 32 * ((nr + 31) / 32);
@@ -695,7 +876,14 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
         }
         if (c < nx)
           s0 += V[(size_t)c * nx + i] * x[c];
-        lb_b[(size_t)(tt - 1) * nx + i] = s0 + s1;
+        double lam = s0 + s1;
+        if (theta) {
+          double acc = 0.0;
+          for (int c2 = 0; c2 < nth; ++c2)
+            acc += Vxtf[(size_t)tt * nx * nth + i + c2 * nx] * theta[c2];
+          lam += acc;
+        }
+        lb_b[(size_t)(tt - 1) * nx + i] = lam;
       }
     };
     // Pass 1: x_{t+1} = a + Ahat x_t (and u, v): thread r owns gain row r (nr <= T).
@@ -715,7 +903,13 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
         }
         if (c < nx)
           s0 += slot[r * nx + c] * xc[c];
-        const double sv = s0 + s1;
+        double sv = s0 + s1;
+        if (theta) {
+          double acc = 0.0;
+          for (int c2 = 0; c2 < nth; ++c2)
+            acc += fthf[((size_t)t * nr + r) * nth + c2] * theta[c2];
+          sv += acc;
+        }
         if (r < nu)
           us_b[(size_t)t * nu + r] = sv;
         else if (r < nk)

@@ -8,9 +8,9 @@
 namespace ab2 {
 struct SweepParams;
 // threads per CTA for this shape (0 = a row count exceeds one CTA)
-int block_threads(int nx, int nu, int nc, int nc0);
-size_t block_smem_bytes(int nx, int nu, int nc, int nc0);
-bool block_supported(int nx, int nu, int nc, int nc0);
+int block_threads(int nx, int nu, int nc, int nc0, int nth = 0);
+size_t block_smem_bytes(int nx, int nu, int nc, int nc0, int nth = 0);
+bool block_supported(int nx, int nu, int nc, int nc0, int nth = 0);
 // info != nullptr: fill {threads, smem, threads, grid, regs, CTAs/SM} instead of launching
 cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st, int *info);
 } // namespace ab2

@@ -80,6 +80,16 @@ struct SweepParams {
   int stagger_ns;  // start-up delay per resident warp slot: de-phases the warps of an SM
   int num_sms;
   int ctas_per_sm; // host-side launch hint: resident CTAs per SM wanted (0 = whatever fits)
+  // parametric problems (nth > 0; CTA-per-instance kernel only): riccati-kernel.hxx:185-192, 278-311
+  int nth;
+  const double *theta; // [batch][nth] or null (forward)
+  double *fth;         // [batch][N][NR*nth]      row-major [Kth; Zth; Yth]
+  double *Vxt;         // [batch][N+1][NX*nth]    column-major
+  double *Vtt;         // [batch][N+1][nth*nth]
+  double *vt;          // [batch][N+1][nth]
+  double *kkt0fth;     // [batch][(NX+nc0)*nth]   row-major
+  double *thGrad;      // [batch][nth]
+  double *thHess;      // [batch][nth*nth]
 };
 
 // ---------------------------------------------------------------------------

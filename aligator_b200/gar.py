@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_PKG, "libaligator_b200_gar.so")
 
 AB2_HOST, AB2_DEVICE = 0, 1
 (OUT_FF, OUT_FB, OUT_VXX, OUT_VX, OUT_FFT, OUT_FBT, OUT_KKT0, OUT_XS, OUT_US, OUT_VS, OUT_VST,
- OUT_LBD0, OUT_LBDAS) = range(13)
+ OUT_LBD0, OUT_LBDAS, OUT_FTH, OUT_VXT, OUT_VTT, OUT_VT, OUT_KKT0FTH, OUT_THGRAD, OUT_THHESS) = range(20)
 
 _dp = C.POINTER(C.c_double)
 
@@ -73,6 +73,10 @@ def lib():
         L.ab2_gar_backward.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.ab2_gar_forward.argtypes = [C.c_void_p, C.c_void_p]
         L.ab2_gar_sweep.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.ab2_gar_create_parametric.argtypes = [C.POINTER(GarDims), C.c_int, C.POINTER(C.c_void_p)]
+        L.ab2_gar_stage_record_doubles_th.restype = C.c_size_t
+        L.ab2_gar_term_record_doubles_th.restype = C.c_size_t
+        L.ab2_gar_forward_theta.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_sweep_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_double, C.c_int, C.POINTER(C.c_int),
                                          C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
@@ -131,14 +135,15 @@ class CudaRiccatiBatch:
     identical dimensions (stage knots (nx,nu,nc), terminal knot (nx,0,nct))."""
 
     def __init__(self, nx, nu, nc, nct, nc0, horizon, batch, device=0, variant=-1, stagger_ns=0,
-                 ctas_per_sm=0):
+                 ctas_per_sm=0, nth=0):
         self.dims = GarDims(nx, nu, nc, nct, nc0, horizon, batch, device)
+        self.nth = int(nth)
         self.h = C.c_void_p()
-        _check(lib().ab2_gar_create(C.byref(self.dims), C.byref(self.h)))
+        _check(lib().ab2_gar_create_parametric(C.byref(self.dims), self.nth, C.byref(self.h)))
         if variant >= 0 or stagger_ns or ctas_per_sm:
             _check(lib().ab2_gar_set_tuning(self.h, C.byref(GarTuning(variant, stagger_ns, ctas_per_sm))))
-        self.srec = stage_record_doubles(nx, nu, nc)
-        self.trec = term_record_doubles(nx, nct)
+        self.srec = int(lib().ab2_gar_stage_record_doubles_th(nx, nu, nc, self.nth))
+        self.trec = int(lib().ab2_gar_term_record_doubles_th(nx, nct, self.nth))
         self._keep = None
 
     def close(self):
@@ -168,8 +173,16 @@ class CudaRiccatiBatch:
     def backward(self, mueq, stream=0):
         _check(lib().ab2_gar_backward(self.h, float(mueq), C.c_void_p(stream)))
 
-    def forward(self, stream=0):
-        _check(lib().ab2_gar_forward(self.h, C.c_void_p(stream)))
+    def forward(self, stream=0, theta=None):
+        """forward(); with ``theta`` ([batch][nth] host array) the parametric rollout."""
+        if theta is None:
+            _check(lib().ab2_gar_forward(self.h, C.c_void_p(stream)))
+        else:
+            th = np.ascontiguousarray(theta, dtype=np.float64)
+            assert th.size == self.dims.batch * self.nth
+            self._keep_theta = th
+            _check(lib().ab2_gar_forward_theta(self.h, _ptr(th), AB2_HOST, C.c_void_p(stream)))
+            self.synchronize(stream)
 
     def sweep(self, mueq, stream=0):
         _check(lib().ab2_gar_sweep(self.h, float(mueq), C.c_void_p(stream)))
@@ -200,7 +213,11 @@ class CudaRiccatiBatch:
             OUT_KKT0: (d.batch, d.nx + d.nc0), OUT_XS: (d.batch, d.horizon + 1, d.nx),
             OUT_US: (d.batch, d.horizon, d.nu), OUT_VS: (d.batch, d.horizon, d.nc),
             OUT_VST: (d.batch, d.nct), OUT_LBD0: (d.batch, d.nc0),
-            OUT_LBDAS: (d.batch, d.horizon, d.nx)}[what]
+            OUT_LBDAS: (d.batch, d.horizon, d.nx),
+            OUT_FTH: (d.batch, d.horizon, nr, self.nth), OUT_VXT: (d.batch, d.horizon + 1, self.nth, d.nx),
+            OUT_VTT: (d.batch, d.horizon + 1, self.nth, self.nth), OUT_VT: (d.batch, d.horizon + 1, self.nth),
+            OUT_KKT0FTH: (d.batch, d.nx + d.nc0, self.nth), OUT_THGRAD: (d.batch, self.nth),
+            OUT_THHESS: (d.batch, self.nth, self.nth)}[what]
 
     def get(self, what, out=None, stream=0, sync=True):
         """Copy an output array to the host.  VXX blocks are column-major in memory; the
@@ -214,8 +231,10 @@ class CudaRiccatiBatch:
             if sync:
                 self.synchronize(stream)
         a = buf[:n].reshape(shape)
-        if what == OUT_VXX:
+        if what in (OUT_VXX, OUT_VXT, OUT_VTT):  # column-major blocks -> [b, t, i, j]
             a = a.transpose(0, 1, 3, 2)
+        elif what == OUT_THHESS:
+            a = a.transpose(0, 2, 1)
         return a
 
     def get_into(self, what, dst, memspace, stream=0):
@@ -318,13 +337,18 @@ def _F(a):
 def pack_stage_knot(k, srec):
     rec = np.concatenate([_F(k.A), _F(k.B), _F(k.f), _F(k.Q), _F(k.S), _F(k.R), _F(k.q), _F(k.r),
                           _F(k.C), _F(k.D), _F(k.d)])
+    if k.nth:  # parametric blocks (gar/lqr-problem.hpp:66-71)
+        rec = np.concatenate([rec, _F(k.Gx), _F(k.Gu), _F(k.Gv), _F(k.Gth), _F(k.gamma)])
     if rec.size < srec:
         rec = np.concatenate([rec, np.zeros(srec - rec.size)])
     return rec
 
 
 def pack_term_knot(k):
-    return np.concatenate([_F(k.Q), _F(k.q), _F(k.C), _F(k.d)])
+    rec = np.concatenate([_F(k.Q), _F(k.q), _F(k.C), _F(k.d)])
+    if k.nth:
+        rec = np.concatenate([rec, _F(k.Gx), _F(k.Gv), _F(k.Gth), _F(k.gamma)])
+    return rec
 
 
 def pack_problems(problems):
@@ -335,14 +359,15 @@ def pack_problems(problems):
     kt = p0.stages[N]
     nx = kt.nx
     nu, nc = (k0.nu, k0.nc) if N > 0 else (1, 0)
-    srec = stage_record_doubles(nx, nu, nc)
+    nth = p0.ntheta
+    srec = int(lib().ab2_gar_stage_record_doubles_th(nx, nu, nc, nth))
     for p in problems:
         if p.horizon != N or p.nc0 != p0.nc0:
             raise GarError("all problems of a batch must share horizon and nc0")
         for t, s in enumerate(p.stages):
-            want = (nx, nu, nc, nx, 0) if t < N else (nx, 0, kt.nc, s.nx2, 0)
+            want = (nx, nu, nc, nx, nth) if t < N else (nx, 0, kt.nc, s.nx2, nth)
             if s.dims != want:
-                raise GarError("knot %d has dims %s, expected %s (uniform dims, terminal nu=0, nth=0)"
+                raise GarError("knot %d has dims %s, expected %s (uniform dims, terminal nu=0)"
                                % (t, s.dims, want))
     stage = np.empty((len(problems), N, srec))
     for b, p in enumerate(problems):
@@ -382,8 +407,7 @@ class ProximalRiccatiSolver:
             nu, nc = k0.nu, k0.nc
         else:
             nu, nc = 1, 0  # no stage knots: any instantiated shape serves
-        if p0.ntheta != 0:
-            raise GarError("parameterised problems (nth > 0) are not supported by the CUDA path")
+        self.nth = p0.ntheta  # parametric problems run the CTA-per-instance kernel
         self.nx, self.nu, self.nc, self.nct = kt.nx, nu, nc, kt.nc
         if N == 0:
             for cand in (2, 3, 1, 4, 6):
@@ -391,7 +415,7 @@ class ProximalRiccatiSolver:
                     self.nu = cand
                     break
         self.batch = CudaRiccatiBatch(self.nx, self.nu, self.nc, self.nct, p0.nc0, N,
-                                      len(self.problems), device, variant)
+                                      len(self.problems), device, variant, nth=self.nth)
         self._single = isinstance(problem, LqrProblem)
         self._cache = {}
 
@@ -410,8 +434,12 @@ class ProximalRiccatiSolver:
 
     def forward(self, xs, us, vs, lbdas, theta=None):
         if theta is not None:
-            raise GarError("theta is not supported (nth = 0 only)")
-        self.batch.forward()
+            if self.nth == 0:
+                raise GarError("theta given to a problem without parameters (nth = 0)")
+            th = np.asarray(theta, dtype=np.float64).reshape(len(self.problems), self.nth)
+            self.batch.forward(theta=th)
+        else:
+            self.batch.forward()
         B = self.batch
         N = B.dims.horizon
         X, U, V, VT = B.get(OUT_XS), B.get(OUT_US), B.get(OUT_VS), B.get(OUT_VST)
@@ -445,6 +473,15 @@ class ProximalRiccatiSolver:
         """fb = [K; Z; Ahat] of knot i, (nu+nc+nx) x nx; the terminal knot's is [Z]."""
         N = self.batch.dims.horizon
         return self._get(OUT_FBT)[b] if i == N else self._get(OUT_FB)[b, i]
+
+    def getFeedbackTheta(self, i, b=0):
+        """fth = [Kth; Zth; Yth] of stage knot i, (nu+nc+nx) x nth (StageFactor::fth)."""
+        return self._get(OUT_FTH)[b, i]
+
+    def kkt0(self, b=0):
+        """ff, fth of the initial stage and thGrad, thHess (proximal-riccati.hpp:40-43)."""
+        return dict(ff=self._get(OUT_KKT0)[b], fth=self._get(OUT_KKT0FTH)[b],
+                    thGrad=self._get(OUT_THGRAD)[b], thHess=self._get(OUT_THHESS)[b])
 
     def Vxx(self, i, b=0):
         return self._get(OUT_VXX)[b, i]

@@ -73,7 +73,15 @@ enum {
   AB2_OUT_VST = 10,
   AB2_OUT_LBD0 = 11,
   AB2_OUT_LBDAS = 12,
-  AB2_OUT_COUNT = 13
+  /* parametric problems (nth > 0), riccati-kernel.hpp:86-101, proximal-riccati.hpp:40-43 */
+  AB2_OUT_FTH = 13,     /* [batch][N][(nu+nc+nx)*nth]  row-major [Kth; Zth; Yth]      (StageFactor::fth) */
+  AB2_OUT_VXT = 14,     /* [batch][N+1][nx*nth]        column-major                   (vm.Vxt) */
+  AB2_OUT_VTT = 15,     /* [batch][N+1][nth*nth]                                      (vm.Vtt) */
+  AB2_OUT_VT = 16,      /* [batch][N+1][nth]                                          (vm.vt)  */
+  AB2_OUT_KKT0FTH = 17, /* [batch][(nx+nc0)*nth]       row-major                      (kkt0.fth) */
+  AB2_OUT_THGRAD = 18,  /* [batch][nth]                                               (thGrad) */
+  AB2_OUT_THHESS = 19,  /* [batch][nth*nth]            column-major                   (thHess) */
+  AB2_OUT_COUNT = 20
 };
 
 typedef struct ab2_gar_dims {
@@ -110,6 +118,17 @@ int ab2_gar_supported(int nx, int nu, int nc, int nc0);
 /* Replaces: ProximalRiccatiSolver(const LqrProblemTpl&), gar/proximal-riccati.hxx:13-31
  * (allocates all factor storage once; the hot calls below never allocate). */
 int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out);
+/* Parametric problems (LqrKnotTpl::Gth, Gx, Gu, Gv, gamma with nth > 0, gar/lqr-problem.hpp:66-71;
+ * what ParallelRiccatiSolver's legs solve).  Same as ab2_gar_create with `nth` parameters: stage
+ * records grow by [Gx nx*nth | Gu nu*nth | Gv nc*nth | Gth nth*nth | gamma nth], the terminal record
+ * by [Gx | Gv nct*nth | Gth | gamma] (ab2_gar_*_record_doubles_th); backward also produces
+ * AB2_OUT_FTH..THHESS; runs the CTA-per-instance kernel. */
+int ab2_gar_create_parametric(const ab2_gar_dims *dims, int nth, ab2_gar_solver **out);
+size_t ab2_gar_stage_record_doubles_th(int nx, int nu, int nc, int nth);
+size_t ab2_gar_term_record_doubles_th(int nx, int nct, int nth);
+/* forward(xs, us, vs, lbdas, theta) (riccati-base.hpp:21-24 with the optional theta): theta is
+ * [batch][nth] in host or device memory, NULL = no parameter (like std::nullopt). */
+int ab2_gar_forward_theta(ab2_gar_solver *s, const double *theta, int memspace, void *stream);
 int ab2_gar_destroy(ab2_gar_solver *s);
 int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t);
 

@@ -74,6 +74,14 @@ extern "C" int emu_block_sweep_static(int nx, int nu, int nc, int nwarps, const 
   return 1;
 }
 
+// parametric problems (nth > 0)
+extern "C" int emu_block_stage_record_th(int nx, int nu, int nc, int nth) {
+  return ab2::make_block_dims(nx, nu, nc, 0, nth).srec_pad;
+}
+extern "C" int emu_block_sweep_th(int nx, int nu, int nc, int nth, int nwarps, const ab2::SweepParams *pp) {
+  return run_block(ab2::make_block_dims(nx, nu, nc, pp->nc0, nth), nwarps, *pp);
+}
+
 extern "C" int emu_block_sweep(int nx, int nu, int nc, int nwarps, const ab2::SweepParams *pp) {
   return run_block(ab2::make_block_dims(nx, nu, nc, pp->nc0), nwarps, *pp);
 }
@@ -81,7 +89,7 @@ extern "C" int emu_block_sweep(int nx, int nu, int nc, int nwarps, const ab2::Sw
 template <class D> static int run_block(const D &d, int nwarps, const ab2::SweepParams &p) {
   const int nx = d.nx;
   const int T = 32 * nwarps;
-  if (nx + 1 > T || d.nk > T || nx + p.nc0 > T || d.nr > T)
+  if (nx + 1 > T || d.nk > T || nx + p.nc0 > T || d.nr > T || d.nth > T)
     return 2;
   for (int inst = 0; inst < p.batch; ++inst) {
     std::vector<double> sm((size_t)d.s_end, std::numeric_limits<double>::quiet_NaN());

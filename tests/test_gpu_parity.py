@@ -504,3 +504,76 @@ def test_kkt_error_of_every_instance_at_full_size(gar):
     assert e.shape == (B, 3) and np.all(np.isfinite(e))
     assert e.max() <= 1e-8, e.max()
     s.close()
+
+
+@pytest.mark.parametrize("shape", [(5, 2, 0, 0, 3, 6, 1e-8), (4, 3, 2, 0, 2, 5, 1e-3), (7, 3, 0, 2, 7, 4, 1e-2)])
+def test_parametric_problems(gar, shape):
+    """nth > 0 (riccati-kernel.hxx:185-192, 278-311; proximal-riccati.hxx:50-59; forward with theta)
+    through the Python mirror of ProximalRiccatiSolver, against the oracle."""
+    import test_block_parametric as tp
+    nx, nu, nc, nct, nth, N, mueq = shape
+    probs = [tp.make_problem(50 + b, N, nx, nu, nc, nct, nth) for b in range(3)]
+    solver = gar.ProximalRiccatiSolver(probs)
+    assert solver.backward(mueq)
+    thetas = np.random.default_rng(1).standard_normal((3, nth))
+    sols = [gar.lqr_initialize_solution(p) for p in probs] if hasattr(gar, "lqr_initialize_solution") else None
+    tol = 1e-9 if (nc or nct) else TOL
+    for b, p in enumerate(probs):
+        op = orc.OracleProblem(p)
+        ref = orc.ProximalRiccatiSolver(op)
+        assert ref.backward(mueq)
+        for t in range(N):
+            f = ref.factor(t)
+            assert gen.rel_fro(solver.getFeedback(t, b), f["fb"]) <= tol
+            assert gen.rel_fro(solver.getFeedbackTheta(t, b), f["fth"]) <= tol
+        k0 = ref.kkt0()
+        mine = solver.kkt0(b)
+        for key in ("ff", "fth", "thGrad", "thHess"):
+            assert gen.rel_fro(mine[key], k0[key]) <= tol, key
+        for t in range(N + 1):
+            f = ref.factor(t)
+            assert gen.rel_fro(solver._get(gar.OUT_VXT)[b, t], f["Vxt"]) <= tol
+            assert gen.rel_fro(solver._get(gar.OUT_VTT)[b, t], f["Vtt"]) <= tol
+            assert gen.rel_fro(solver._get(gar.OUT_VT)[b, t], f["vt"]) <= tol
+    # forward with theta
+    solver.batch.forward(theta=thetas)
+    X, U = solver.batch.get(gar.OUT_XS), solver.batch.get(gar.OUT_US)
+    L0, L = solver.batch.get(gar.OUT_LBD0), solver.batch.get(gar.OUT_LBDAS)
+    for b, p in enumerate(probs):
+        op = orc.OracleProblem(p)
+        ref = orc.ProximalRiccatiSolver(op)
+        ref.backward(mueq)
+        sol = orc.OracleSolution(op)
+        assert ref.forward(sol, thetas[b])
+        xs, us, vs, lb = sol.get()
+        assert gen.rel_fro(X[b], np.array(xs)) <= tol and gen.rel_fro(U[b], np.array(us[:N])) <= tol
+        assert gen.rel_fro(L0[b], lb[0]) <= tol and gen.rel_fro(L[b], np.array(lb[1:])) <= tol
+
+
+@pytest.mark.parametrize("shape", [(4, 2, 0, 0, 11, 3), (6, 3, 0, 0, 20, 4), (4, 2, 2, 0, 13, 2)])
+def test_parallel_solver_mirror_on_gpu(gar, shape):
+    """ParallelRiccatiSolver mirror (aligator_b200/parallel.py) with the CUDA leg back end: the legs are
+    parametric problems on the CTA-per-instance kernel, the condensed system is solved on the host;
+    the rollout equals the serial oracle solution."""
+    import copy
+    from aligator_b200 import parallel as par
+    nx, nu, nc, nct, N, J1 = shape
+    mueq = 1e-3 if nc else 1e-8
+    p = gen.generate_batch(77, 1, N, nx, nu, nc, nct)[0]
+    ops = orc.OracleProblem(copy.deepcopy(p))
+    ser = orc.ProximalRiccatiSolver(ops)
+    ser.backward(mueq)
+    sol = orc.OracleSolution(ops)
+    ser.forward(sol)
+    xs_s, us_s, vs_s, ls_s = sol.get()
+    mine = par.ParallelRiccatiSolver(p, J1, par.CudaLegBackend())
+    assert mine.backward(mueq)
+    xs = [np.zeros(nx) for _ in range(N + 1)]
+    us = [np.zeros(nu) for _ in range(N)]
+    vs = [np.zeros(nc) for _ in range(N)] + [np.zeros(nct)]
+    lb = [np.zeros(p.nc0)] + [np.zeros(nx) for _ in range(N)]
+    mine.forward(xs, us, vs, lb)
+    tol = 1e-7 if nc else 1e-8
+    assert gen.rel_fro(np.array(xs), np.array(xs_s)) <= tol
+    assert gen.rel_fro(np.array(us), np.array(us_s[:N])) <= tol
+    assert gen.rel_fro(np.array(lb[1:]), np.array(ls_s[1:])) <= tol

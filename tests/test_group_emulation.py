@@ -24,7 +24,8 @@ class SweepParams(C.Structure):
                [(n, _dp) for n in ("stage", "term", "G0", "g0", "ff", "fb", "Vxx", "vx", "ffT",
                                    "fbT", "kkt0", "xs", "us", "vs", "vsT", "lbd0", "lbdas")] + \
                [("status", C.POINTER(C.c_int)), ("stagger_ns", C.c_int), ("num_sms", C.c_int),
-                ("ctas_per_sm", C.c_int)]
+                ("ctas_per_sm", C.c_int), ("nth", C.c_int)] + \
+               [(n, _dp) for n in ("theta", "fth", "Vxt", "Vtt", "vt", "kkt0fth", "thGrad", "thHess")]
 
 
 def _lib():
