@@ -19,6 +19,8 @@ struct BlockDevCtx {
   // barrier over the first `nth` threads (whole warps) of the CTA: named barrier 1
   __device__ __forceinline__ void sync_sub(int nth) { asm volatile("bar.sync 1, %0;" ::"r"(nth) : "memory"); }
   __device__ __forceinline__ void wsync() { __syncwarp(); }
+  // generic-proxy writes of this thread (shared and global) ordered before later TMA accesses
+  __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
   __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
   __device__ __forceinline__ bool all(bool p) { return __all_sync(0xffffffffu, p); }
   __device__ __forceinline__ void mma(double (&d)[2], double a, double b) {

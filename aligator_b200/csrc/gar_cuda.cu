@@ -107,7 +107,7 @@ struct ab2_gar_solver {
   size_t out_rec[AB2_OUT_COUNT] = {};  // doubles per knot (or per instance)
   int out_knots[AB2_OUT_COUNT] = {};   // knots per instance (1 for per-instance arrays)
   int *status = nullptr;
-  bool have_problem = false, have_backward = false;
+  bool have_problem = false, have_backward = false, have_forward = false;
   long launches = 0;
   int variant = -1;
   int group_doubles[4] = {0, 0, 0, 0};
@@ -418,6 +418,7 @@ static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream
   s->launches += 1;
   if (bwd)
     s->have_backward = true;
+  s->have_forward = fwd != 0; // a backward-only launch invalidates the previous trajectory
   return AB2_OK;
 }
 
@@ -591,6 +592,7 @@ int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *ter
     CUDA_TRY(cudaStreamWaitEvent(user, s->pipe_done[i], 0));
   }
   s->have_backward = true;
+  s->have_forward = true;
   return AB2_OK;
 }
 
@@ -682,8 +684,8 @@ int ab2_gar_get_gains(ab2_gar_solver *s, double *dst, int memspace, void *stream
 int ab2_gar_kkt_error(ab2_gar_solver *s, double mueq, double *dst, int memspace, void *stream) {
   if (!s || !dst)
     return fail(AB2_ERR_INVALID, "bad argument");
-  if (!s->have_problem || !s->have_backward)
-    return fail(AB2_ERR_STATE, "kkt_error needs a problem and a completed sweep");
+  if (!s->have_problem || !s->have_backward || !s->have_forward)
+    return fail(AB2_ERR_STATE, "kkt_error needs a problem and a completed sweep (no forward pass since the last backward)");
   if (s->nth > 0)
     return fail(AB2_ERR_UNSUPPORTED, "kkt_error: parametric problems (nth > 0) are not supported");
   CUDA_TRY(cudaSetDevice(s->d.device));
@@ -771,6 +773,7 @@ int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace
   }
   CUDA_TRY(cudaGetLastError());
   s->have_backward = false;
+  s->have_forward = false;
   return AB2_OK;
 }
 

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256, 4)
 // Terminal knot (:785-795), initial condition (:797-800): a warp per instance.
 __global__ void __launch_bounds__(256)
     lq_assemble_term_kernel(const ab2_lq_inputs in, double *__restrict__ term, double *__restrict__ G0,
-                            double *__restrict__ g0, int batch, int nx, int nct, int nc0, int trec) {
+                            double *__restrict__ g0, int batch, int N, int nx, int nct, int nc0, int trec) {
   const int lane = threadIdx.x & 31;
   const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(256)
   for (long b = warp; b < batch; b += nwarps) {
     double *dst = term + b * trec;
     for (int e = lane; e < nxx; e += 32) // knot.Q = tcd.Lxx_; diag += preg
-      dst[e] = in.Lxx_N[b * nxx + e] + ((e % (nx + 1) == 0) ? in.preg : 0.0);
+      dst[e] = in.Lxx_N[b * nxx + e] + ((e % (nx + 1) == 0) ? in.preg : 0.0) +
+               ((N == 0 && in.Hxx0) ? in.Hxx0[b * nxx + e] : 0.0); // stages[0] is the terminal knot when N = 0 (:803-804)
     for (int j = lane; j < nx; j += 32) { // knot.q = Lxs[N] + cstr_lx_corr[N]
       double full = 0.0, proj = 0.0;
       for (int i = 0; i < nct; ++i) {
@@ -219,7 +220,7 @@ cudaError_t launch_lq_assemble(const ab2_lq_inputs &in, double *stage, double *t
   long grid = ((long)batch + 7) / 8;
   if (grid > full)
     grid = full;
-  lq_assemble_term_kernel<<<(int)grid, 256, 0, st>>>(in, term, G0, g0, batch, nx, nct, nc0, trec);
+  lq_assemble_term_kernel<<<(int)grid, 256, 0, st>>>(in, term, G0, g0, batch, N, nx, nct, nc0, trec);
   return cudaGetLastError();
 }
 

@@ -823,12 +823,18 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
     double *ring = sm;
     double *xc = sm + RING * FS;
     double *xnx = xc + blk_ev(nx);
+    // generic-proxy writes of the backward pass (fb in global memory, the initial-stage
+    // workspace in shared memory) ordered before the ring's bulk copies read / overwrite them
+    ctx.proxy_fence();
     ctx.sync();
     // fb record of knot t -> ring slot s by one TMA bulk copy.  A record that starts at an
     // odd double (odd-sized records) is fetched from the aligned double before it; the
     // record then sits one double into the slot.
     const size_t e_inst = (size_t)inst * N * R;
-    auto rec_shift = [&](int t) { return (int)((e_inst + (size_t)t * R) & 1); };
+    // (parity of the ABSOLUTE address: a batch slice may start at an odd double of the array)
+    auto rec_shift = [&](int t) {
+      return (int)((reinterpret_cast<uintptr_t>(p.fb + e_inst + (size_t)t * R) >> 3) & 1);
+    };
     auto fill_slot = [&](int s_, int t) {
       const int a = rec_shift(t);
       ctx.issue_copy(s_, ring + s_ * FS, p.fb + (e_inst + (size_t)t * R - a), blk_ev(R + a));

@@ -1593,6 +1593,8 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           }
         }
       }
+      if (STASH) // the stashed columns were written through the generic proxy into the record
+        ctx.proxy_fence_smem(); // buffer the next bulk copy overwrites (issued after the sync below)
       ctx.sync();
       if (t > 0 && colA) { // symmetric Vxx_t, as the next step of the reference leaves it
         double *Vt = Vxx_b + (size_t)t * NX * NX;
@@ -1675,6 +1677,11 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     double *xc = sm + RING * FS;       // x_t
     double *xnx = xc + C::NXE;         // x_{t+1}
     (void)xv;
+    // The ring's bulk copies overwrite shared memory this group wrote through the generic
+    // proxy (initial-stage workspace) and, in the fused sweep, read ff / fb / Vxx / vx this
+    // group stored to global memory during the backward pass: every lane orders its
+    // generic-proxy writes before the async proxy, then the group synchronises.
+    ctx.proxy_fence();
     ctx.sync();
     auto fill_slot = [&](int d, int t) { // fb record of knot t -> ring slot d
       if (FUSED) { // [K; Z; Ahat]_t | Vxx_t (symmetric for t >= 1: row i = column i) | vx_t

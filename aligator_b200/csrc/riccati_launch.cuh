@@ -53,9 +53,13 @@ template <int G, bool TMA> struct DevCtx {
       if (lane == 0) {
         const uint32_t bar = bar0 + 8 * part;
         const uint32_t bytes = (uint32_t)nd * 8u;
-        // No proxy fence: every refill targets a buffer whose last generic-proxy READS have
-        // completed (their values were consumed before the group synchronisation that
-        // precedes this call), and nothing was written to it through the generic proxy.
+        // Ordering against the generic proxy: a refill of a buffer that was only READ through
+        // the generic proxy needs no proxy fence (the reads completed before the group
+        // synchronisation that precedes this call -- the consumer-release pattern).  Every
+        // place where lanes WROTE through the generic proxy what a bulk copy later overwrites
+        // (stashed columns in the record buffer, the initial-stage workspace under the forward
+        // ring) or reads (ff / fb / Vxx / vx in global memory, re-read by the fused forward)
+        // executes proxy_fence() in the writing lanes before that synchronisation.
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                      : "memory");
         asm volatile(
@@ -102,6 +106,11 @@ template <int G, bool TMA> struct DevCtx {
   // Every lane that wrote (through the generic proxy) shared memory a bulk store will read
   // calls this BEFORE the group synchronisation that precedes bulk_store().
   __device__ __forceinline__ void async_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+  // Generic-proxy writes of this lane (shared AND global) ordered before later async-proxy
+  // (TMA) accesses: executed by every writing lane before the synchronisation that precedes
+  // the bulk copy which overwrites or reads what it wrote (PTX memory model, proxies).
+  __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
+  __device__ __forceinline__ void proxy_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
   // Shared -> global bulk store of `nd` doubles (TMA).  One lane issues.
   __device__ __forceinline__ void bulk_store(double *gdst, const double *ssrc, int nd) {
     if (lane == 0) {

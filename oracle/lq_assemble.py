@@ -78,8 +78,8 @@ def assemble_problem(inp, N, nx, nu, nc, nct, nc0):
         term["q"] += lx                                             # :794
     else:
         term["C"], term["d"] = np.zeros((0, nx)), np.zeros(0)
-    if N > 0 and inp.get("Hxx0") is not None:
-        stages[0]["Q"] += inp["Hxx0"]                               # :803-804
+    if inp.get("Hxx0") is not None:                                 # :803-804 (stages[0] is the terminal knot when N = 0)
+        (stages[0] if N > 0 else term)["Q"] += inp["Hxx0"]
     G0 = inp["G0"].copy() if nc0 else np.zeros((0, nx))             # :799-800
     g0 = inp["g0"].copy() if nc0 else np.zeros(0)
     return {"stages": stages, "term": term, "G0": G0, "g0": g0}

@@ -55,6 +55,7 @@ struct HostBlockCtx {
       std::memcpy(dst, src, sizeof(double) * (size_t)nd);
   }
   void wait_copy(int) { sync(); }
+  void proxy_fence() {}
 };
 } // namespace
 

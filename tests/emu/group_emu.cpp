@@ -49,6 +49,8 @@ struct HostCtx {
   }
   void bulk_store_wait_read() {}
   void async_fence() {}
+  void proxy_fence() {}
+  void proxy_fence_smem() {}
 };
 
 template <class C> int run(const ab2::SweepParams &p) {
