@@ -888,6 +888,25 @@ AB2_D void sts2(double *p, double x, double y) {
 #endif
 }
 
+// Per-CTA table of per-lane constants of the tensor-core step: lut[t][lane] = record offset of
+// logical column 8t+g; lut[NT + mt*NT + nt][lane] = packed record offsets of the two H0
+// entries of accumulator tile (mt, nt) (structural zeros point at the zero slot behind the
+// record).  Written by ONE warp of the CTA (or one host thread per lane) before any sweep.
+template <class C> AB2_HD void fill_mma_lut(int *lut, const int lane) {
+  constexpr int NT = C::NT;
+  const int g = lane >> 2, q = lane & 3;
+  for (int t = 0; t < NT; ++t)
+    lut[t * 32 + lane] = C::col_offset(8 * t + g);
+  for (int mt = 0; mt < NT; ++mt)
+    for (int nt = 0; nt < NT; ++nt) {
+      const int o0 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q);
+      const int o1 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q + 1);
+      const unsigned u0 = o0 < 0 ? (unsigned)C::SREC_PAD : (unsigned)o0; // structural zero -> the zero slot
+      const unsigned u1 = o1 < 0 ? (unsigned)C::SREC_PAD : (unsigned)o1;
+      lut[(NT + mt * NT + nt) * 32 + lane] = (int)(u0 | (u1 << 16));
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Stage knots N-1..0 on the FP64 tensor cores (mma.sync m8n8k4, SASS DMMA).
 //
@@ -933,24 +952,10 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
   double *KKs = sm + C::S_KK;
 
   // per-lane constants: record offsets of the logical columns 8t+g and of H0's entries.
-  // They live in a small per-CTA table in shared memory (identical for every warp of the
-  // CTA; each warp writes and reads only its own lanes' entries) instead of 12 registers
+  // They live in a small per-CTA table in shared memory, filled ONCE per CTA before the
+  // sweeps start (fill_mma_lut, called by the kernel prologue), instead of 12 registers
   // that would be spilled to local memory, which has no L1 behind it in this kernel.
-  int *lut = ctx.cta_ints(); // [(NT + NT*NT)][32]
-  AB2_UNROLL
-  for (int t = 0; t < NT; ++t)
-    lut[t * 32 + lane] = C::col_offset(8 * t + g);
-  AB2_UNROLL
-  for (int mt = 0; mt < NT; ++mt) {
-    AB2_UNROLL
-    for (int nt = 0; nt < NT; ++nt) {
-      const int o0 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q);
-      const int o1 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q + 1);
-      const unsigned u0 = o0 < 0 ? (unsigned)C::SREC_PAD : (unsigned)o0; // structural zero -> the zero slot
-      const unsigned u1 = o1 < 0 ? (unsigned)C::SREC_PAD : (unsigned)o1;
-      lut[(NT + mt * NT + nt) * 32 + lane] = (int)(u0 | (u1 << 16));
-    }
-  }
+  const int *lut = ctx.cta_ints(); // [(NT + NT*NT)][32]
   if (lane < (C::DB ? 4 : 2))
     sm[C::S_REC + (lane >> 1) * C::RSTRIDE + C::SREC_PAD + (lane & 1)] = 0.0;
   for (int i = lane; i < C::S_MMA_END - C::S_WSM; i += 32)

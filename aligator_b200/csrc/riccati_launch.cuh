@@ -160,6 +160,12 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
   const int gsub = lane32 / C::G;
   const int group_in_cta = warp * IPW + gsub;
   const int inst = blockIdx.x * (WARPS * IPW) + group_in_cta;
+  if constexpr (C::MMA) { // the per-CTA table of per-lane constants: one writer, then a CTA barrier
+    if (warp == 0)
+      fill_mma_lut<C>(reinterpret_cast<int *>(smem + (size_t)(WARPS * IPW) * group_doubles + (size_t)(WARPS * IPW) * NBAR),
+                      lane32);
+    __syncthreads();
+  }
   if (inst >= p.batch)
     return; // whole group leaves together
   double *sm = smem + (size_t)group_in_cta * group_doubles;

@@ -254,6 +254,58 @@ class ParallelRiccatiSolver(_FactorAccess):
             pass
 
 
+class RiccatiSolverDense:
+    """Oracle counterpart of gar::RiccatiSolverDense (dense-riccati.hxx, dense-kernel.hpp):
+    the reference's second, algorithmically independent solver of the same problem."""
+
+    def __init__(self, oprob):
+        self.oprob = oprob
+        lib().gar_oracle_dense_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib().gar_oracle_dense_create(oprob.h))
+
+    def backward(self, mueq):
+        return bool(lib().gar_oracle_dense_backward(self.h, C.c_double(mueq)))
+
+    def forward(self, osol, theta=None):
+        th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+        return bool(lib().gar_oracle_dense_forward(self.h, osol.h, _d(th) if th is not None else None))
+
+    def factor(self, t):
+        """ff = [k; z; l; y], fb = [K; Z; L; Y] (row-major), value function Pxx, px (+ parametric)."""
+        nx, nu, nc, nx2, nth = [int(v) for v in self.oprob.dims()[t]]
+        n = nu + nc + 2 * nx2
+
+        def g(field, cnt):
+            buf = np.zeros(max(cnt, 1))
+            got = lib().gar_oracle_dense_get(self.h, int(t), int(field), _d(buf))
+            assert got == cnt, (got, cnt, field)
+            return buf[:cnt]
+        return dict(ff=g(0, n), fb=g(1, n * nx).reshape(n, nx), ft=g(2, n * nth).reshape(n, nth),
+                    Pxx=g(3, nx * nx).reshape(nx, nx, order="F"), px=g(4, nx),
+                    Pxt=g(5, nx * nth).reshape(nx, nth, order="F"),
+                    Ptt=g(6, nth * nth).reshape(nth, nth, order="F"), pt=g(7, nth),
+                    dims=(nx, nu, nc, nx2, nth))
+
+    def kkt0(self):
+        nx, nth = int(self.oprob.dims()[0][0]), int(self.oprob.dims()[0][4])
+        n0 = nx + int(self.oprob.py.nc0)
+        ff = np.zeros(max(n0, 1))
+        lib().gar_oracle_dense_get_kkt0(self.h, 0, _d(ff))
+        out = dict(ff=ff[:n0])
+        if nth:
+            g = np.zeros(nth); H = np.zeros(nth * nth)
+            lib().gar_oracle_dense_get_kkt0(self.h, 3, _d(g))
+            lib().gar_oracle_dense_get_kkt0(self.h, 4, _d(H))
+            out.update(thGrad=g, thHess=H.reshape(nth, nth, order="F"))
+        return out
+
+    def __del__(self):
+        try:
+            lib().gar_oracle_dense_destroy(self.h)
+        except Exception:
+            pass
+
+
 def bk_compute(a):
     """Eigen::BunchKaufman<MatrixXd, Lower>::compute restated
     (core/bunchkaufman.hpp:654-676).  Returns (info, mat, subdiag, piv)."""

@@ -1,6 +1,7 @@
 // gar_oracle_capi.cpp -- extern "C" surface of the CPU oracle, for ctypes.
 // TEST INFRASTRUCTURE ONLY (see gar_oracle.hpp header).  Build: oracle/Makefile.
 #include "gar_oracle.hpp"
+#include "gar_oracle_dense.hpp"
 
 #include <chrono>
 #include <memory>
@@ -252,6 +253,48 @@ void gar_oracle_serial_cycle_append(void *sv, const int *dm,
   Knot k(dm[0], dm[1], dm[2], dm[3], dm[4]);
   load_knot(k, rec);
   ((ProximalRiccatiSolver *)sv)->cycleAppend(k);
+}
+
+// ---- stage-dense solver (gar/dense-riccati.hxx) --------------------------------
+void *gar_oracle_dense_create(void *pv) { return new RiccatiSolverDense(*(Problem *)pv); }
+void gar_oracle_dense_destroy(void *s) { delete (RiccatiSolverDense *)s; }
+int gar_oracle_dense_backward(void *s, double mueq) {
+  return ((RiccatiSolverDense *)s)->backward(mueq) ? 1 : 0;
+}
+int gar_oracle_dense_forward(void *s, void *hv, const double *theta) {
+  return ((RiccatiSolverDense *)s)->forward(((SolHolder *)hv)->s, theta) ? 1 : 0;
+}
+// field: 0 ff [k;z;l;y], 1 fb row-major [K;Z;L;Y], 2 ft, 3 Pxx, 4 px, 5 Pxt, 6 Ptt, 7 pt
+int gar_oracle_dense_get(void *sv, int t, int field, double *out) {
+  auto *s = (RiccatiSolverDense *)sv;
+  const vecd *src = nullptr;
+  switch (field) {
+  case 0: src = &s->stage_factors[t].ff; break;
+  case 1: src = &s->stage_factors[t].fb; break;
+  case 2: src = &s->stage_factors[t].ft; break;
+  case 3: src = &s->P[t].Pxx; break;
+  case 4: src = &s->P[t].px; break;
+  case 5: src = &s->P[t].Pxt; break;
+  case 6: src = &s->P[t].Ptt; break;
+  case 7: src = &s->P[t].pt; break;
+  default: return -1;
+  }
+  std::copy(src->begin(), src->end(), out);
+  return (int)src->size();
+}
+int gar_oracle_dense_get_kkt0(void *sv, int which, double *out) {
+  auto *s = (RiccatiSolverDense *)sv;
+  const vecd *src = nullptr;
+  switch (which) {
+  case 0: src = &s->kkt0.ff; break;
+  case 1: src = &s->kkt0.fth; break;
+  case 2: src = &s->kkt0.mat; break;
+  case 3: src = &s->thGrad; break;
+  case 4: src = &s->thHess; break;
+  default: return -1;
+  }
+  std::copy(src->begin(), src->end(), out);
+  return (int)src->size();
 }
 
 // ---- parallel solver ---------------------------------------------------------

@@ -63,6 +63,9 @@ template <class C> int run(const ab2::SweepParams &p) {
     std::barrier<> bar(G);
     std::vector<double> xa(G), xb(G);
     std::vector<int> lutv(C::LUT_INTS + 32);
+    if constexpr (C::MMA)
+      for (int l = 0; l < 32; ++l)
+        ab2::fill_mma_lut<C>(lutv.data(), l);
     std::vector<std::thread> th;
     for (int l = 0; l < G; ++l)
       th.emplace_back([&, l] {
