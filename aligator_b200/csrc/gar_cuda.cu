@@ -106,7 +106,7 @@ struct ab2_gar_solver {
   size_t out_doubles[AB2_OUT_COUNT] = {};
   size_t out_rec[AB2_OUT_COUNT] = {};  // doubles per knot (or per instance)
   int out_knots[AB2_OUT_COUNT] = {};   // knots per instance (1 for per-instance arrays)
-  int *status = nullptr;
+  int *status = nullptr, *pivstat = nullptr;
   bool have_problem = false, have_backward = false, have_forward = false;
   long launches = 0;
   int variant = -1;
@@ -235,6 +235,15 @@ int ab2_gar_create_parametric(const ab2_gar_dims *dims, int nth, ab2_gar_solver 
       return fail(AB2_ERR_CUDA, std::string("cudaMalloc status: ") + cudaGetErrorString(e));
     }
   }
+  {
+    cudaError_t e = cudaMalloc(&s->pivstat, sizeof(int) * B);
+    if (e == cudaSuccess)
+      e = cudaMemset(s->pivstat, 0, sizeof(int) * B);
+    if (e != cudaSuccess) {
+      ab2_gar_destroy(s);
+      return fail(AB2_ERR_CUDA, std::string("cudaMalloc pivstat: ") + cudaGetErrorString(e));
+    }
+  }
   ab2::SweepParams &p = s->p;
   std::memset(&p, 0, sizeof(p));
   p.N = N;
@@ -255,6 +264,7 @@ int ab2_gar_create_parametric(const ab2_gar_dims *dims, int nth, ab2_gar_solver 
   p.lbd0 = s->out[AB2_OUT_LBD0];
   p.lbdas = s->out[AB2_OUT_LBDAS];
   p.status = s->status;
+  p.pivstat = s->pivstat;
   p.nth = nth;
   p.theta = nullptr;
   p.fth = s->out[AB2_OUT_FTH];
@@ -282,6 +292,8 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
       cudaFree(s->out[w]);
   if (s->status)
     cudaFree(s->status);
+  if (s->pivstat)
+    cudaFree(s->pivstat);
   for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev})
     if (q)
       cudaFree(q);
@@ -384,6 +396,7 @@ static ab2::SweepParams slice_params(const ab2_gar_solver *s, int b0, int nb) {
   q.lbd0 += b * s->out_rec[AB2_OUT_LBD0];
   q.lbdas += b * s->out_knots[AB2_OUT_LBDAS] * s->out_rec[AB2_OUT_LBDAS];
   q.status += b;
+  q.pivstat += b;
   if (s->nth > 0) {
     q.fth += b * s->out_knots[AB2_OUT_FTH] * s->out_rec[AB2_OUT_FTH];
     q.Vxt += b * s->out_knots[AB2_OUT_VXT] * s->out_rec[AB2_OUT_VXT];
@@ -733,6 +746,18 @@ int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream) {
     return fail(AB2_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(s->d.device));
   CUDA_TRY(cudaMemcpyAsync(dst, s->status, sizeof(int) * s->d.batch,
+                           memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+  return AB2_OK;
+}
+
+int ab2_gar_pivot_stats(ab2_gar_solver *s, int *dst, int memspace, void *stream) {
+  if (!s || !dst)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  if (!s->have_backward)
+    return fail(AB2_ERR_STATE, "pivot_stats before backward()");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  CUDA_TRY(cudaMemcpyAsync(dst, s->pivstat, sizeof(int) * s->d.batch,
                            memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                            (cudaStream_t)stream));
   return AB2_OK;

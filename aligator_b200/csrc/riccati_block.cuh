@@ -369,6 +369,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
 
   if (p.do_bwd) {
     int st = ST_OK;
+    int pv = 0; // pivot statistics (threads 0..bk_threads-1 all see the same decisions)
     if (N > 0) {
       const double *src = stage_b + (size_t)(N - 1) * d.srec_pad;
       ctx.issue_copy(0, rec, src, d.split);
@@ -573,7 +574,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
             for (int e = lane; e < nk * nk; e += 32)
               kkt[e] = Ys[e];
         }
-        if (!done && !bk_factor_group<16>(grp, kkt, nk, nk, dd, sd, perm, kind))
+        if (!done && !bk_factor_group<16>(grp, kkt, nk, nk, dd, sd, perm, kind, pv))
           st |= ST_STAGE_FACTOR_FAILED;
       }
       ctx.sync();
@@ -770,7 +771,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       ctx.sync();
       CtaAsGroup<Ctx> grp0{ctx, tid, 32 * ((n0 + 31) / 32)};
       if (tid < grp0.nthreads) {
-        if (!bk_factor_group<8>(grp0, K0, n0, n0, dd0, sd0, perm0, kind0))
+        if (!bk_factor_group<8>(grp0, K0, n0, n0, dd0, sd0, perm0, kind0, pv))
           st |= ST_INIT_FACTOR_FAILED;
         bk_solve_vec_group(grp0, K0, n0, n0, dd0, sd0, perm0, kind0, b0, x0w, o0);
       }
@@ -806,8 +807,11 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
         ctx.sync();
       }
     }
-    if (tid == 0)
+    if (tid == 0) {
       p.status[inst] = st;
+      if (p.pivstat)
+        p.pivstat[inst] = pv;
+    }
   }
 
   // ---------------- forward rollout: riccati-kernel.hxx:196-207, 315-377

@@ -76,6 +76,7 @@ struct SweepParams {
   double *lbd0;  // [batch][nc0]
   double *lbdas; // [batch][N][NX]         lbda_1..lbda_N
   int *status;   // [batch]
+  int *pivstat;  // [batch] or null: low 16 bits = 2x2 pivots, high 16 = interchanges (stage + initial factorisations)
   // launch tuning (device only; 0 = off)
   int stagger_ns;  // start-up delay per resident warp slot: de-phases the warps of an SM
   int num_sms;
@@ -320,7 +321,7 @@ template <int N, bool ALIGNED> AB2_D double dot_bcast(const double *row, const d
 // the CTA-per-instance kernel, whose matrices are large.
 template <int CHUNK = 1, class Ctx>
 AB2_D bool bk_factor_group(Ctx &ctx, double *a, const int lda, const int n,
-                            double *dd, double *sd, int *perm, int *kind) {
+                            double *dd, double *sd, int *perm, int *kind, int &pv) {
   const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
   const int lane = ctx.lane;
 #define A_(i, j) a[(i) + (j) * lda]
@@ -390,6 +391,7 @@ AB2_D bool bk_factor_group(Ctx &ctx, double *a, const int lda, const int n,
       }
     }
     const int kk = k + kstep - 1;
+    pv += (kstep == 2 ? 1 : 0) + (kp != kk ? 0x10000 : 0); // pivot statistics (ab2_gar_pivot_stats)
     if (kp != kk) { // ---- symmetric interchange kk <-> kp, whole rows ----
       ctx.sync();   // everyone finished reading before anyone writes
       const int i = lane;
@@ -703,7 +705,7 @@ template <int N> struct RegFactor {
 
   // one elimination step with a COMPILE-TIME column index (so that every register
   // index stays static even if the compiler declines to unroll a large loop body)
-  template <int K> AB2_D void step(bool &ok, bool &skip, bool &dead) {
+  template <int K> AB2_D void step(bool &ok, bool &skip, bool &dead, int &pv) {
     constexpr int k = K;
     const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
     if (skip || dead) {
@@ -757,6 +759,7 @@ template <int N> struct RegFactor {
       }
     }
     constexpr int k1 = (k + 1 < N) ? k + 1 : k;
+    pv += (kstep == 2 ? 1 : 0) + (kp != k + kstep - 1 ? 0x10000 : 0); // pivot statistics
     if (kstep == 1) {
       if (kp != k) {
         AB2_UNROLL
@@ -810,11 +813,12 @@ template <int N> struct RegFactor {
       skip = true;
     }
   }
-  template <int... Ks> AB2_D void steps(bool &ok, bool &skip, bool &dead, std::integer_sequence<int, Ks...>) {
-    (step<Ks>(ok, skip, dead), ...);
+  template <int... Ks>
+  AB2_D void steps(bool &ok, bool &skip, bool &dead, int &pv, std::integer_sequence<int, Ks...>) {
+    (step<Ks>(ok, skip, dead, pv), ...);
   }
 
-  AB2_D bool factor() {
+  AB2_D bool factor(int &pv) {
     bool ok = true, skip = false, dead = false;
     AB2_UNROLL
     for (int i = 0; i < N; ++i) {
@@ -823,7 +827,7 @@ template <int N> struct RegFactor {
       d[i] = 0.0;
       s[i] = 0.0;
     }
-    steps(ok, skip, dead, std::make_integer_sequence<int, N>{});
+    steps(ok, skip, dead, pv, std::make_integer_sequence<int, N>{});
     return ok;
   }
 };
@@ -925,7 +929,7 @@ template <class C> AB2_HD void fill_mma_lut(int *lut, const int lane) {
 //  (5) [Vxx vx] = [Qhat qhat] + X^T KK            same shapes (A: X from smem, B: same KK)
 // ---------------------------------------------------------------------------
 template <class C, class Ctx>
-AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ sm, int &st,
+AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ sm, int &st, int &pv,
                           const int inst) {
   constexpr int NX = C::NX, NU = C::NU, NK = C::NK, NR = C::NR;
   constexpr int MTX = C::MTX, KT = C::KT, NT = C::NT, NT2 = C::NT2, KT2 = C::KT2;
@@ -1091,7 +1095,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
         if (colS)
           F.solve(X + lane, SX, kz);
       } else { // an interchange / 2x2 pivot / singular column: general algorithm
-        if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind))
+        if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind, pv))
           st |= ST_STAGE_FACTOR_FAILED;
         if (colS) {
           const SmemFactor<NK> G{kkt, dd, sd, perm, kind};
@@ -1279,6 +1283,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
   double *Vxx_b = p.Vxx + (size_t)inst * (N + 1) * NX * NX;
   double *vx_b = p.vx + (size_t)inst * (N + 1) * NX;
   int st = ST_OK;
+  int pv = 0; // pivot statistics: +1 per 2x2 pivot, +0x10000 per interchange
 
   // lane classes
   const bool colA = lane < NX;                 // owns a state column
@@ -1355,7 +1360,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
 
     // ---------------- stage knots N-1 .. 0: riccati-kernel.hxx:210-277
     if constexpr (C::MMA) {
-      stage_loop_mma<C>(ctx, p, sm, st, inst);
+      stage_loop_mma<C>(ctx, p, sm, st, pv, inst);
     } else {
     constexpr int RS = C::RS;
     constexpr bool EV = C::EVEN;
@@ -1473,7 +1478,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           if (colA || colF)
             F.solve(rhs0 + jj, RS, kz);
         } else { // an interchange / 2x2 pivot / singular column: general algorithm
-          if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind))
+          if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind, pv))
             st |= ST_STAGE_FACTOR_FAILED;
           if (colA || colF) {
             const SmemFactor<NK> G{kkt, dd, sd, perm, kind};
@@ -1488,12 +1493,12 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
           for (int i = c; i < NK; ++i)
             F.a[i][c] = kkt[i + c * NK];
         }
-        if (!F.factor())
+        if (!F.factor(pv))
           st |= ST_STAGE_FACTOR_FAILED;
         if (colA || colF)
           bk_solve_column<NK>(F, rhs0 + jj, sol + jj, RS, kz);
       } else {
-        if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind))
+        if (!bk_factor_group(ctx, kkt, NK, NK, dd, sd, perm, kind, pv))
           st |= ST_STAGE_FACTOR_FAILED;
         if (colA || colF) {
           const SmemFactor<NK> F{kkt, dd, sd, perm, kind};
@@ -1648,15 +1653,18 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
         b0[NX + m] = -g0[m];
       }
       ctx.sync();
-      if (!bk_factor_group<4>(ctx, K0, n0, n0, dd0, sd0, perm0, kind0))
+      if (!bk_factor_group<4>(ctx, K0, n0, n0, dd0, sd0, perm0, kind0, pv))
         st |= ST_INIT_FACTOR_FAILED;
       bk_solve_vec_group(ctx, K0, n0, n0, dd0, sd0, perm0, kind0, b0, x0w, o0);
       for (int i = lane; i < n0; i += C::G)
         p.kkt0[(size_t)inst * n0 + i] = o0[i];
       ctx.sync();
     }
-    if (lane == 0)
+    if (lane == 0) {
       p.status[inst] = st;
+      if (p.pivstat)
+        p.pivstat[inst] = pv;
+    }
   }
 
   // ---------------- forward rollout: riccati-kernel.hxx:196-207, 315-377

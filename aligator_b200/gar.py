@@ -91,6 +91,7 @@ def lib():
         L.ab2_gar_first_step_policy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ab2_gar_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ab2_gar_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_pivot_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_cycle_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_synchronize.argtypes = [C.c_void_p, C.c_void_p]
         L.ab2_gar_kernel_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5
@@ -306,6 +307,13 @@ class CudaRiccatiBatch:
         _check(lib().ab2_gar_status(self.h, _ptr(st), AB2_HOST, C.c_void_p(stream)))
         self.synchronize(stream)
         return st
+
+    def pivot_stats(self, stream=0):
+        """(n_2x2, n_interchanges) per instance of the last backward pass (``ab2_gar_pivot_stats``)."""
+        pv = np.empty(self.dims.batch, dtype=np.int32)
+        _check(lib().ab2_gar_pivot_stats(self.h, _ptr(pv), AB2_HOST, C.c_void_p(stream)))
+        self.synchronize(stream)
+        return pv & 0xffff, (pv >> 16) & 0xffff
 
     def cycle_append(self, new_last, memspace=AB2_HOST, stream=0):
         if memspace == AB2_HOST:

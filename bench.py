@@ -46,7 +46,7 @@ def bytes_per_knot(nx, nu, nc):
     return 8 * (rd + wr + fw)
 
 
-def synth_batch_torch(torch, batch, N, nx, nu, device, seed, nc=0):
+def synth_batch_torch(torch, batch, N, nx, nu, device, seed, nc=0, nct=0, cstyle="control"):
     """SURVEY section 8(d) synthetic inputs (conditioned variant), generated on `device`,
     packed in the C-ABI layout [A|B|f|Q|S|R|q|r] (column-major blocks)."""
     g = torch.Generator(device=device)
@@ -63,17 +63,24 @@ def synth_batch_torch(torch, batch, N, nx, nu, device, seed, nc=0):
     Bm = ru(batch, N, nx, nu)
     cm = lambda M: M.transpose(-1, -2).reshape(batch, N, -1)  # column-major flatten
     parts = [cm(A), cm(Bm), rn(batch, N, nx), cm(Q), cm(S), cm(R), ru(batch, N, nx), ru(batch, N, nu)]
-    if nc > 0:  # C = 0, D = I rows with a random half zeroed (inactive box rows), d ~ U[-1,1]
+    if nc > 0 and cstyle == "control":  # C = 0, D = I rows with a random half zeroed (inactive box rows), d ~ U[-1,1]
         act = (torch.rand(batch, N, nc, generator=g, device=device, dtype=f64) < 0.5).to(f64)
         D = torch.eye(nc, nu, device=device, dtype=f64).expand(batch, N, nc, nu) * act[..., None]
         parts += [torch.zeros(batch, N, nc * nx, device=device, dtype=f64), cm(D), ru(batch, N, nc) * act]
+    elif nc > 0:  # the reference generator's state constraints: C = I, D = 0, d ~ U[-1,1] (tests/gar/test_util.cpp:41-44)
+        Cm = torch.eye(nc, nx, device=device, dtype=f64).expand(batch, N, nc, nx)
+        parts += [cm(Cm), torch.zeros(batch, N, nc * nu, device=device, dtype=f64), ru(batch, N, nc)]
     stage = torch.cat(parts, dim=-1)
     if stage.shape[-1] % 2:
         stage = torch.cat([stage, torch.zeros(batch, N, 1, device=device, dtype=f64)], dim=-1)
     stage = stage.contiguous()
     Wt = rn(batch, nx, nx + 1)
     Qt = Wt @ Wt.transpose(-1, -2) / nx
-    term = torch.cat([Qt.transpose(-1, -2).reshape(batch, -1), ru(batch, nx)], dim=-1).contiguous()
+    tparts = [Qt.transpose(-1, -2).reshape(batch, -1), ru(batch, nx)]
+    if nct > 0:  # terminal knot: C = I (nct x nx), d ~ U[-1,1]
+        Ct = torch.eye(nct, nx, device=device, dtype=f64).expand(batch, nct, nx)
+        tparts += [Ct.transpose(-1, -2).reshape(batch, -1), ru(batch, nct)]
+    term = torch.cat(tparts, dim=-1).contiguous()
     G0 = (-torch.eye(nx, device=device, dtype=f64)).expand(batch, nx, nx).reshape(batch, -1).contiguous()
     g0 = rn(batch, nx).contiguous()
     return stage, term, G0, g0

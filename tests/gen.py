@@ -204,3 +204,40 @@ def make_pivoting(probs):
             k.B *= 0.02
             k.S *= 0.0
     return probs
+
+
+def make_2x2_pivots(probs):
+    """Force 2x2 Bunch-Kaufman pivots on control-constrained knots: a light control cost
+    (R = 1e-3 I, S = 0, weak B so Rhat = R + B^T V B stays small) against fully active rows
+    D = I makes |a_kk| < alpha*colmax, fails the row test too (rowmax = 1) and leaves
+    |a_imax,imax| = mu < alpha*rowmax: the pivot is the 2x2 block {k, nu + k}
+    (core/bunchkaufman.hpp:61-83).  Needs nc >= 1."""
+    for p in probs:
+        for k in p.stages[:-1]:
+            nu, nc = k.nu, k.nc
+            assert nc >= 1
+            k.R[:] = 1e-3 * np.eye(nu)
+            k.S[:] = 0.0
+            k.B *= 0.01
+            k.C[:] = 0.0
+            k.D[:] = np.eye(nc, nu)
+            k.d[:] = np.linspace(-0.5, 0.5, nc)
+    return probs
+
+
+def kkt_condition(probs, Vxx, mueq, tmax=8):
+    """max over (sampled) knots of cond([[Rhat, D^T],[D, -mu I]]) with Rhat = R + B^T V' B: the factor
+    by which two correct fp64 solvers may differ on K, k, Z, z.
+    Vxx: [B][N+1][nx][nx] (from the oracle)."""
+    worst = 1.0
+    for b, p in enumerate(probs):
+        N = p.horizon
+        for t in list(range(min(N, tmax))) + list(range(max(N - tmax, 0), N)):
+            k = p.stages[t]
+            if k.nc == 0:
+                continue
+            V = np.tril(Vxx[b, t + 1]) + np.tril(Vxx[b, t + 1], -1).T
+            Rh = k.R + k.B.T @ V @ k.B
+            M = np.block([[Rh, k.D.T], [k.D, -mueq * np.eye(k.nc)]])
+            worst = max(worst, np.linalg.cond(M))
+    return worst

@@ -131,7 +131,7 @@ def test_terminal_constraints_and_edge_horizons(gar):
         probs = gen.generate_batch(11, B, N, nx, nu, nc, nct)
         got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq)
         ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
-        compare(got, ref, nu, nc, N, mueq, tol=1e-9 if nct else TOL)
+        compare(got, ref, nu, nc, N, mueq)
 
 
 def test_reference_style_generator_reaches_reference_kkt_thresholds(gar):
@@ -303,7 +303,7 @@ def test_unconstrained_knots_that_need_interchanges(gar, shape, variant):
     probs = gen.make_pivoting(gen.generate_batch(31, B, N, nx, nu, nc, nct))
     got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, 1e-8, variant=variant)
     ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, 1e-8)
-    compare(got, ref, nu, nc, N, 1e-8, tol=1e-9)
+    compare(got, ref, nu, nc, N, 1e-8)
 
 
 @pytest.mark.parametrize("variant", [7, 8, 10])
@@ -316,7 +316,7 @@ def test_tensor_core_variants(gar, shape, variant):
     probs = gen.generate_batch(55 + nx, B, N, nx, nu, nc, nct)
     got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq, variant=variant)
     ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
-    compare(got, ref, nu, nc, N, mueq, tol=1e-9 if nct else TOL)
+    compare(got, ref, nu, nc, N, mueq)
 
 
 BLOCK_SHAPES = [  # (nx, nu, nc, nct, N, batch, mueq): no compile-time instantiation -> CTA per instance
@@ -339,7 +339,7 @@ def test_block_kernel_runtime_shapes(gar, shape):
     probs = gen.generate_batch(200 + nx, B, N, nx, nu, nc, nct)
     got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq)
     ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, mueq)
-    compare(got, ref, nu, nc, N, mueq, tol=1e-9 if (nct or nc) else TOL)
+    compare(got, ref, nu, nc, N, mueq)
     assert got["launches"] == 1
 
 
@@ -363,7 +363,7 @@ def test_block_kernel_interchanges(gar):
     probs = gen.make_pivoting(gen.generate_batch(31, B, N, nx, nu, nc, nct))
     got, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, 1e-8)
     ref = oracle_batch(probs, packed, nx, nu, nc, nct, N, 1e-8)
-    compare(got, ref, nu, nc, N, 1e-8, tol=1e-9)
+    compare(got, ref, nu, nc, N, 1e-8)
 
 
 def test_shape_too_large_for_one_cta_is_refused(gar):
@@ -448,7 +448,7 @@ def test_cuda_matches_committed_fixture(gar):
     for case, (nx, nu, nc, nct, N, mueq, seed) in mg.CASES.items():
         probs = gen.generate_batch(seed, 2, N, nx, nu, nc, nct)
         got, _ = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq)
-        tol = 1e-9 if (nc or nct) else TOL
+        tol = TOL
         for k in ("fb", "ff", "Vxx", "vx", "xs", "us", "lbdas"):
             assert gen.rel_fro(got[k], ref["%s/%s" % (case, k)]) <= tol, (case, k)
 
@@ -517,7 +517,7 @@ def test_parametric_problems(gar, shape):
     assert solver.backward(mueq)
     thetas = np.random.default_rng(1).standard_normal((3, nth))
     sols = [gar.lqr_initialize_solution(p) for p in probs] if hasattr(gar, "lqr_initialize_solution") else None
-    tol = 1e-9 if (nc or nct) else TOL
+    tol = TOL
     for b, p in enumerate(probs):
         op = orc.OracleProblem(p)
         ref = orc.ProximalRiccatiSolver(op)

@@ -23,7 +23,8 @@ class SweepParams(C.Structure):
                 ("mueq", C.c_double), ("do_bwd", C.c_int), ("do_fwd", C.c_int)] + \
                [(n, _dp) for n in ("stage", "term", "G0", "g0", "ff", "fb", "Vxx", "vx", "ffT",
                                    "fbT", "kkt0", "xs", "us", "vs", "vsT", "lbd0", "lbdas")] + \
-               [("status", C.POINTER(C.c_int)), ("stagger_ns", C.c_int), ("num_sms", C.c_int),
+               [("status", C.POINTER(C.c_int)), ("pivstat", C.POINTER(C.c_int)), ("stagger_ns", C.c_int),
+                ("num_sms", C.c_int),
                 ("ctas_per_sm", C.c_int), ("nth", C.c_int)] + \
                [(n, _dp) for n in ("theta", "fth", "Vxt", "Vtt", "vt", "kkt0fth", "thGrad", "thHess")]
 
@@ -77,6 +78,8 @@ def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0, block=0):
     for k, v in keep.items():
         setattr(p, k, v.ctypes.data_as(_dp))
     p.status = status.ctypes.data_as(C.POINTER(C.c_int))
+    pivstat = np.zeros(B, dtype=np.int32)
+    p.pivstat = pivstat.ctypes.data_as(C.POINTER(C.c_int))
     if block < 0:  # compile-time specialisation of the block program (StaticBlockDims)
         rc = lib.emu_block_sweep_static(nx, nu, nc, int(-block), C.byref(p))
     elif block:
@@ -86,6 +89,7 @@ def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0, block=0):
     assert rc == 0
     out["Vxx"] = out["Vxx"].reshape(B, N + 1, nx, nx).transpose(0, 1, 3, 2)
     out["status"] = status
+    out["pivots_2x2"], out["interchanges"] = pivstat & 0xffff, (pivstat >> 16) & 0xffff
     return out
 
 
