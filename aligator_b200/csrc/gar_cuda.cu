@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -279,6 +280,8 @@ int ab2_gar_create_parametric(const ab2_gar_dims *dims, int nth, ab2_gar_solver 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device);
     p.num_sms = sms > 0 ? sms : 148;
   }
+  if (const char *f = std::getenv("AB2_DEBUG_FLAGS")) // experiment switches, see SweepParams::dbg
+    p.dbg = std::atoi(f);
   *out = s;
   return AB2_OK;
 }

@@ -76,11 +76,12 @@ struct SweepParams {
   double *lbd0;  // [batch][nc0]
   double *lbdas; // [batch][N][NX]         lbda_1..lbda_N
   int *status;   // [batch]
-  int *pivstat;  // [batch] or null: low 16 bits = 2x2 pivots, high 16 = interchanges (stage + initial factorisations)
+  int *pivstat;  // [batch] or null: bits 0-14 = 2x2 pivots, bit 15 = initial system on the register fast path, high 16 = interchanges
   // launch tuning (device only; 0 = off)
   int stagger_ns;  // start-up delay per resident warp slot: de-phases the warps of an SM
   int num_sms;
   int ctas_per_sm; // host-side launch hint: resident CTAs per SM wanted (0 = whatever fits)
+  int dbg;         // experiment switches (env AB2_DEBUG_FLAGS): 1 = no register fast path for the initial system, 2 = no proxy fence before the forward ring
   // parametric problems (nth > 0; CTA-per-instance kernel only): riccati-kernel.hxx:185-192, 278-311
   int nth;
   const double *theta; // [batch][nth] or null (forward)
@@ -872,6 +873,79 @@ AB2_D void bk_solve_vec_group(Ctx &ctx, const double *a, const int lda, const in
 }
 
 
+// ---------------------------------------------------------------------------
+// Fast path of the initial saddle system [[Vxx_0, G0^T],[G0, 0]] x = b
+// (proximal-riccati.hxx:44-55): LDL^T for the case in which every pivot test of the
+// Bunch-Kaufman algorithm picks the 1x1 pivot in place by its first test
+// (|a_kk| >= alpha*colmax, core/bunchkaufman.hpp:61) -- what happens for the saddle systems
+// of well-posed problems.  Same arithmetic, in the same order, as bk_factor_group +
+// bk_solve_vec_group on that path (so the result is identical), but: lane = row, the column
+// test is a vote instead of a redundant scan by every lane, the pivot column's entries
+// travel by shuffles, every shared-memory access is conflict-free (odd leading dimension),
+// the solves keep x in a register.  About a tenth of the general routine's shared-memory
+// wavefronts.  Returns false at the first failing test with the matrix partly overwritten:
+// the caller then rebuilds it and runs the general algorithm.
+//   a: n x n, lower triangle, column-major with ODD leading dimension lda.
+template <class Ctx>
+AB2_D bool kkt0_fast(Ctx &ctx, double *a, const int lda, const int n, const double rhs, double &x_out) {
+  const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
+  const int lane = ctx.lane;
+  const bool in = lane < n;
+  double myd = 0.0;
+  for (int k = 0; k < n; ++k) {
+    ctx.sync(); // column k is final
+    const double akk = a[k + k * lda];
+    const bool below = lane > k && in;
+    const double my = below ? a[lane + k * lda] : 0.0;
+    const bool ok = (fabs(my) * alpha <= fabs(akk)) && (fabs(akk) > 0.0);
+    if (!ctx.all(ok))
+      return false;
+    const double d = 1.0 / akk;
+    if (lane == k)
+      myd = d;
+    // trailing rows: a_ij -= (a_jk d) a_ik, i >= j > k; four columns per round so that the
+    // shuffles and loads of a round are in flight together
+    int j = k + 1;
+    for (; j + 4 <= n; j += 4) {
+      const double m0 = ctx.shfl(my, j), m1 = ctx.shfl(my, j + 1), m2 = ctx.shfl(my, j + 2),
+                   m3 = ctx.shfl(my, j + 3);
+      double *pj = a + (in ? lane : 0) + j * lda;
+      const double r0 = pj[0], r1 = pj[lda], r2 = pj[2 * lda], r3 = pj[3 * lda];
+      if (in && lane >= j)
+        pj[0] = r0 - (m0 * d) * my;
+      if (in && lane >= j + 1)
+        pj[lda] = r1 - (m1 * d) * my;
+      if (in && lane >= j + 2)
+        pj[2 * lda] = r2 - (m2 * d) * my;
+      if (in && lane >= j + 3)
+        pj[3 * lda] = r3 - (m3 * d) * my;
+    }
+    for (; j < n; ++j) {
+      const double mj = ctx.shfl(my, j);
+      if (in && lane >= j)
+        a[lane + j * lda] -= (mj * d) * my;
+    }
+    if (below)
+      a[lane + k * lda] = my * d;
+  }
+  ctx.sync();
+  double x = rhs;
+  for (int c = 0; c + 1 < n; ++c) { // unit-lower solve, column-oriented (bunchkaufman.hpp:472)
+    const double xc = ctx.shfl(x, c);
+    if (lane > c && in)
+      x -= a[lane + c * lda] * xc;
+  }
+  x *= myd; // D^-1 (1x1 pivots, :499)
+  for (int i = n - 1; i >= 1; --i) { // unit-upper solve with L^T (:504)
+    const double xi = ctx.shfl(x, i);
+    if (lane < i)
+      x -= a[i + lane * lda] * xi;
+  }
+  x_out = x;
+  ctx.sync(); // everyone is done with the matrix
+  return true;
+}
+
 // 128-bit global store of two consecutive doubles (p 16-byte aligned).
 AB2_D void stg2(double *p, double x, double y) {
 #if defined(__CUDA_ARCH__)
@@ -896,19 +970,21 @@ AB2_D void sts2(double *p, double x, double y) {
 // logical column 8t+g; lut[NT + mt*NT + nt][lane] = packed record offsets of the two H0
 // entries of accumulator tile (mt, nt) (structural zeros point at the zero slot behind the
 // record).  Written by ONE warp of the CTA (or one host thread per lane) before any sweep.
-template <class C> AB2_HD void fill_mma_lut(int *lut, const int lane) {
+template <class C> AB2_HD void fill_mma_lut(int *lut, const int lane, const int first = 0, const int step = 1) {
   constexpr int NT = C::NT;
   const int g = lane >> 2, q = lane & 3;
-  for (int t = 0; t < NT; ++t)
-    lut[t * 32 + lane] = C::col_offset(8 * t + g);
-  for (int mt = 0; mt < NT; ++mt)
-    for (int nt = 0; nt < NT; ++nt) {
+  for (int r = first; r < NT + NT * NT; r += step) { // table rows are dealt out over the CTA's warps
+    if (r < NT) {
+      lut[r * 32 + lane] = C::col_offset(8 * r + g);
+    } else {
+      const int mt = (r - NT) / NT, nt = (r - NT) % NT;
       const int o0 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q);
       const int o1 = C::h0_offset(8 * mt + g, 8 * nt + 2 * q + 1);
       const unsigned u0 = o0 < 0 ? (unsigned)C::SREC_PAD : (unsigned)o0; // structural zero -> the zero slot
       const unsigned u1 = o1 < 0 ? (unsigned)C::SREC_PAD : (unsigned)o1;
-      lut[(NT + mt * NT + nt) * 32 + lane] = (int)(u0 | (u1 << 16));
+      lut[r * 32 + lane] = (int)(u0 | (u1 << 16));
     }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1638,27 +1714,55 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       ctx.sync();
       const double *G0 = p.G0 + (size_t)inst * nc0 * NX;
       const double *g0 = p.g0 + (size_t)inst * nc0;
-      if (colA) {
-        AB2_UNROLL
-        for (int i = 0; i < NX; ++i)
-          if (i >= lane)
-            K0[i + lane * n0] = vcol[i]; // lower triangle of Vxx_0
-        for (int m = 0; m < nc0; ++m)
-          K0[NX + m + lane * n0] = G0[m + (size_t)lane * nc0];
-        b0[lane] = -vx0;
+      // fast path: LDL^T in registers (lane = column), valid when no pivot test asks for an
+      // interchange or a 2x2 pivot; otherwise the general algorithm below, from the same sources
+      bool fast_done = false;
+      if (!(p.dbg & 1)) {
+        const int ld0 = n0 | 1; // odd leading dimension: rows and columns both conflict-free
+        if (colA) {
+          AB2_UNROLL
+          for (int i = 0; i < NX; ++i)
+            if (i >= lane)
+              K0[i + lane * ld0] = vcol[i]; // lower triangle of Vxx_0
+          for (int m = 0; m < nc0; ++m)
+            K0[NX + m + lane * ld0] = G0[m + (size_t)lane * nc0];
+        }
+        for (int m = lane; m < nc0; m += C::G)
+          for (int m2 = m; m2 < nc0; ++m2)
+            K0[NX + m2 + (NX + m) * ld0] = 0.0;
+        const double b = (lane < NX) ? -vx0 : ((lane < n0) ? -g0[lane - NX] : 0.0);
+        double x = 0.0;
+        fast_done = kkt0_fast(ctx, K0, ld0, n0, b, x); // (synchronises before reading)
+        if (fast_done && lane < n0)
+          p.kkt0[(size_t)inst * n0 + lane] = x;
+        if (fast_done)
+          pv |= 0x8000; // statistics: the initial system took the fast path
+        else
+          ctx.sync();   // everyone has left the fast path before the matrix is rebuilt
       }
-      for (int m = lane; m < nc0; m += C::G) {
-        for (int m2 = m; m2 < nc0; ++m2)
-          K0[NX + m2 + (NX + m) * n0] = 0.0;
-        b0[NX + m] = -g0[m];
+      if (!fast_done) {
+        if (colA) {
+          AB2_UNROLL
+          for (int i = 0; i < NX; ++i)
+            if (i >= lane)
+              K0[i + lane * n0] = vcol[i]; // lower triangle of Vxx_0
+          for (int m = 0; m < nc0; ++m)
+            K0[NX + m + lane * n0] = G0[m + (size_t)lane * nc0];
+          b0[lane] = -vx0;
+        }
+        for (int m = lane; m < nc0; m += C::G) {
+          for (int m2 = m; m2 < nc0; ++m2)
+            K0[NX + m2 + (NX + m) * n0] = 0.0;
+          b0[NX + m] = -g0[m];
+        }
+        ctx.sync();
+        if (!bk_factor_group<4>(ctx, K0, n0, n0, dd0, sd0, perm0, kind0, pv))
+          st |= ST_INIT_FACTOR_FAILED;
+        bk_solve_vec_group(ctx, K0, n0, n0, dd0, sd0, perm0, kind0, b0, x0w, o0);
+        for (int i = lane; i < n0; i += C::G)
+          p.kkt0[(size_t)inst * n0 + i] = o0[i];
+        ctx.sync();
       }
-      ctx.sync();
-      if (!bk_factor_group<4>(ctx, K0, n0, n0, dd0, sd0, perm0, kind0, pv))
-        st |= ST_INIT_FACTOR_FAILED;
-      bk_solve_vec_group(ctx, K0, n0, n0, dd0, sd0, perm0, kind0, b0, x0w, o0);
-      for (int i = lane; i < n0; i += C::G)
-        p.kkt0[(size_t)inst * n0 + i] = o0[i];
-      ctx.sync();
     }
     if (lane == 0) {
       p.status[inst] = st;
@@ -1694,7 +1798,8 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     // proxy (initial-stage workspace) and, in the fused sweep, read ff / fb / Vxx / vx this
     // group stored to global memory during the backward pass: every lane orders its
     // generic-proxy writes before the async proxy, then the group synchronises.
-    ctx.proxy_fence();
+    if (!(p.dbg & 2))
+      ctx.proxy_fence();
     ctx.sync();
     auto fill_slot = [&](int d, int t) { // fb record of knot t -> ring slot d
       if (FUSED) { // [K; Z; Ahat]_t | Vxx_t (symmetric for t >= 1: row i = column i) | vx_t
@@ -1751,10 +1856,17 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
               if (FUSED && (C::FWD_FF || r >= NR)) // ff_t sits right behind vx_t: one bias vector
                 s0 = slot[(NR + NX) * NX + (r >= NR ? r - NR : NX + r)];
               if (EVF) {
+                // Row r starts NX/2 16-byte units into the slot: with NX/2 = 2 mod 4 (nx = 4, 12)
+                // rows r and r+4 of a quarter-warp's 128-bit load fall on the same banks.  Those
+                // rows walk their column pairs rotated by one (pairs 1,2,..,0): the two halves
+                // then sit on units of different parity -- no conflict, same products.
+                constexpr bool ROT = ((NX / 2) % 4) == 2;
+                const int rot2 = ROT ? ((r >> 1) & 2) : 0; // 2 doubles for rows 4..7 (mod 8)
                 AB2_UNROLL
                 for (int c = 0; c < NX; c += 2) {
-                  const D2 gg = lds2(slot + r * NX + c);
-                  const D2 xx = lds2(xc + c);
+                  const int cc = (ROT && c + 2 == NX) ? (rot2 ? 0 : c) : c + rot2;
+                  const D2 gg = lds2(slot + r * NX + cc);
+                  const D2 xx = lds2(xc + cc);
                   s0 += gg.x * xx.x;
                   s1 += gg.y * xx.y;
                 }

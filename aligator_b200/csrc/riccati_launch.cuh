@@ -26,6 +26,9 @@ template <int G, bool TMA> struct DevCtx {
   __device__ __forceinline__ int *cta_ints() const { return cta_lut; }
 
   __device__ __forceinline__ void sync() { __syncwarp(mask); }
+  // value of `v` in lane `src` of this group / vote over the group
+  __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(mask, v, src, G); }
+  __device__ __forceinline__ bool all(bool p) { return __all_sync(mask, p); }
 
   // D(8x8) += A(8x4) B(4x8) on the FP64 tensor cores (SASS: DMMA.884); full warp only.
   __device__ __forceinline__ void mma(double (&d)[2], double a, double b) {
@@ -161,9 +164,8 @@ __global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
   const int group_in_cta = warp * IPW + gsub;
   const int inst = blockIdx.x * (WARPS * IPW) + group_in_cta;
   if constexpr (C::MMA) { // the per-CTA table of per-lane constants: one writer, then a CTA barrier
-    if (warp == 0)
-      fill_mma_lut<C>(reinterpret_cast<int *>(smem + (size_t)(WARPS * IPW) * group_doubles + (size_t)(WARPS * IPW) * NBAR),
-                      lane32);
+    fill_mma_lut<C>(reinterpret_cast<int *>(smem + (size_t)(WARPS * IPW) * group_doubles + (size_t)(WARPS * IPW) * NBAR),
+                    lane32, warp, WARPS);
     __syncthreads();
   }
   if (inst >= p.batch)

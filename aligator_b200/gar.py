@@ -313,7 +313,8 @@ class CudaRiccatiBatch:
         pv = np.empty(self.dims.batch, dtype=np.int32)
         _check(lib().ab2_gar_pivot_stats(self.h, _ptr(pv), AB2_HOST, C.c_void_p(stream)))
         self.synchronize(stream)
-        return pv & 0xffff, (pv >> 16) & 0xffff
+        self.kkt0_fast_path = ((pv >> 15) & 1).astype(bool)
+        return pv & 0x7fff, (pv >> 16) & 0xffff
 
     def cycle_append(self, new_last, memspace=AB2_HOST, stream=0):
         if memspace == AB2_HOST:

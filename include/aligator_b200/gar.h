@@ -223,8 +223,9 @@ int ab2_gar_kkt_error(ab2_gar_solver *s, double mueq, double *dst, int memspace,
 int ab2_gar_device_ptr(ab2_gar_solver *s, int what, double **out);
 /* Per-instance status words (layout above). */
 int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream);
-/* Pivot statistics of the last backward pass, one int per instance: low 16 bits = number of
- * 2x2 pivots, high 16 bits = number of symmetric interchanges the Bunch-Kaufman factorisations
+/* Pivot statistics of the last backward pass, one int per instance: bits 0-14 = number of
+ * 2x2 pivots, bit 15 = the initial saddle system needed no interchange / 2x2 pivot and ran on the
+ * register fast path, high 16 bits = number of symmetric interchanges the Bunch-Kaufman factorisations
  * of the stage KKT matrices and of the initial saddle system took (core/bunchkaufman.hpp:61-83,
  * what Eigen::BunchKaufman reports through pivots() / m_pivot_count, :158-163).  Diagnostics:
  * lets a caller (and the tests) see that the pivoted code paths actually ran. */

@@ -14,6 +14,7 @@
 namespace {
 struct HostCtx {
   int lane;
+  int G_; // lanes in the group
   std::barrier<> *bar;
   double *xa, *xb; // fragment exchange for the emulated mma (one slot per lane)
   int *lutp;
@@ -32,6 +33,22 @@ struct HostCtx {
       d[e] += s;
     }
     sync();
+  }
+  double shfl(double v, int src) { // every lane publishes, then reads lane `src`
+    xa[lane] = v;
+    sync();
+    const double r = xa[src];
+    sync();
+    return r;
+  }
+  bool all(bool p) {
+    xa[lane] = p ? 1.0 : 0.0;
+    sync();
+    bool r = true;
+    for (int l = 0; l < G_; ++l)
+      r = r && (xa[l] != 0.0);
+    sync();
+    return r;
   }
   void issue_copy(int, double *dst, const double *src, int nd) {
     if (lane == 0)
@@ -69,7 +86,7 @@ template <class C> int run(const ab2::SweepParams &p) {
     std::vector<std::thread> th;
     for (int l = 0; l < G; ++l)
       th.emplace_back([&, l] {
-        HostCtx ctx{l, &bar, xa.data(), xb.data(), lutv.data()};
+        HostCtx ctx{l, G, &bar, xa.data(), xb.data(), lutv.data()};
         ab2::riccati_group_sweep<C>(ctx, p, inst, sm.data());
       });
     for (auto &t : th)

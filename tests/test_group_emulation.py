@@ -25,7 +25,7 @@ class SweepParams(C.Structure):
                                    "fbT", "kkt0", "xs", "us", "vs", "vsT", "lbd0", "lbdas")] + \
                [("status", C.POINTER(C.c_int)), ("pivstat", C.POINTER(C.c_int)), ("stagger_ns", C.c_int),
                 ("num_sms", C.c_int),
-                ("ctas_per_sm", C.c_int), ("nth", C.c_int)] + \
+                ("ctas_per_sm", C.c_int), ("dbg", C.c_int), ("nth", C.c_int)] + \
                [(n, _dp) for n in ("theta", "fth", "Vxt", "Vtt", "vt", "kkt0fth", "thGrad", "thHess")]
 
 
@@ -89,7 +89,8 @@ def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0, block=0):
     assert rc == 0
     out["Vxx"] = out["Vxx"].reshape(B, N + 1, nx, nx).transpose(0, 1, 3, 2)
     out["status"] = status
-    out["pivots_2x2"], out["interchanges"] = pivstat & 0xffff, (pivstat >> 16) & 0xffff
+    out["pivots_2x2"], out["interchanges"] = pivstat & 0x7fff, (pivstat >> 16) & 0xffff
+    out["kkt0_fast"] = ((pivstat >> 15) & 1).astype(bool)
     return out
 
 
@@ -200,3 +201,24 @@ def test_emulated_tensor_core_step_edge_horizons(db):
     check_against_oracle(12, 6, 0, 0, 0, B=1, mueq=1e-8, seed=3, db=db)
     check_against_oracle(12, 6, 0, 0, 1, B=1, mueq=1e-8, seed=4, db=db)
     check_against_oracle(12, 6, 0, 2, 4, B=1, mueq=1e-2, seed=5, db=db, tol=1e-9)
+
+
+def test_pivot_statistics_and_initial_fast_path():
+    """ab2_gar_pivot_stats semantics in the emulation: well-posed problems take the register fast path
+    of the initial saddle system and no 2x2 pivot; make_2x2_pivots() problems take min(nu,nc) 2x2
+    pivots per knot; make_pivoting() problems take one interchange per knot."""
+    nx, nu, N, B = 12, 6, 6, 3
+    got = run_emulated(nx, nu, 0, 0, N, gen.generate_batch(3, B, N, nx, nu, 0, 0), 1e-8, db=2)
+    assert np.all(got["kkt0_fast"]) and np.all(got["pivots_2x2"] == 0) and np.all(got["interchanges"] == 0)
+    got = run_emulated(nx, nu, 0, 0, N, gen.make_pivoting(gen.generate_batch(3, B, N, nx, nu, 0, 0)), 1e-8, db=2)
+    assert np.all(got["interchanges"] >= N)
+    nx, nu, nc = 4, 2, 2
+    probs = gen.make_2x2_pivots(gen.generate_batch(4, B, N, nx, nu, nc, 0))
+    got = run_emulated(nx, nu, nc, 0, N, probs, 1e-3, db=1)
+    assert np.all(got["pivots_2x2"] >= N * min(nu, nc))
+    stage, term, G0, g0 = gen.pack_problems(probs)
+    bo = orc.BatchedOracle(nx, nu, nc, 0, nx, N, B, stage, term, G0, g0)
+    bo.sweep(1e-3)
+    ref = bo.get()
+    for k in ("fb", "ff", "Vxx", "xs", "us", "vs", "lbdas"):
+        assert gen.rel_fro(got[k], ref[k]) <= 1e-10, k
