@@ -19,6 +19,8 @@ struct BlockDevCtx {
   // barrier over the first `nth` threads (whole warps) of the CTA: named barrier 1
   __device__ __forceinline__ void sync_sub(int nth) { asm volatile("bar.sync 1, %0;" ::"r"(nth) : "memory"); }
   __device__ __forceinline__ void wsync() { __syncwarp(); }
+  __device__ __forceinline__ void atomic_or(int *q, int v) { atomicOr(q, v); }
+  __device__ __forceinline__ void atomic_add(int *q, int v) { atomicAdd(q, v); }
   // generic-proxy writes of this thread (shared and global) ordered before later TMA accesses
   __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
   __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -85,10 +87,37 @@ __global__ void __launch_bounds__(256) __maxnreg__(MAXREG)
   ctx.lane = threadIdx.x & 31;
   ctx.nwarps = blockDim.x >> 5;
   ctx.init(reinterpret_cast<uint64_t *>(smem + d.s_end));
-  for (int inst = blockIdx.x; inst < p.batch; inst += gridDim.x) {
-    riccati_block_sweep(ctx, p, d, inst, smem);
+  const int legs = p.legs > 1 ? p.legs : 1; // leg mode: a work item is one (instance, leg)
+  for (int item = blockIdx.x; item < p.batch * legs; item += gridDim.x) {
+    riccati_block_sweep(ctx, p, d, item / legs, smem, item % legs);
     __syncthreads();
   }
+}
+
+// Leg mode, between the legs' backward and forward launches: the condensed block-tridiagonal
+// system of every instance (condensed_solve), one CTA per instance.
+__global__ void __launch_bounds__(256) condensed_kernel(const SweepParams p, const int nx) {
+  extern __shared__ __align__(16) double smem[];
+  BlockDevCtx ctx;
+  ctx.tid = threadIdx.x;
+  ctx.nthreads = blockDim.x;
+  ctx.warp = threadIdx.x >> 5;
+  ctx.lane = threadIdx.x & 31;
+  ctx.nwarps = blockDim.x >> 5;
+  ctx.bar0 = 0;
+  ctx.phase = 0;
+  for (int inst = blockIdx.x; inst < p.batch; inst += gridDim.x) {
+    condensed_solve(ctx, p, nx, inst, smem);
+    __syncthreads();
+  }
+}
+
+__global__ void collapse_kernel(const SweepParams p, const int nx, const int nu, const int nc) {
+  BlockDevCtx ctx;
+  ctx.tid = threadIdx.x;
+  ctx.nthreads = blockDim.x;
+  for (int inst = blockIdx.x; inst < p.batch; inst += gridDim.x)
+    collapse_feedback(ctx, p, nx, nu, nc, inst);
 }
 
 int block_threads(int nx, int nu, int nc, int nc0, int nth) {
@@ -141,9 +170,10 @@ static cudaError_t launch_block_t(const SweepParams &p, const D &d, int threads,
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int grid = sms * (nb > 0 ? nb : 1); // persistent CTAs, instances strided over them
-  if (grid > p.batch)
-    grid = p.batch;
+  int grid = sms * (nb > 0 ? nb : 1); // persistent CTAs, instances (or legs) strided over them
+  const long items = (long)p.batch * (p.legs > 1 ? p.legs : 1);
+  if (grid > items)
+    grid = (int)items;
   if (info) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, kern);
@@ -159,8 +189,37 @@ static cudaError_t launch_block_t(const SweepParams &p, const D &d, int threads,
   return cudaGetLastError();
 }
 
+// leg mode: the condensed solve of every instance / collapseFeedback
+bool condensed_supported(int nx, int nc0, int legs) {
+  const int dmax = nx > nc0 ? nx : nc0;
+  return legs >= 2 && dmax <= 256 && (size_t)condensed_smem_doubles(nx, nc0, legs) * sizeof(double) <= (size_t)227 * 1024;
+}
+cudaError_t launch_condensed(const SweepParams &p, int nx, cudaStream_t st) {
+  const int dmax = nx > p.nc0 ? nx : p.nc0;
+  const int threads = 32 * ((dmax + 31) / 32);
+  const size_t smem = (size_t)condensed_smem_doubles(nx, p.nc0, p.legs) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(condensed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm);
+  int grid = sms * per_sm;
+  if (grid > p.batch)
+    grid = p.batch;
+  condensed_kernel<<<grid, threads, smem, st>>>(p, nx);
+  return cudaGetLastError();
+}
+cudaError_t launch_collapse(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st) {
+  int grid = p.batch < 148 * 8 ? p.batch : 148 * 8;
+  collapse_kernel<<<grid, 128, 0, st>>>(p, nx, nu, nc);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st, int *info) {
-  const BlockDims d = make_block_dims(nx, nu, nc, p.nc0, p.nth);
+  const BlockDims d = make_block_dims(nx, nu, nc, p.nc0, p.nth, p.legs > 1 ? 0 : -1);
   const int threads = block_threads(nx, nu, nc, p.nc0, p.nth);
   const size_t smem = block_smem_bytes(nx, nu, nc, p.nc0, p.nth);
   // BASELINE config 5 (Talos whole-body walk, nx 57 nu 28, initial condition on the full state):

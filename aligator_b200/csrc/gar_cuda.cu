@@ -102,7 +102,10 @@ struct ab2_gar_solver {
   // owned device storage
   double *own_stage = nullptr, *own_term = nullptr, *own_G0 = nullptr, *own_g0 = nullptr;
   double *gains_tmp = nullptr, *kkt_tmp = nullptr, *theta_dev = nullptr;
-  int nth = 0;
+  int nth = 0;  // parameter dimension of the value function outputs (= nx in leg mode)
+  int rec_nth = 0; // parameter blocks carried by the knot records (0 in leg mode)
+  int legs = 0;    // >= 2: gar::ParallelRiccatiSolver (leg mode)
+  double *cond = nullptr;
   double *out[AB2_OUT_COUNT] = {};
   size_t out_doubles[AB2_OUT_COUNT] = {};
   size_t out_rec[AB2_OUT_COUNT] = {};  // doubles per knot (or per instance)
@@ -153,19 +156,33 @@ int ab2_gar_supported(int nx, int nu, int nc, int nc0) {
   return ab2::block_supported(nx, nu, nc, nc0) ? 2 : 0; // run-time shape, one CTA per instance
 }
 
-int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) { return ab2_gar_create_parametric(dims, 0, out); }
-
+static int create_impl(const ab2_gar_dims *dims, int nth, int legs, ab2_gar_solver **out);
+int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) { return create_impl(dims, 0, 0, out); }
 int ab2_gar_create_parametric(const ab2_gar_dims *dims, int nth, ab2_gar_solver **out) {
+  return create_impl(dims, nth, 0, out);
+}
+int ab2_gar_create_parallel(const ab2_gar_dims *dims, int num_legs, ab2_gar_solver **out) {
+  if (num_legs < 2) // parallel-solver.hxx:42-46 throws "numThreads should be greater than or equal to 2"
+    return fail(AB2_ERR_INVALID, "num_legs (" + std::to_string(num_legs) + ") should be greater than or equal to 2");
+  if (dims && dims->horizon + 1 < num_legs)
+    return fail(AB2_ERR_INVALID, "every leg needs at least one knot: horizon + 1 >= num_legs");
+  return create_impl(dims, dims ? dims->nx : 0, num_legs, out);
+}
+
+static int create_impl(const ab2_gar_dims *dims, int nth, int legs, ab2_gar_solver **out) {
   if (!dims || !out)
     return fail(AB2_ERR_INVALID, "null argument");
   const ab2_gar_dims &d = *dims;
   if (d.nx < 1 || d.nu < 1 || d.nc < 0 || d.nct < 0 || d.nc0 < 0 || d.horizon < 0 || d.batch < 1 || nth < 0)
     return fail(AB2_ERR_INVALID, "bad dimensions");
+  const int rec_nth = legs > 1 ? 0 : nth; // leg mode: plain records, the parameterisation is implicit
   // compile-time shapes run one warp (or part of one) per instance; every other shape runs
   // the CTA-per-instance kernel with run-time dimensions (block_kernel.cu)
   const ab2::KernelEntry *k = ab2::find_kernel(d.nx, d.nu, d.nc);
   if (k && (d.nx + d.nc0 > k->G || nth > 0))
     k = nullptr; // parametric problems run the CTA-per-instance kernel
+  if (legs > 1 && !ab2::condensed_supported(d.nx, d.nc0, legs))
+    return fail(AB2_ERR_UNSUPPORTED, "the condensed system of " + std::to_string(legs) + " legs does not fit one CTA's shared memory");
   if (!k && !ab2::block_supported(d.nx, d.nu, d.nc, d.nc0, nth))
     return fail(AB2_ERR_UNSUPPORTED,
                 "(nx,nu,nc,nc0) = (" + std::to_string(d.nx) + "," + std::to_string(d.nu) + "," +
@@ -180,12 +197,14 @@ int ab2_gar_create_parametric(const ab2_gar_dims *dims, int nth, ab2_gar_solver 
   s->d = d;
   s->k = k;
   s->nth = nth;
-  s->srec = (int)ab2_gar_stage_record_doubles_th(d.nx, d.nu, d.nc, nth);
+  s->rec_nth = rec_nth;
+  s->legs = legs;
+  s->srec = (int)ab2_gar_stage_record_doubles_th(d.nx, d.nu, d.nc, rec_nth);
   if (k && k->srec_pad != s->srec) {
     delete s;
     return fail(AB2_ERR_INVALID, "internal: record size mismatch");
   }
-  s->trec = (int)ab2_gar_term_record_doubles_th(d.nx, d.nct, nth);
+  s->trec = (int)ab2_gar_term_record_doubles_th(d.nx, d.nct, rec_nth);
   s->nr = d.nu + d.nc + d.nx;
   if (k)
     k->group_doubles(d.nc0, s->group_doubles);
@@ -245,8 +264,20 @@ int ab2_gar_create_parametric(const ab2_gar_dims *dims, int nth, ab2_gar_solver 
       return fail(AB2_ERR_CUDA, std::string("cudaMalloc pivstat: ") + cudaGetErrorString(e));
     }
   }
+  if (legs > 1) {
+    const size_t td = (size_t)d.nc0 + (size_t)d.nx * (2 * legs - 1);
+    cudaError_t e = cudaMalloc(&s->cond, sizeof(double) * B * td);
+    if (e == cudaSuccess)
+      e = cudaMemset(s->cond, 0, sizeof(double) * B * td);
+    if (e != cudaSuccess) {
+      ab2_gar_destroy(s);
+      return fail(AB2_ERR_CUDA, std::string("cudaMalloc cond: ") + cudaGetErrorString(e));
+    }
+  }
   ab2::SweepParams &p = s->p;
   std::memset(&p, 0, sizeof(p));
+  p.legs = legs;
+  p.cond = s->cond;
   p.N = N;
   p.nct = d.nct;
   p.nc0 = d.nc0;
@@ -297,7 +328,7 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
     cudaFree(s->status);
   if (s->pivstat)
     cudaFree(s->pivstat);
-  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev})
+  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev, s->cond})
     if (q)
       cudaFree(q);
   for (int i = 0; i < ab2_gar_solver::kPipeStreams; ++i) {
@@ -411,7 +442,42 @@ static ab2::SweepParams slice_params(const ab2_gar_solver *s, int b0, int nb) {
     if (q.theta)
       q.theta += b * s->nth;
   }
+  if (q.cond)
+    q.cond += b * ((size_t)s->d.nc0 + (size_t)nx * (2 * s->legs - 1));
   return q;
+}
+
+// The kernels of one (sub-)batch.  Serial solver: ONE launch (backward and/or forward).  Leg mode
+// (gar::ParallelRiccatiSolver): the legs' backward recursions of all instances in one launch, the
+// condensed block-tridiagonal systems in a second, the legs' rollouts in a third
+// (parallel-solver.hxx:150-164, 166-203, 221-241).
+static int run_kernels(ab2_gar_solver *s, ab2::SweepParams q, int bwd, int fwd, cudaStream_t st) {
+  if (s->legs > 1) {
+    if (bwd) {
+      CUDA_TRY(cudaMemsetAsync(q.status, 0, sizeof(int) * q.batch, st)); // the legs OR / add into these
+      CUDA_TRY(cudaMemsetAsync(q.pivstat, 0, sizeof(int) * q.batch, st));
+      q.do_bwd = 1;
+      q.do_fwd = 0;
+      CUDA_TRY(ab2::launch_block(q, s->d.nx, s->d.nu, s->d.nc, st, nullptr));
+      CUDA_TRY(ab2::launch_condensed(q, s->d.nx, st));
+      s->launches += 2;
+    }
+    if (fwd) {
+      q.do_bwd = 0;
+      q.do_fwd = 1;
+      CUDA_TRY(ab2::launch_block(q, s->d.nx, s->d.nu, s->d.nc, st, nullptr));
+      s->launches += 1;
+    }
+    return AB2_OK;
+  }
+  q.do_bwd = bwd;
+  q.do_fwd = fwd;
+  if (s->k && s->variant != 9)
+    CUDA_TRY(s->k->launch(q, s->variant, s->group_doubles, st, nullptr));
+  else
+    CUDA_TRY(ab2::launch_block(q, s->d.nx, s->d.nu, s->d.nc, st, nullptr));
+  s->launches += 1;
+  return AB2_OK;
 }
 
 static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream) {
@@ -427,11 +493,8 @@ static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream
   s->p.mueq = mueq;
   s->p.do_bwd = bwd;
   s->p.do_fwd = fwd;
-  if (s->k && s->variant != 9)
-    CUDA_TRY(s->k->launch(s->p, s->variant, s->group_doubles, (cudaStream_t)stream, nullptr));
-  else
-    CUDA_TRY(ab2::launch_block(s->p, s->d.nx, s->d.nu, s->d.nc, (cudaStream_t)stream, nullptr));
-  s->launches += 1;
+  if (int rc = run_kernels(s, s->p, bwd, fwd, (cudaStream_t)stream))
+    return rc;
   if (bwd)
     s->have_backward = true;
   s->have_forward = fwd != 0; // a backward-only launch invalidates the previous trajectory
@@ -444,8 +507,8 @@ int ab2_gar_sweep(ab2_gar_solver *s, double mueq, void *stream) { return launch(
 int ab2_gar_forward_theta(ab2_gar_solver *s, const double *theta, int memspace, void *stream) {
   if (!s)
     return fail(AB2_ERR_INVALID, "null solver");
-  if (theta && s->nth == 0)
-    return fail(AB2_ERR_INVALID, "theta given to a solver without parameters (nth = 0)");
+  if (theta && (s->nth == 0 || s->legs > 1))
+    return fail(AB2_ERR_INVALID, "theta given to a solver without parameters (nth = 0; the parallel solver ignores theta, parallel-solver.hxx:211)");
   CUDA_TRY(cudaSetDevice(s->d.device));
   s->p.theta = nullptr;
   if (theta) {
@@ -467,7 +530,7 @@ int ab2_gar_forward_theta(ab2_gar_solver *s, const double *theta, int memspace, 
 int ab2_gar_assemble(ab2_gar_solver *s, const ab2_lq_inputs *in, void *stream) {
   if (!s || !in)
     return fail(AB2_ERR_INVALID, "null argument");
-  if (s->nth > 0)
+  if (s->rec_nth > 0)
     return fail(AB2_ERR_UNSUPPORTED, "assemble: parametric problems (nth > 0) are not supported");
   const ab2_gar_dims &d = s->d;
   const bool stage_ok = d.horizon == 0 || (in->Jx && in->Ju && in->slack && in->Lxx && in->Lxu && in->Luu &&
@@ -590,11 +653,8 @@ int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *ter
         (rc = up(s->own_G0, G0, (size_t)nc0 * nx)) != AB2_OK || (rc = up(s->own_g0, g0, nc0)) != AB2_OK)
       return rc;
     const ab2::SweepParams q = slice_params(s, b0, nb);
-    if (s->k && s->variant != 9)
-      CUDA_TRY(s->k->launch(q, s->variant, s->group_doubles, st, nullptr));
-    else
-      CUDA_TRY(ab2::launch_block(q, s->d.nx, s->d.nu, s->d.nc, st, nullptr));
-    s->launches += 1;
+    if (int rc2 = run_kernels(s, q, 1, 1, st))
+      return rc2;
     for (int i = 0; i < nwhat; ++i) {
       const int w = whats[i];
       const size_t per_inst = (size_t)s->out_knots[w] * s->out_rec[w];
@@ -702,7 +762,7 @@ int ab2_gar_kkt_error(ab2_gar_solver *s, double mueq, double *dst, int memspace,
     return fail(AB2_ERR_INVALID, "bad argument");
   if (!s->have_problem || !s->have_backward || !s->have_forward)
     return fail(AB2_ERR_STATE, "kkt_error needs a problem and a completed sweep (no forward pass since the last backward)");
-  if (s->nth > 0)
+  if (s->rec_nth > 0)
     return fail(AB2_ERR_UNSUPPORTED, "kkt_error: parametric problems (nth > 0) are not supported");
   CUDA_TRY(cudaSetDevice(s->d.device));
   if (!s->kkt_tmp)
@@ -754,6 +814,21 @@ int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream) {
   return AB2_OK;
 }
 
+int ab2_gar_collapse_feedback(ab2_gar_solver *s, void *stream) {
+  if (!s)
+    return fail(AB2_ERR_INVALID, "null solver");
+  if (s->legs <= 1)
+    return AB2_OK; // the serial solver's collapseFeedback is a no-op (riccati-base.hpp:32)
+  if (!s->have_backward)
+    return fail(AB2_ERR_STATE, "collapse_feedback before backward()");
+  if (s->d.horizon < 1)
+    return AB2_OK;
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  CUDA_TRY(ab2::launch_collapse(s->p, s->d.nx, s->d.nu, s->d.nc, (cudaStream_t)stream));
+  s->launches += 1;
+  return AB2_OK;
+}
+
 int ab2_gar_pivot_stats(ab2_gar_solver *s, int *dst, int memspace, void *stream) {
   if (!s || !dst)
     return fail(AB2_ERR_INVALID, "bad argument");
@@ -772,14 +847,21 @@ int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace
   const int N = s->d.horizon, B = s->d.batch;
   if (N < 1)
     return fail(AB2_ERR_INVALID, "cycle_append needs horizon >= 1");
-  if (s->nth > 0)
+  if (s->rec_nth > 0)
     return fail(AB2_ERR_UNSUPPORTED, "cycle_append: parametric problems (nth > 0) are not supported");
   CUDA_TRY(cudaSetDevice(s->d.device));
   cudaStream_t st = (cudaStream_t)stream;
   // factors: datas[0..N-1] rotate left, datas[N-1] re-created (zeros), terminal kept
   // (proximal-riccati.hxx:79-83).  Vxx/vx have N+1 entries; the last is the terminal's.
+  if (s->legs > 1) { // the parallel solver drops every factor and starts over (parallel-solver.hxx:246-258)
+    for (int w : {AB2_OUT_FF, AB2_OUT_FB, AB2_OUT_VXX, AB2_OUT_VX, AB2_OUT_FTH, AB2_OUT_VXT, AB2_OUT_VTT, AB2_OUT_VT})
+      if (s->out_doubles[w])
+        CUDA_TRY(cudaMemsetAsync(s->out[w], 0, s->out_doubles[w] * sizeof(double), st));
+  }
   const int whats[4] = {AB2_OUT_FF, AB2_OUT_FB, AB2_OUT_VXX, AB2_OUT_VX};
   for (int w : whats) {
+    if (s->legs > 1)
+      break;
     const int rec = (int)s->out_rec[w];
     if (rec == 0)
       continue;

@@ -30,7 +30,7 @@ struct BlockDims {
   int s_rec, s_vn, s_vxn, s_w, s_x, s_kk, s_y, s_h, s_kkt, s_dd, s_sd, s_int, s_end; // doubles
   int fwd_ring, fwd_slot, slack;
   // parametric terms (nth > 0): record offsets [Gx | Gu | Gv | Gth | gamma] and the theta workspace
-  int nth, off_gx, off_gu, off_gv, off_gth, off_gam;
+  int nth, rec_nth, off_gx, off_gu, off_gv, off_gth, off_gam;
   int s_th; // start of the theta workspace (behind everything else, incl. the initial-stage overlay)
 };
 
@@ -49,9 +49,16 @@ AB2_HD constexpr int blk_s8(int n) { // smallest stride >= n that is 8 mod 16
 }
 
 // Layout shared by the host (sizing the launch) and the device.
-AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0, int nth = 0) {
+// nth: parameter dimension of the value function (workspace); rec_nth: parameter blocks carried
+// by the knot RECORDS (-1 = nth).  Leg mode (ParallelRiccatiSolver, gar/parallel-solver.hxx) has
+// nth = nx with plain records: the parameterisation of a leg is implicit (Gx = A^T, Gu = B^T,
+// gamma = f on the leg's last knot, zero elsewhere, :136-147).
+AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0, int nth = 0, int rec_nth = -1) {
   BlockDims d{};
   d.nth = nth;
+  if (rec_nth < 0)
+    rec_nth = nth;
+  d.rec_nth = rec_nth;
   d.nx = nx;
   d.nu = nu;
   d.nc = nc;
@@ -75,13 +82,13 @@ AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0, int 
   d.off_d = d.off_c + nc * nx;
   d.off_dv = d.off_d + nc * nu;
   d.off_gx = d.off_dv + nc;
-  d.off_gu = d.off_gx + nx * nth;
-  d.off_gv = d.off_gu + nu * nth;
-  d.off_gth = d.off_gv + nc * nth;
-  d.off_gam = d.off_gth + nth * nth;
-  d.srec_pad = blk_ev(d.off_gam + nth);
+  d.off_gu = d.off_gx + nx * rec_nth;
+  d.off_gv = d.off_gu + nu * rec_nth;
+  d.off_gth = d.off_gv + nc * rec_nth;
+  d.off_gam = d.off_gth + rec_nth * rec_nth;
+  d.srec_pad = blk_ev(d.off_gam + rec_nth);
   // (parametric knots read [Gx .. gamma] at the end of the step: no early refill of the tail)
-  d.split = (d.off_q % 2 == 0 && nth == 0) ? d.off_q : d.srec_pad;
+  d.split = (d.off_q % 2 == 0 && rec_nth == 0) ? d.off_q : d.srec_pad;
   d.vs = blk_fstride(4 * d.kt);
   d.vrows = 8 * d.mtx;
   d.sw = blk_s8(d.njp);
@@ -151,7 +158,7 @@ template <int NX, int NU, int NC, int NC0> struct StaticBlockDims {
   AB2_SD(sw) AB2_SD(wrows) AB2_SD(sh) AB2_SD(sx) AB2_SD(xrows) AB2_SD(s_rec) AB2_SD(s_vn) AB2_SD(s_vxn) AB2_SD(s_w)
   AB2_SD(s_x) AB2_SD(s_kk) AB2_SD(s_y) AB2_SD(s_h) AB2_SD(s_kkt) AB2_SD(s_dd) AB2_SD(s_sd) AB2_SD(s_int) AB2_SD(s_end)
   AB2_SD(fwd_ring) AB2_SD(fwd_slot) AB2_SD(slack) AB2_SD(nth) AB2_SD(off_gx) AB2_SD(off_gu) AB2_SD(off_gv)
-  AB2_SD(off_gth) AB2_SD(off_gam) AB2_SD(s_th)
+  AB2_SD(off_gth) AB2_SD(off_gam) AB2_SD(s_th) AB2_SD(rec_nth)
 #undef AB2_SD
 };
 
@@ -202,7 +209,7 @@ template <class Ctx> struct CtaAsGroup {
 // result is -(KKT^-1 rhs).
 AB2_D void bk_solve_column_rt(const double *a, const int n, const double *dd, const double *sd,
                               const int *perm, const int *kind, const double *rhs, double *work,
-                              double *sol, const int stride) {
+                              double *sol, const int stride, const bool negate = true) {
   for (int i = 0; i < n; ++i)
     work[i * stride] = rhs[perm[i] * stride];
   for (int i = 1; i < n; ++i) { // forward: unit lower, row i of L against x_0..x_{i-1}
@@ -250,7 +257,7 @@ AB2_D void bk_solve_column_rt(const double *a, const int n, const double *dd, co
     work[c * stride] = s0 + s1;
   }
   for (int i = 0; i < n; ++i)
-    sol[perm[i] * stride] = -work[i * stride];
+    sol[perm[i] * stride] = negate ? -work[i * stride] : work[i * stride];
 }
 
 // LDL^T of a matrix on which every pivot test of the Bunch-Kaufman algorithm picks the 1x1
@@ -317,12 +324,18 @@ constexpr int BLK_CH = 4; // n-tiles accumulated together by one warp (one work 
 // ---------------------------------------------------------------------------
 template <class Ctx, class D>
 AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const int inst,
-                               double *__restrict__ sm) {
+                               double *__restrict__ sm, const int leg = 0) {
   const int nx = d.nx, nu = d.nu, nc = d.nc, nk = d.nk, nr = d.nr;
   const int tid = ctx.tid, T = ctx.nthreads, warp = ctx.warp, lane = ctx.lane, NW = ctx.nwarps;
   const int g = lane >> 2, q = lane & 3;
   const int N = p.N, nct = p.nct, nc0 = p.nc0;
   const double mueq = p.mueq;
+  // leg mode: this CTA owns knots [t_lo, t_hi) of the instance (gar/parallel-solver.hxx:150-164)
+  const int NLEG = p.legs > 1 ? p.legs : 1;
+  const bool legmode = NLEG > 1;
+  const int t_lo = legmode ? leg_begin(N, leg, NLEG) : 0;
+  const int t_hi = legmode ? leg_begin(N, leg + 1, NLEG) : N + 1;
+  const bool last_leg = t_hi == N + 1; // the leg that holds the terminal knot (no parameters)
 
   double *rec = sm + d.s_rec;
   double *Vn = sm + d.s_vn;
@@ -346,7 +359,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
   const int bk_threads = 32 * ((nk + 31) / 32); // warps that own rows of the KKT matrix
   CtaAsGroup<Ctx> grp{ctx, tid, bk_threads};
   // ---- parametric terms (nth > 0): workspace behind everything else ----
-  const int nth = d.nth;
+  const int nth = (legmode && last_leg) ? 0 : d.nth;
   double *th = sm + d.s_th;
   double *vxt2 = th;                                  // [2][nx*nth]  Vxt' (current / next), column-major
   double *vtt2 = vxt2 + blk_ev(2 * nx * nth);         // [2][nth*nth]
@@ -370,8 +383,9 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
   if (p.do_bwd) {
     int st = ST_OK;
     int pv = 0; // pivot statistics (threads 0..bk_threads-1 all see the same decisions)
-    if (N > 0) {
-      const double *src = stage_b + (size_t)(N - 1) * d.srec_pad;
+    const int t_first = last_leg ? N - 1 : t_hi - 1; // first stage knot of the (descending) loop
+    if (t_first >= t_lo) {
+      const double *src = stage_b + (size_t)t_first * d.srec_pad;
       ctx.issue_copy(0, rec, src, d.split);
       if (two_parts)
         ctx.issue_copy(1, rec + d.split, src + d.split, d.srec_pad - d.split);
@@ -384,10 +398,25 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
     for (int i = tid; i < d.s_kkt - d.s_w; i += T)
       Wsm[i] = 0.0;
     ctx.sync();
+    if (!last_leg) {
+      // A leg that ends on a stage knot: that knot is the leg's terminal knot WITH controls
+      // (riccati-kernel.hxx:151-172, 185-192), parameterised by Gx = A^T, Gu = B^T, gamma = f
+      // (parallel-solver.hxx:136-147).  It is the ordinary stage step below started from a zero
+      // value function (V' = 0, vx' = 0, Vxt' = Vtt' = 0, vt' = 0) -- adding exact zeros.
+      for (int i = tid; i < nx; i += T)
+        vxn[i] = 0.0;
+      for (int e = tid; e < nx * nth; e += T)
+        vxt2[e] = 0.0;
+      for (int e = tid; e < nth * nth; e += T)
+        vtt2[e] = 0.0;
+      for (int e = tid; e < nth; e += T)
+        vtv2[e] = 0.0;
+      ctx.sync();
+    } else
     // ---------------- terminal knot (nu = 0): riccati-kernel.hxx:146-149,175-183
     {
       const int trec = nx * nx + nx + nct * nx + nct;
-      const int trec_th = trec + nx * nth + nct * nth + nth * nth + nth; // + [Gx | Gv | Gth | gamma]
+      const int trec_th = trec + nx * d.rec_nth + nct * d.rec_nth + d.rec_nth * d.rec_nth + d.rec_nth; // + [Gx | Gv | Gth | gamma]
       const double *tr = p.term + (size_t)inst * trec_th;
       const double *Qt = tr, *qt = tr + nx * nx, *Ct = qt + nx, *dt = Ct + (size_t)nct * nx;
       double *VN = Vxx_b + (size_t)N * nx * nx;
@@ -418,7 +447,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
         vxn[i] = s;
       }
       ctx.sync();
-      if (N > 0) // symmetrised by the step N-1 of the reference (A1)
+      if (N > t_lo) // symmetrised by the step N-1 of the reference (A1); a leg head is not
         for (int e = tid; e < nx * nx; e += T)
           VN[(e % nx) + (e / nx) * nx] = Vn[(e / nx) * d.vs + (e % nx)];
       if (nth > 0) { // nu = 0: Vxt = Gx, Vtt = Gth, vt = gamma (:185-192); Zth = 0 (:146-149)
@@ -442,7 +471,9 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
     // ---------------- stage knots N-1 .. 0: riccati-kernel.hxx:210-277
     const int nchunk = (d.nt + BLK_CH - 1) / BLK_CH;
     const int nchunk2 = (d.nt2 + BLK_CH - 1) / BLK_CH;
-    for (int t = N - 1; t >= 0; --t) {
+    for (int t = t_first; t >= t_lo; --t) {
+      const bool legl = !last_leg && t == t_hi - 1; // the last knot of a parametric leg
+      const int gmode = !legmode ? 0 : (legl ? 2 : 1); // parametric blocks: record / zero / leg-last
       double *fbt = fb_b + (size_t)t * nr * nx;
       double *fft = ff_b + (size_t)t * nr;
       ctx.wait_copy(0);
@@ -554,7 +585,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       }
       ctx.sync();
       // the tail of the record (cost blocks, C, D, d) is consumed: fetch the next knot's
-      if (two_parts && t > 0) {
+      if (two_parts && t > t_lo) {
         const double *src = stage_b + (size_t)(t - 1) * d.srec_pad;
         ctx.issue_copy(1, rec + d.split, src + d.split, d.srec_pad - d.split);
       }
@@ -634,17 +665,18 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
               for (int e = 0; e < 2; ++e) {
                 const int jj = 8 * (n0 + c) + 2 * q + e;
                 if (jj < nx) {
-                  fbt[(nk + i) * nx + jj] = EA[c][e];
+                  // (the third block of a leg's terminal knot is never written by the reference, A6)
+                  fbt[(nk + i) * nx + jj] = legl ? 0.0 : EA[c][e];
                   if (nth > 0)
                     ahat[i * nx + jj] = EA[c][e];
-                  if (t == 0)
-                    Vxx_b[i + jj * nx] = VV[c][e]; // datas[0].Vxx is left unsymmetrised (A1)
+                  if (t == t_lo) // datas[0].Vxx -- and every leg head -- is left unsymmetrised (A1)
+                    Vxx_b[(size_t)t * nx * nx + i + jj * nx] = VV[c][e];
                   if (i >= jj) { // V' = lower triangle mirrored (:216 of the next step)
                     Vn[i * d.vs + jj] = VV[c][e];
                     Vn[jj * d.vs + i] = VV[c][e];
                   }
                 } else if (jj == nx) {
-                  fft[nk + i] = EA[c][e];
+                  fft[nk + i] = legl ? 0.0 : EA[c][e];
                   if (nth > 0)
                     aff[i] = EA[c][e];
                   vx_b[(size_t)t * nx + i] = VV[c][e];
@@ -657,8 +689,15 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       ctx.sync();
       if (nth > 0) { // (8) parametric terms, riccati-kernel.hxx:278-311 -- plain thread-parallel loops
         const double *Am = rec, *Bm = rec + d.off_b;
-        const double *Gx = rec + d.off_gx, *Gu = rec + d.off_gu, *Gv = rec + d.off_gv, *Gth = rec + d.off_gth,
-                     *gam = rec + d.off_gam;
+        // parametric blocks of this knot: from the record (gmode 0), zero (inner knot of a leg),
+        // or Gx = A^T, Gu = B^T, Gth = 0, gamma = f (a leg's last knot, parallel-solver.hxx:136-147)
+        const double *Gxr = rec + d.off_gx, *Gur = rec + d.off_gu, *Gvr = rec + d.off_gv, *Gthr = rec + d.off_gth,
+                     *gamr = rec + d.off_gam, *fr = rec + d.off_f;
+        auto gx = [&](int i, int j) { return gmode == 0 ? Gxr[i + j * nx] : (gmode == 2 ? Am[j + i * nx] : 0.0); };
+        auto gu = [&](int c, int j) { return gmode == 0 ? Gur[c + j * nu] : (gmode == 2 ? Bm[j + c * nx] : 0.0); };
+        auto gv = [&](int m, int j) { return gmode == 0 ? Gvr[m + j * nc] : 0.0; };
+        auto gth = [&](int e) { return gmode == 0 ? Gthr[e] : 0.0; };
+        auto gam = [&](int i) { return gmode == 0 ? gamr[i] : (gmode == 2 ? fr[i] : 0.0); };
         const double *Vxtn = vxt2 + thcur * nx * nth, *Vttn = vtt2 + thcur * nth * nth, *vtn = vtv2 + thcur * nth;
         double *Vxtc = vxt2 + (thcur ^ 1) * nx * nth, *Vttc = vtt2 + (thcur ^ 1) * nth * nth,
                *vtc = vtv2 + (thcur ^ 1) * nth;
@@ -671,14 +710,14 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
           for (int c = 0; c < nx; ++c)
             acc += Mc[c] * Vxtn[c + j * nx];
           if (isx)
-            gxh[i + j * nx] = Gx[i + j * nx] + acc;
+            gxh[i + j * nx] = gx(i, j) + acc;
           else
-            guh[i + j * nu] = Gu[i + j * nu] + acc;
+            guh[i + j * nu] = gu(i, j) + acc;
         }
         ctx.sync();
         for (int e = tid; e < nk * nth; e += T) { // right-hand sides [Guhat; Gv] (the solve negates)
           const int r = e / nth, j = e % nth;
-          trhs[e] = (r < nu) ? guh[r + j * nu] : Gv[(r - nu) + j * nc];
+          trhs[e] = (r < nu) ? guh[r + j * nu] : gv(r - nu, j);
         }
         ctx.sync();
         if (tid < nth)
@@ -693,13 +732,13 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
           for (int c = 0; c < nu; ++c)
             acc += Bm[i + c * nx] * tsol[c * nth + j];
           yth[e] = acc;
-          ftt[nk * nth + e] = acc;
+          ftt[nk * nth + e] = legl ? 0.0 : acc; // (never written on a leg's terminal knot)
         }
         for (int i = tid; i < nth; i += T) { // vt = (gamma + vt') + Gu^T k + Vxt'^T a
-          const double s0 = gam[i] + vtn[i];
+          const double s0 = gam(i) + vtn[i];
           double s1 = 0.0, s2 = 0.0;
           for (int c = 0; c < nu; ++c)
-            s1 += Gu[c + i * nu] * KKs[c * d.sx + nx];
+            s1 += gu(c, i) * KKs[c * d.sx + nx];
           for (int c = 0; c < nx; ++c)
             s2 += Vxtn[c + i * nx] * aff[c];
           const double v = (s0 + s1) + s2;
@@ -710,10 +749,10 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
           const int i = e % nx, j = e / nx;
           double s1 = 0.0, s2 = 0.0;
           for (int c = 0; c < nu; ++c)
-            s1 += KKs[c * d.sx + i] * Gu[c + j * nu];
+            s1 += KKs[c * d.sx + i] * gu(c, j);
           for (int c = 0; c < nx; ++c)
             s2 += ahat[c * nx + i] * Vxtn[c + j * nx];
-          const double v = (Gx[e] + s1) + s2;
+          const double v = (gx(i, j) + s1) + s2;
           Vxtc[e] = v;
           Vxt_b[(size_t)t * nx * nth + e] = v;
         }
@@ -722,17 +761,17 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
           const int i = e % nth, j = e / nth;
           double s1 = 0.0, s2 = 0.0;
           for (int c = 0; c < nu; ++c)
-            s1 += Gu[c + i * nu] * tsol[c * nth + j];
+            s1 += gu(c, i) * tsol[c * nth + j];
           for (int c = 0; c < nx; ++c)
             s2 += Vxtn[c + i * nx] * yth[c * nth + j];
-          const double v = ((Gth[e] + Vttn[e]) + s1) + s2;
+          const double v = ((gth(e) + Vttn[e]) + s1) + s2;
           Vttc[e] = v;
           Vtt_b[(size_t)t * nth * nth + e] = v;
         }
         thcur ^= 1;
         ctx.sync();
       }
-      if (t > 0) {
+      if (t > t_lo) {
         const double *src = stage_b + (size_t)(t - 1) * d.srec_pad;
         ctx.issue_copy(0, rec, src, d.split);
         double *Vt = Vxx_b + (size_t)t * nx * nx; // symmetric Vxx_t, as the next step leaves it
@@ -742,7 +781,8 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
     }
 
     // ---------------- initial stage: proximal-riccati.hxx:42-55 (nth = 0)
-    {
+    // (leg mode: the condensed block-tridiagonal system takes its place, condensed_solve below)
+    if (!legmode) {
       const int n0 = nx + nc0;
       double *K0 = sm; // n0 x n0 column-major (overlays the stage buffers)
       double *b0 = K0 + n0 * n0;
@@ -808,9 +848,15 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       }
     }
     if (tid == 0) {
-      p.status[inst] = st;
-      if (p.pivstat)
-        p.pivstat[inst] = pv;
+      if (legmode) { // several CTAs report on one instance (the host clears both words first)
+        ctx.atomic_or(p.status + inst, st);
+        if (p.pivstat)
+          ctx.atomic_add(p.pivstat + inst, pv);
+      } else {
+        p.status[inst] = st;
+        if (p.pivstat)
+          p.pivstat[inst] = pv;
+      }
     }
   }
 
@@ -843,13 +889,32 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       const int a = rec_shift(t);
       ctx.issue_copy(s_, ring + s_ * FS, p.fb + (e_inst + (size_t)t * R - a), blk_ev(R + a));
     };
-    for (int s_ = 0; s_ < RING && s_ < N; ++s_)
-      fill_slot(s_, s_);
-    // theta terms of the rollout (riccati-kernel.hxx:196-207, 315-377): only when theta is given
-    const double *theta = (nth > 0 && p.theta) ? p.theta + (size_t)inst * nth : nullptr;
-    const double *f0th = theta ? p.kkt0fth + (size_t)inst * n0 * nth : nullptr;
+    // stage knots of this CTA: [t_lo, t_s1) (all of them outside leg mode); a parametric leg's
+    // last knot t_hi - 1 yields u and v only (riccati-kernel.hxx:352-353)
+    const int t_s1 = last_leg ? N : t_hi;
+    for (int s_ = 0; s_ < RING && t_lo + s_ < t_s1; ++s_)
+      fill_slot(s_, t_lo + s_);
+    // theta terms of the rollout (riccati-kernel.hxx:196-207, 315-377): only when theta is given.
+    // Leg mode: theta = the co-state at the head of the NEXT leg, x and lbda at this leg's head =
+    // blocks of the condensed solution (parallel-solver.hxx:214-238).
+    const double *condv = legmode ? p.cond + (size_t)inst * (nc0 + nx * (2 * NLEG - 1)) : nullptr;
+    const double *theta = legmode ? (last_leg ? nullptr : condv + cond_offset(2 * (leg + 1), nc0, nx))
+                                  : ((nth > 0 && p.theta) ? p.theta + (size_t)inst * nth : nullptr);
+    const double *f0th = (theta && !legmode) ? p.kkt0fth + (size_t)inst * n0 * nth : nullptr;
     const double *fthf = theta ? p.fth + (size_t)inst * N * nr * nth : nullptr;
     const double *Vxtf = theta ? p.Vxt + (size_t)inst * (N + 1) * nx * nth : nullptr;
+    if (legmode) {
+      const double *xh = condv + cond_offset(2 * leg + 1, nc0, nx), *lh = condv + cond_offset(2 * leg, nc0, nx);
+      for (int i = tid; i < nx; i += T) {
+        xc[i] = xh[i];
+        xs_b[(size_t)t_lo * nx + i] = xh[i];
+        if (leg > 0)
+          lb_b[(size_t)(t_lo - 1) * nx + i] = lh[i];
+      }
+      if (leg == 0)
+        for (int m = tid; m < nc0; m += T)
+          p.lbd0[(size_t)inst * nc0 + m] = lh[m];
+    } else {
     for (int i = tid; i < nx; i += T) {
       double v = k0[i];
       if (theta) {
@@ -870,6 +935,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
         v += acc;
       }
       p.lbd0[(size_t)inst * nc0 + m] = v;
+    }
     }
     // lbda_t = vx_t + Vxx_t x_t (t >= 1; Vxx_t symmetric: element (c, i) read as (i, c) keeps
     // the loads of neighbouring threads contiguous).  Runs on the warps pass 1 leaves idle.
@@ -897,10 +963,11 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       }
     };
     // Pass 1: x_{t+1} = a + Ahat x_t (and u, v): thread r owns gain row r (nr <= T).
-    double gff = (tid < nr && N > 0) ? ff_b[tid] : 0.0;
+    double gff = (tid < nr && t_lo < t_s1) ? ff_b[(size_t)t_lo * nr + tid] : 0.0;
     ctx.sync();
-    for (int t = 0; t < N; ++t) {
-      const int s_ = t % RING;
+    for (int t = t_lo; t < t_s1; ++t) {
+      const int s_ = (t - t_lo) % RING;
+      const bool legl = !last_leg && t == t_hi - 1;
       ctx.wait_copy(s_);
       const double *slot = ring + s_ * FS + rec_shift(t);
       if (tid < nr) {
@@ -924,28 +991,29 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
           us_b[(size_t)t * nu + r] = sv;
         else if (r < nk)
           vs_b[(size_t)t * nc + (r - nu)] = sv;
-        else {
+        else if (!legl) { // (the state at the next leg's head comes from the condensed solution)
           xnx[r - nk] = sv;
           xs_b[(size_t)(t + 1) * nx + (r - nk)] = sv;
         }
-        gff = (t + 1 < N) ? ff_b[(size_t)(t + 1) * nr + r] : 0.0;
-      } else if (lam_overlap && tid >= lam0 && t >= 1) {
+        gff = (t + 1 < t_s1) ? ff_b[(size_t)(t + 1) * nr + r] : 0.0;
+      } else if (lam_overlap && tid >= lam0 && t > t_lo) {
         lam_rows(t, xc, tid - lam0, T - lam0);
       }
       double *tmp = xc;
       xc = xnx;
       xnx = tmp;
       ctx.sync(); // x_{t+1} visible; everyone is done with x_t and with this slot
-      if (t + RING < N)
+      if (t + RING < t_s1)
         fill_slot(s_, t + RING);
     }
     if (lam_overlap) {
-      if (N >= 1)
+      if (last_leg && N > t_lo)
         lam_rows(N, xc, tid, T);
     } else {
-      for (int tt = 1; tt <= N; ++tt) // xs is in global memory, written by this CTA
+      for (int tt = t_lo + 1; tt <= (last_leg ? N : t_hi - 1); ++tt) // xs is in global memory, written by this CTA
         lam_rows(tt, xs_b + (size_t)tt * nx, tid, T);
     }
+    if (last_leg)
     // terminal multipliers v_N = z + Z x_N
     for (int m = tid; m < nct; m += T) {
       double s = p.ffT[(size_t)inst * nct + m];
@@ -954,6 +1022,262 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       p.vsT[(size_t)inst * nct + m] = s;
     }
     ctx.sync();
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// Leg mode, step 2: the condensed system of one instance (the "boundary consensus" of the
+// legs).  Restates ParallelRiccatiSolver::assembleCondensedSystem + the solve + the iterative
+// refinement of ::backward (gar/parallel-solver.hxx:85-129, 166-203) on top of
+// symmetricBlockTridiagSolve / blockTridiagMatMul / blockTridiagRefinementStep
+// (gar/block-tridiagonal.hpp:82-138, 52-75, 147-182), one CTA per instance, everything in
+// shared memory.  Unknowns [lbda_0 | x_0 | theta_0 | x_{h1} | theta_1 | x_{h2} | ...]
+// (h_j = head knot of leg j, theta_{j-1} = lbda_{h_j}); block b = 2j+1 is x_{h_j}, b = 2j
+// (j >= 1) is theta_{j-1}:
+//   diagonal   D_0 = 0,  D_{2j+1} = Vxx[h_j] (as stored, lower triangle factored),  D_{2j} = Vtt[h_{j-1}]
+//   super      S_0 = G0, S_{2j+1} = Vxt[h_j],                                        S_{2j} = -I
+//   rhs        -g0,      -vx[h_j],                                                   -vt[h_{j-1}]
+// Backward-looking block U D U^T with one Bunch-Kaufman per diagonal block, then at most
+// `max_refine` refinement steps until the residual's infinity norm is <= thr.
+// (The reference's first refinement pass starts from a stale error buffer -- condensedErr is
+// only reset at the END of a pass, :201 -- which on a fresh solver zeroes the solution and
+// re-solves it; the intended algorithm is what runs here: identical to rounding.)
+// Writes p.cond (the solution), p.kkt0 = [x_0; lbda_0]; a failed block factorisation sets
+// ST_CONDENSED_FACTOR_FAILED and leaves the solve where the reference's early return does.
+AB2_HD constexpr int condensed_smem_doubles(int nx, int nc0, int T) {
+  const int NB = 2 * T, dmax = nx > nc0 ? nx : nc0, TD = nc0 + nx * (2 * T - 1);
+  return NB * dmax * dmax + (NB - 1) * dmax * dmax + NB * (3 * dmax + 2) + 2 * blk_ev(TD) + dmax * dmax + 2 * blk_ev(dmax);
+}
+
+template <class Ctx>
+AB2_D void condensed_solve(Ctx &ctx, const SweepParams &p, const int nx, const int inst, double *__restrict__ sm,
+                           const int max_refine = 5, const double thr = 1e-10) {
+  const int tid = ctx.tid, NT_ = ctx.nthreads;
+  const int N = p.N, nc0 = p.nc0, T = p.legs, nth = nx;
+  const int NB = 2 * T, dmax = nx > nc0 ? nx : nc0, TD = nc0 + nx * (2 * T - 1);
+  const int blk = dmax * dmax, auxs = 3 * dmax + 2;
+  double *Df = sm;
+  double *U = Df + (size_t)NB * blk;
+  double *aux = U + (size_t)(NB - 1) * blk;
+  double *sol = aux + (size_t)NB * auxs;
+  double *err = sol + blk_ev(TD);
+  double *wk = err + blk_ev(TD);
+  double *vw = wk + blk; // 2 * ev(dmax): work + out of the vector solves
+  auto dm = [&](int b) { return b == 0 ? nc0 : nx; };
+  auto off = [&](int b) { return cond_offset(b, nc0, nx); };
+  auto head = [&](int j) { return leg_begin(N, j, T); };
+  const double *Vxx_b = p.Vxx + (size_t)inst * (N + 1) * nx * nx;
+  const double *vx_b = p.vx + (size_t)inst * (N + 1) * nx;
+  const double *Vxt_b = p.Vxt + (size_t)inst * (N + 1) * nx * nth;
+  const double *Vtt_b = p.Vtt + (size_t)inst * (N + 1) * nth * nth;
+  const double *vt_b = p.vt + (size_t)inst * (N + 1) * nth;
+  const double *G0 = p.G0 + (size_t)inst * nc0 * nx;
+  const double *g0 = p.g0 + (size_t)inst * nc0;
+  // original blocks (global memory)
+  auto Dorig = [&](int b) -> const double * { // nullptr = zero block
+    if (b == 0)
+      return nullptr;
+    return (b & 1) ? Vxx_b + (size_t)head(b / 2) * nx * nx : Vtt_b + (size_t)head(b / 2 - 1) * nth * nth;
+  };
+  auto Sup = [&](int b) -> const double * { // nullptr = -I (even b >= 2)
+    if (b == 0)
+      return G0;
+    return (b & 1) ? Vxt_b + (size_t)head(b / 2) * nx * nth : nullptr;
+  };
+  auto rhs_at = [&](int b, int i) {
+    if (b == 0)
+      return -g0[i];
+    return (b & 1) ? -vx_b[(size_t)head(b / 2) * nx + i] : -vt_b[(size_t)head(b / 2 - 1) * nth + i];
+  };
+  // y (dm(b)) -= S_b x (dm(b+1))
+  auto sub_Sx = [&](int b, double *y, const double *x) {
+    const double *S = Sup(b);
+    const int r = dm(b), c = dm(b + 1);
+    for (int i = tid; i < r; i += NT_) {
+      double acc = 0.0;
+      if (S) {
+        for (int k = 0; k < c; ++k)
+          acc += S[i + (size_t)k * r] * x[k];
+      } else {
+        acc = -x[i];
+      }
+      y[i] -= acc;
+    }
+  };
+  CtaAsGroup<Ctx> grp{ctx, tid, NT_};
+  int st = 0, pv = 0;
+  auto bptr = [&](int b) { return Df + (size_t)b * blk; };
+  auto uptr = [&](int b) { return U + (size_t)b * blk; };
+  auto dd_ = [&](int b) { return aux + (size_t)b * auxs; };
+  auto sd_ = [&](int b) { return aux + (size_t)b * auxs + dmax; };
+  auto pm_ = [&](int b) { return reinterpret_cast<int *>(aux + (size_t)b * auxs + 2 * dmax); };
+  auto kd_ = [&](int b) { return reinterpret_cast<int *>(aux + (size_t)b * auxs + 2 * dmax) + dmax; };
+  // x (dm(b)) = D_b^-1 x  with the factor of block b
+  auto solve_vec = [&](int b, double *x) {
+    const int n = dm(b);
+    if (n == 0)
+      return;
+    bk_solve_vec_group(grp, bptr(b), n, n, dd_(b), sd_(b), pm_(b), kd_(b), x, vw, vw + blk_ev(dmax));
+    for (int i = tid; i < n; i += NT_)
+      x[i] = vw[blk_ev(dmax) + i];
+    ctx.sync();
+  };
+  // ---- assemble
+  for (int b = 0; b < NB; ++b) {
+    const double *Do = Dorig(b);
+    const int n = dm(b);
+    for (int e = tid; e < n * n; e += NT_)
+      bptr(b)[e] = Do ? Do[e] : 0.0;
+    for (int i = tid; i < n; i += NT_)
+      sol[off(b) + i] = rhs_at(b, i);
+    if (b + 1 < NB) { // U_b = S_b^T: dm(b+1) x dm(b)
+      const double *S = Sup(b);
+      const int r = dm(b + 1), c = n;
+      for (int e = tid; e < r * c; e += NT_) {
+        const int i = e % r, j = e / r; // U(i, j) = S(j, i)
+        uptr(b)[e] = S ? S[j + (size_t)i * c] : (i == j ? -1.0 : 0.0);
+      }
+    }
+  }
+  ctx.sync();
+  // ---- symmetricBlockTridiagSolve (block-tridiagonal.hpp:99-135)
+  bool ok = true;
+  for (int i = NB - 2; i >= 0 && ok; --i) {
+    const int n1 = dm(i + 1), n0 = dm(i);
+    if (!bk_factor_group<8>(grp, bptr(i + 1), n1, n1, dd_(i + 1), sd_(i + 1), pm_(i + 1), kd_(i + 1), pv)) {
+      ok = false;
+      break;
+    }
+    solve_vec(i + 1, sol + off(i + 1));
+    sub_Sx(i, sol + off(i), sol + off(i + 1));
+    // U_i = D_{i+1}^-1 U_i, column by column (thread j owns column j)
+    for (int j0 = 0; j0 < n0; j0 += NT_) {
+      const int j = j0 + tid;
+      if (j < n0)
+        bk_solve_column_rt(bptr(i + 1), n1, dd_(i + 1), sd_(i + 1), pm_(i + 1), kd_(i + 1), uptr(i) + (size_t)j * n1,
+                           wk + (size_t)j * n1, uptr(i) + (size_t)j * n1, 1, false);
+    }
+    ctx.sync();
+    // D_i -= S_i U_i
+    {
+      const double *S = Sup(i);
+      for (int e = tid; e < n0 * n0; e += NT_) {
+        const int r = e % n0, c = e / n0;
+        double acc = 0.0;
+        if (S) {
+          for (int k = 0; k < n1; ++k)
+            acc += S[r + (size_t)k * n0] * uptr(i)[k + (size_t)c * n1];
+        } else {
+          acc = -uptr(i)[r + (size_t)c * n1];
+        }
+        bptr(i)[e] -= acc;
+      }
+    }
+    ctx.sync();
+  }
+  if (ok && dm(0) > 0) {
+    if (!bk_factor_group<8>(grp, bptr(0), dm(0), dm(0), dd_(0), sd_(0), pm_(0), kd_(0), pv))
+      ok = false;
+    else
+      solve_vec(0, sol + off(0));
+  }
+  if (ok) {
+    auto fwd_U = [&](double *v) { // v_{i+1} -= U_i v_i   (:130-133)
+      for (int i = 0; i + 1 < NB; ++i) {
+        const int n1 = dm(i + 1), n0 = dm(i);
+        for (int r = tid; r < n1; r += NT_) {
+          double acc = 0.0;
+          for (int k = 0; k < n0; ++k)
+            acc += uptr(i)[r + (size_t)k * n1] * v[off(i) + k];
+          v[off(i + 1) + r] -= acc;
+        }
+        ctx.sync();
+      }
+    };
+    fwd_U(sol);
+    // ---- iterative refinement (parallel-solver.hxx:185-202)
+    for (int it = 0; it < max_refine; ++it) {
+      // err = rhs - A sol  (blockTridiagMatMul with the ORIGINAL blocks, block-tridiagonal.hpp:52-75)
+      for (int b = 0; b < NB; ++b) {
+        const int n = dm(b);
+        const double *Do = Dorig(b);
+        for (int i = tid; i < n; i += NT_) {
+          double acc = 0.0;
+          if (b > 0) { // sub-diagonal block = S_{b-1}^T
+            const double *S = Sup(b - 1);
+            const int c = dm(b - 1);
+            if (S) {
+              for (int k = 0; k < c; ++k)
+                acc += S[k + (size_t)i * c] * sol[off(b - 1) + k];
+            } else {
+              acc += -sol[off(b - 1) + i];
+            }
+          }
+          if (Do)
+            for (int k = 0; k < n; ++k)
+              acc += Do[i + (size_t)k * n] * sol[off(b) + k];
+          if (b + 1 < NB) {
+            const double *S = Sup(b);
+            const int c = dm(b + 1);
+            if (S) {
+              for (int k = 0; k < c; ++k)
+                acc += S[i + (size_t)k * n] * sol[off(b + 1) + k];
+            } else {
+              acc += -sol[off(b + 1) + i];
+            }
+          }
+          err[off(b) + i] = rhs_at(b, i) - acc;
+        }
+      }
+      ctx.sync();
+      double resdl = 0.0; // infinity norm, computed redundantly by every thread
+      for (int i = 0; i < TD; ++i)
+        resdl = fmax(resdl, fabs(err[i]));
+      if (!(resdl > thr)) // (NaN residuals stop the loop as well)
+        break;
+      // blockTridiagRefinementStep (block-tridiagonal.hpp:147-182)
+      for (int i = NB - 2; i >= 0; --i) {
+        solve_vec(i + 1, err + off(i + 1));
+        sub_Sx(i, err + off(i), err + off(i + 1));
+        ctx.sync();
+      }
+      solve_vec(0, err + off(0));
+      fwd_U(err);
+      for (int i = tid; i < TD; i += NT_)
+        sol[i] += err[i];
+      ctx.sync();
+    }
+  } else {
+    st |= ST_CONDENSED_FACTOR_FAILED;
+  }
+  double *cond = p.cond + (size_t)inst * TD;
+  for (int i = tid; i < TD; i += NT_)
+    cond[i] = sol[i];
+  for (int i = tid; i < nx + nc0; i += NT_) // kkt0.ff = [x_0; lbda_0]
+    p.kkt0[(size_t)inst * (nx + nc0) + i] = (i < nx) ? sol[nc0 + i] : sol[i - nx];
+  if (tid == 0) {
+    if (st)
+      ctx.atomic_or(p.status + inst, st);
+    if (p.pivstat && pv)
+      ctx.atomic_add(p.pivstat + inst, pv);
+  }
+  ctx.sync();
+}
+
+// collapseFeedback of the parallel solver (gar/parallel-solver.hpp:41-51): K_0 -= Kth_0 * sub[1],
+// where after the swap of :180-181 sub[1] is the ORIGINAL sub-diagonal block Vxt_0^T.
+template <class Ctx> AB2_D void collapse_feedback(Ctx &ctx, const SweepParams &p, const int nx, const int nu, const int nc, const int inst) {
+  const int N = p.N, nr = nu + nc + nx, nth = nx;
+  double *K = p.fb + (size_t)inst * N * nr * nx;
+  const double *Kth = p.fth + (size_t)inst * N * nr * nth;
+  const double *Vxt0 = p.Vxt + (size_t)inst * (N + 1) * nx * nth; // nx x nth column-major
+  for (int e = ctx.tid; e < nu * nx; e += ctx.nthreads) {
+    const int i = e / nx, j = e % nx;
+    double acc = 0.0;
+    for (int c = 0; c < nth; ++c)
+      acc += Kth[i * nth + c] * Vxt0[j + (size_t)c * nx];
+    K[i * nx + j] -= acc;
   }
 }
 

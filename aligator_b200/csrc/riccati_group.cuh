@@ -92,7 +92,20 @@ struct SweepParams {
   double *kkt0fth;     // [batch][(NX+nc0)*nth]   row-major
   double *thGrad;      // [batch][nth]
   double *thHess;      // [batch][nth*nth]
+  // leg mode (CTA-per-instance kernel only): gar::ParallelRiccatiSolver, gar/parallel-solver.hxx.
+  // legs = T >= 2: the horizon of every instance is cut into T legs [i(N+1)/T, (i+1)(N+1)/T)
+  // (:23-28); a work item of the kernel is one (instance, leg).  nth = nx; records are plain.
+  int legs;
+  double *cond; // [batch][nc0 + nx*(2T-1)]: condensed solution [lbda0, x0, (theta_i, x_{head i+1})...] (:92-112)
 };
+
+// status bits: see ST_*; in leg mode several CTAs report on one instance
+enum : int { ST_CONDENSED_FACTOR_FAILED = 4 };
+
+// leg i of T over a horizon of N stage knots + the terminal knot (get_work, parallel-solver.hxx:23-28)
+AB2_HD int leg_begin(int N, int i, int T) { return (int)((long long)i * (N + 1) / T); }
+// doubles before block b of the condensed vector: blocks [nc0, nx, nx, nx, ...]
+AB2_HD int cond_offset(int b, int nc0, int nx) { return b == 0 ? 0 : nc0 + (b - 1) * nx; }
 
 // ---------------------------------------------------------------------------
 // Compile-time shape of one kernel instantiation.

@@ -74,6 +74,8 @@ def lib():
         L.ab2_gar_forward.argtypes = [C.c_void_p, C.c_void_p]
         L.ab2_gar_sweep.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.ab2_gar_create_parametric.argtypes = [C.POINTER(GarDims), C.c_int, C.POINTER(C.c_void_p)]
+        L.ab2_gar_create_parallel.argtypes = [C.POINTER(GarDims), C.c_int, C.POINTER(C.c_void_p)]
+        L.ab2_gar_collapse_feedback.argtypes = [C.c_void_p, C.c_void_p]
         L.ab2_gar_stage_record_doubles_th.restype = C.c_size_t
         L.ab2_gar_term_record_doubles_th.restype = C.c_size_t
         L.ab2_gar_forward_theta.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -136,15 +138,22 @@ class CudaRiccatiBatch:
     identical dimensions (stage knots (nx,nu,nc), terminal knot (nx,0,nct))."""
 
     def __init__(self, nx, nu, nc, nct, nc0, horizon, batch, device=0, variant=-1, stagger_ns=0,
-                 ctas_per_sm=0, nth=0):
+                 ctas_per_sm=0, nth=0, legs=0):
+        """``legs >= 2``: the parallel-in-time solver (``ab2_gar_create_parallel`` =
+        gar::ParallelRiccatiSolver): plain records, value-function parameters nth = nx."""
         self.dims = GarDims(nx, nu, nc, nct, nc0, horizon, batch, device)
-        self.nth = int(nth)
+        self.legs = int(legs)
+        self.nth = int(nx) if self.legs else int(nth)
         self.h = C.c_void_p()
-        _check(lib().ab2_gar_create_parametric(C.byref(self.dims), self.nth, C.byref(self.h)))
+        if self.legs:
+            _check(lib().ab2_gar_create_parallel(C.byref(self.dims), self.legs, C.byref(self.h)))
+        else:
+            _check(lib().ab2_gar_create_parametric(C.byref(self.dims), self.nth, C.byref(self.h)))
         if variant >= 0 or stagger_ns or ctas_per_sm:
             _check(lib().ab2_gar_set_tuning(self.h, C.byref(GarTuning(variant, stagger_ns, ctas_per_sm))))
-        self.srec = int(lib().ab2_gar_stage_record_doubles_th(nx, nu, nc, self.nth))
-        self.trec = int(lib().ab2_gar_term_record_doubles_th(nx, nct, self.nth))
+        rec_nth = 0 if self.legs else self.nth
+        self.srec = int(lib().ab2_gar_stage_record_doubles_th(nx, nu, nc, rec_nth))
+        self.trec = int(lib().ab2_gar_term_record_doubles_th(nx, nct, rec_nth))
         self._keep = None
 
     def close(self):
@@ -184,6 +193,9 @@ class CudaRiccatiBatch:
             self._keep_theta = th
             _check(lib().ab2_gar_forward_theta(self.h, _ptr(th), AB2_HOST, C.c_void_p(stream)))
             self.synchronize(stream)
+
+    def collapse_feedback(self, stream=0):
+        _check(lib().ab2_gar_collapse_feedback(self.h, C.c_void_p(stream)))
 
     def sweep(self, mueq, stream=0):
         _check(lib().ab2_gar_sweep(self.h, float(mueq), C.c_void_p(stream)))
@@ -508,6 +520,46 @@ class ProximalRiccatiSolver:
         knots = [knot] * len(self.problems) if not isinstance(knot, (list, tuple)) else knot
         rec = np.stack([pack_stage_knot(k, self.batch.srec) for k in knots])
         self.batch.cycle_append(rec)
+        self._cache = {}
+
+
+class ParallelRiccatiSolver(ProximalRiccatiSolver):
+    """Mirror of ``gar::ParallelRiccatiSolver`` (gar/parallel-solver.hpp:21-113) for ONE problem or a
+    batch: ``ParallelRiccatiSolver(problem, num_threads)``.  The horizon is cut into ``num_threads``
+    legs exactly like the reference (get_work, parallel-solver.hxx:23-28); on the device the legs of
+    all instances run as the work items of one launch, followed by the condensed block-tridiagonal
+    solve of every instance and the legs' rollouts.  Unlike the reference the caller's problem is
+    NOT re-parameterised in place (the leg parameterisation is implicit on the device).  Raises
+    like the reference for ``num_threads < 2`` (:42-46); ``forward`` ignores theta (:211)."""
+
+    def __init__(self, problem, num_threads, device=0):
+        self.problems = [problem] if isinstance(problem, LqrProblem) else list(problem)
+        if num_threads < 2:
+            raise GarError("numThreads (%d) should be greater than or equal to 2." % num_threads)
+        p0 = self.problems[0]
+        N = p0.horizon
+        kt = p0.stages[N]
+        if kt.nu != 0 or N < 1:
+            raise GarError("the terminal knot must have nu = 0 and the horizon at least one stage knot")
+        k0 = p0.stages[0]
+        self.nx, self.nu, self.nc, self.nct = kt.nx, k0.nu, k0.nc, kt.nc
+        self.nth = self.nx
+        self.num_threads = int(num_threads)
+        self.batch = CudaRiccatiBatch(self.nx, self.nu, self.nc, self.nct, p0.nc0, N, len(self.problems),
+                                      device, legs=self.num_threads)
+        self._single = isinstance(problem, LqrProblem)
+        self._cache = {}
+
+    def getNumThreads(self):
+        return self.num_threads
+
+    def forward(self, xs, us, vs, lbdas, theta=None):
+        return ProximalRiccatiSolver.forward(self, xs, us, vs, lbdas, None)  # theta ignored (:211)
+
+    def collapseFeedback(self):
+        """parallel-solver.hpp:41-51."""
+        self.batch.collapse_feedback()
+        self.batch.synchronize()
         self._cache = {}
 
 

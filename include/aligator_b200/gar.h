@@ -35,7 +35,8 @@
  *   LBD0 [batch][nc0]    LBDAS [batch][N][nx]  (lbdas[1..N])
  *   STATUS [batch] int   0 = ok, bit0 = a stage LDL^T failed (the reference throws
  *                        "Failed stage LDL factorization", riccati-kernel.hxx:239-241),
- *                        bit1 = the initial-stage factorisation failed.
+ *                        bit1 = the initial-stage factorisation failed,
+ *                        bit2 = (parallel solver) a block of the condensed system failed to factor.
  */
 #ifndef ALIGATOR_B200_GAR_H
 #define ALIGATOR_B200_GAR_H
@@ -131,6 +132,25 @@ size_t ab2_gar_term_record_doubles_th(int nx, int nct, int nth);
 int ab2_gar_forward_theta(ab2_gar_solver *s, const double *theta, int memspace, void *stream);
 int ab2_gar_destroy(ab2_gar_solver *s);
 int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t);
+
+/* Replaces: ParallelRiccatiSolver(LqrProblemTpl&, num_threads), gar/parallel-solver.hxx:32-82 -- the
+ * parallel-in-time variant.  The horizon of EVERY instance is cut into `num_legs` legs
+ * [i(N+1)/T, (i+1)(N+1)/T) (get_work, :23-28); backward() runs the legs of all instances as the work
+ * items of one launch (each leg = the recursion of riccati-kernel.hxx:105-129 on its span, parametric
+ * in the co-state at the next leg's head, nth = nx), then solves the condensed symmetric
+ * block-tridiagonal system of every instance (:85-129, 166-203; block-tridiagonal.hpp:82-182) with at
+ * most 5 refinement steps to 1e-10; forward() rolls the legs out in one launch (:209-243).
+ * Unlike the reference this does NOT mutate the caller's problem (:52-60, :136-147): the records stay
+ * the plain [A|B|f|Q|S|R|q|r|C|D|d] ones, the leg parameterisation (Gx = A^T, Gu = B^T, gamma = f on a
+ * leg's last knot) is implicit.  Outputs: as ab2_gar_create plus FTH/VXT/VTT/VT with nth = nx (zero on
+ * the last leg, which has no parameters).  Status bit2 = a block of the condensed system failed to
+ * factor (the reference ignores that, :176-179).  num_legs < 2 is AB2_ERR_INVALID (the reference
+ * throws, :42-46); horizon + 1 >= num_legs is required. */
+int ab2_gar_create_parallel(const ab2_gar_dims *dims, int num_legs, ab2_gar_solver **out);
+/* Replaces: RiccatiSolverBase::collapseFeedback(), riccati-base.hpp:32 (no-op for the serial solver)
+ * / ParallelRiccatiSolver::collapseFeedback(), parallel-solver.hpp:41-51: K_0 -= Kth_0 * subdiagonal[1]
+ * (restated as written: after the swap at parallel-solver.hxx:180-181 that block is Vxt_0^T). */
+int ab2_gar_collapse_feedback(ab2_gar_solver *s, void *stream);
 
 /* Give the solver the problem data.  Replaces the non-owning `problem_` pointer the
  * reference re-reads at every backward() (proximal-riccati.hpp:46; the knots are

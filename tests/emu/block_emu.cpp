@@ -34,6 +34,8 @@ struct HostBlockCtx {
     wbar->arrive_and_wait();
   }
   void wsync() { wbar->arrive_and_wait(); }
+  void atomic_or(int *q, int v) { *q |= v; }   // (the emulation runs the work items one after another)
+  void atomic_add(int *q, int v) { *q += v; }
   double shfl(double v, int src) {
     xa[lane] = v;
     wbar->arrive_and_wait();
@@ -64,6 +66,7 @@ extern "C" int emu_block_stage_record(int nx, int nu, int nc) {
 }
 
 template <class D> static int run_block(const D &d, int nwarps, const ab2::SweepParams &p);
+template <class F> static void run_cta(int nwarps, size_t smem_doubles, F body);
 
 // the compile-time specialisation (StaticBlockDims) of two small shapes, to execute that
 // instantiation of the code on the CPU
@@ -87,33 +90,75 @@ extern "C" int emu_block_sweep(int nx, int nu, int nc, int nwarps, const ab2::Sw
   return run_block(ab2::make_block_dims(nx, nu, nc, pp->nc0), nwarps, *pp);
 }
 
+// one emulated CTA of 32*nwarps threads running body(ctx, smem)
+template <class F> static void run_cta(int nwarps, size_t smem_doubles, F body) {
+  const int T = 32 * nwarps;
+  std::vector<double> sm(smem_doubles, std::numeric_limits<double>::quiet_NaN());
+  std::barrier<> cta(T);
+  std::vector<std::unique_ptr<std::barrier<>>> wb;
+  for (int w = 0; w < nwarps; ++w)
+    wb.emplace_back(new std::barrier<>(32));
+  std::vector<std::unique_ptr<std::barrier<>>> subs;
+  std::vector<std::barrier<> *> subp;
+  for (int w = 1; w <= nwarps; ++w) {
+    subs.emplace_back(new std::barrier<>(32 * w));
+    subp.push_back(subs.back().get());
+  }
+  std::vector<double> xa(T), xb(T);
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t)
+    th.emplace_back([&, t] {
+      HostBlockCtx ctx{t, T, t / 32, t % 32, nwarps, &cta, subp.data(), wb[t / 32].get(),
+                       xa.data() + 32 * (t / 32), xb.data() + 32 * (t / 32)};
+      body(ctx, sm.data());
+    });
+  for (auto &t : th)
+    t.join();
+}
+
 template <class D> static int run_block(const D &d, int nwarps, const ab2::SweepParams &p) {
   const int nx = d.nx;
   const int T = 32 * nwarps;
   if (nx + 1 > T || d.nk > T || nx + p.nc0 > T || d.nr > T || d.nth > T)
     return 2;
-  for (int inst = 0; inst < p.batch; ++inst) {
-    std::vector<double> sm((size_t)d.s_end, std::numeric_limits<double>::quiet_NaN());
-    std::barrier<> cta(T);
-    std::vector<std::unique_ptr<std::barrier<>>> wb;
-    for (int w = 0; w < nwarps; ++w)
-      wb.emplace_back(new std::barrier<>(32));
-    std::vector<std::unique_ptr<std::barrier<>>> subs;
-    std::vector<std::barrier<> *> subp;
-    for (int w = 1; w <= nwarps; ++w) {
-      subs.emplace_back(new std::barrier<>(32 * w));
-      subp.push_back(subs.back().get());
+  const int legs = p.legs > 1 ? p.legs : 1;
+  for (int item = 0; item < p.batch * legs; ++item)
+    run_cta(nwarps, (size_t)d.s_end,
+            [&](HostBlockCtx &ctx, double *sm) { ab2::riccati_block_sweep(ctx, p, d, item / legs, sm, item % legs); });
+  return 0;
+}
+
+// Leg mode (gar::ParallelRiccatiSolver): legs backward -> condensed solve -> legs forward, as the
+// three launches of the product do it.  mode bit 0: backward + condensed, bit 1: forward, bit 2: collapseFeedback
+extern "C" int emu_block_legs(int nx, int nu, int nc, int nwarps, int mode, const ab2::SweepParams *pp) {
+  ab2::SweepParams p = *pp;
+  if (p.legs < 2 || p.N + 1 < p.legs)
+    return 3;
+  p.nth = nx;
+  const ab2::BlockDims d = ab2::make_block_dims(nx, nu, nc, p.nc0, nx, 0);
+  if (mode & 1) {
+    for (int b = 0; b < p.batch; ++b) {
+      p.status[b] = 0;
+      if (p.pivstat)
+        p.pivstat[b] = 0;
     }
-    std::vector<double> xa(T), xb(T);
-    std::vector<std::thread> th;
-    for (int t = 0; t < T; ++t)
-      th.emplace_back([&, t] {
-        HostBlockCtx ctx{t, T, t / 32, t % 32, nwarps, &cta, subp.data(), wb[t / 32].get(),
-                         xa.data() + 32 * (t / 32), xb.data() + 32 * (t / 32)};
-        ab2::riccati_block_sweep(ctx, p, d, inst, sm.data());
-      });
-    for (auto &t : th)
-      t.join();
+    p.do_bwd = 1;
+    p.do_fwd = 0;
+    if (int rc = run_block(d, nwarps, p))
+      return rc;
+    const int dmax = nx > p.nc0 ? nx : p.nc0;
+    for (int b = 0; b < p.batch; ++b)
+      run_cta((dmax + 31) / 32, (size_t)ab2::condensed_smem_doubles(nx, p.nc0, p.legs),
+              [&](HostBlockCtx &ctx, double *sm) { ab2::condensed_solve(ctx, p, nx, b, sm); });
+  }
+  if (mode & 4)
+    for (int b = 0; b < p.batch; ++b)
+      run_cta(1, 2, [&](HostBlockCtx &ctx, double *) { ab2::collapse_feedback(ctx, p, nx, nu, nc, b); });
+  if (mode & 2) {
+    p.do_bwd = 0;
+    p.do_fwd = 1;
+    if (int rc = run_block(d, nwarps, p))
+      return rc;
   }
   return 0;
 }

@@ -550,30 +550,102 @@ def test_parametric_problems(gar, shape):
         assert gen.rel_fro(L0[b], lb[0]) <= tol and gen.rel_fro(L[b], np.array(lb[1:])) <= tol
 
 
-@pytest.mark.parametrize("shape", [(4, 2, 0, 0, 11, 3), (6, 3, 0, 0, 20, 4), (4, 2, 2, 0, 13, 2)])
-def test_parallel_solver_mirror_on_gpu(gar, shape):
-    """ParallelRiccatiSolver mirror (aligator_b200/parallel.py) with the CUDA leg back end: the legs are
-    parametric problems on the CTA-per-instance kernel, the condensed system is solved on the host;
-    the rollout equals the serial oracle solution."""
-    import copy
-    from aligator_b200 import parallel as par
-    nx, nu, nc, nct, N, J1 = shape
-    mueq = 1e-3 if nc else 1e-8
-    p = gen.generate_batch(77, 1, N, nx, nu, nc, nct)[0]
-    ops = orc.OracleProblem(copy.deepcopy(p))
-    ser = orc.ProximalRiccatiSolver(ops)
-    ser.backward(mueq)
-    sol = orc.OracleSolution(ops)
-    ser.forward(sol)
-    xs_s, us_s, vs_s, ls_s = sol.get()
-    mine = par.ParallelRiccatiSolver(p, J1, par.CudaLegBackend())
-    assert mine.backward(mueq)
+PAR_SHAPES = [  # (nx, nu, nc, nct, N, legs, batch, mueq)
+    (4, 2, 0, 0, 11, 3, 3, 1e-8), (6, 3, 0, 0, 20, 4, 5, 1e-8), (4, 2, 2, 0, 13, 2, 4, 1e-3),
+    (14, 7, 0, 0, 200, 8, 6, 1e-9),   # BASELINE config 4 dims, 8 legs of 25 knots
+    (12, 6, 0, 0, 100, 6, 40, 1e-9),  # config 2 dims, the reference bench's thread count (bench/gar-riccati.cpp:87-90)
+    (5, 3, 2, 2, 9, 3, 3, 1e-2), (7, 3, 0, 0, 7, 8, 2, 1e-8),
+]
+
+
+@pytest.mark.parametrize("shape", PAR_SHAPES)
+def test_parallel_solver_on_device(gar, shape):
+    """gar::ParallelRiccatiSolver on the device (ab2_gar_create_parallel): legs of ALL instances in one
+    launch, condensed block-tridiagonal solve + refinement per instance in a second, legs' rollouts
+    in a third.  Against the oracle's parallel solver (same leg split): every per-knot factor incl. the
+    parametric ones at 1e-10, the rollout at 1e-9; against the serial solution at the reference's own
+    thresholds (tests/gar/parallel.cpp:211-243: 1e-7) and through the KKT residuals of every instance."""
+    nx, nu, nc, nct, N, T, B, mueq = shape
+    probs = gen.generate_batch(90 + nx, B, N, nx, nu, nc, nct)
+    stage, term, G0, g0 = gar.pack_problems(probs)
+    s = gar.CudaRiccatiBatch(nx, nu, nc, nct, nx, N, B, legs=T)
+    s.set_problem(stage, term, G0, g0)
+    s.backward(mueq)
+    s.forward()
+    assert np.all(s.status() == 0)
+    assert s.launch_count() == 3
+    out = {k: s.get(w) for k, w in dict(ff=gar.OUT_FF, fb=gar.OUT_FB, Vxx=gar.OUT_VXX, vx=gar.OUT_VX, fth=gar.OUT_FTH,
+                                        Vxt=gar.OUT_VXT, Vtt=gar.OUT_VTT, vt=gar.OUT_VT, xs=gar.OUT_XS, us=gar.OUT_US,
+                                        vs=gar.OUT_VS, lbd0=gar.OUT_LBD0, lbdas=gar.OUT_LBDAS).items()}
+    kk = s.kkt_error(mueq)
+    assert kk.max() <= 1e-7, kk.max()   # tests/gar/parallel.cpp:211,221
+    for b in sorted({0, B // 2, B - 1}):
+        op = orc.OracleProblem(probs[b].copy())
+        par = orc.ParallelRiccatiSolver(op, T, threaded=False)
+        assert par.backward(mueq)
+        sol = orc.OracleSolution(op)
+        par.forward(sol)
+        for t in range(N):
+            f = par.factor(t)
+            assert gen.rel_fro(out["fb"][b, t], f["fb"]) <= TOL, ("fb", t)
+            assert gen.rel_fro(out["ff"][b, t], f["ff"]) <= TOL, ("ff", t)
+            if f["dims"][4]:
+                assert gen.rel_fro(out["fth"][b, t], f["fth"]) <= TOL, ("fth", t)
+        for t in range(N + 1):
+            f = par.factor(t)
+            assert gen.rel_fro(out["Vxx"][b, t], f["Vxx"]) <= TOL and gen.rel_fro(out["vx"][b, t], f["vx"]) <= TOL
+            if f["dims"][4]:
+                assert gen.rel_fro(out["Vxt"][b, t], f["Vxt"]) <= TOL, ("Vxt", t)
+                assert gen.rel_fro(out["Vtt"][b, t], f["Vtt"]) <= TOL, ("Vtt", t)
+                assert gen.rel_fro(out["vt"][b, t], f["vt"]) <= TOL
+        xs, us, vs, lb = sol.get()
+        assert gen.rel_fro(out["xs"][b], np.stack(xs)) <= 1e-9
+        assert gen.rel_fro(out["us"][b], np.stack(us[:N])) <= 1e-9
+        assert gen.rel_fro(out["lbdas"][b], np.stack(lb[1:])) <= 1e-9
+        ops = orc.OracleProblem(probs[b])
+        ser = orc.ProximalRiccatiSolver(ops)
+        ser.backward(mueq)
+        sols = orc.OracleSolution(ops)
+        ser.forward(sols)
+        xs2, us2, vs2, lb2 = sols.get()
+        assert gen.rel_fro(out["xs"][b], np.stack(xs2)) <= 1e-7
+        assert gen.rel_fro(out["lbdas"][b], np.stack(lb2[1:])) <= 1e-7
+    # collapseFeedback as the reference states it (parallel-solver.hpp:41-51)
+    s.collapse_feedback()
+    fb0 = s.get(gar.OUT_FB)[0, 0, :nu]
+    op = orc.OracleProblem(probs[0].copy())
+    par = orc.ParallelRiccatiSolver(op, T, threaded=False)
+    par.backward(mueq)
+    par.collapseFeedback()
+    assert gen.rel_fro(fb0, par.factor(0)["fb"][:nu]) <= TOL
+    # the fused call and the pipelined host call take the same three launches per (sub-)batch
+    s.sweep(mueq)
+    assert np.array_equal(s.get(gar.OUT_XS), out["xs"])
+    s.close()
+
+
+def test_parallel_solver_python_mirror_and_errors(gar):
+    """The Python mirror of the class (same constructor / call sequence as the reference) and its error
+    behaviour: num_threads < 2 raises (parallel-solver.hxx:42-46)."""
+    nx, nu, N = 6, 3, 20
+    p = gen.generate_batch(5, 1, N, nx, nu, 0, 0)[0]
+    with pytest.raises(gar.GarError):
+        gar.ParallelRiccatiSolver(p, 1)
+    solver = gar.ParallelRiccatiSolver(p, 4)
+    assert solver.getNumThreads() == 4
+    assert solver.backward(1e-9)
     xs = [np.zeros(nx) for _ in range(N + 1)]
     us = [np.zeros(nu) for _ in range(N)]
-    vs = [np.zeros(nc) for _ in range(N)] + [np.zeros(nct)]
-    lb = [np.zeros(p.nc0)] + [np.zeros(nx) for _ in range(N)]
-    mine.forward(xs, us, vs, lb)
-    tol = 1e-7 if nc else 1e-8
-    assert gen.rel_fro(np.array(xs), np.array(xs_s)) <= tol
-    assert gen.rel_fro(np.array(us), np.array(us_s[:N])) <= tol
-    assert gen.rel_fro(np.array(lb[1:]), np.array(ls_s[1:])) <= tol
+    vs = [np.zeros(0) for _ in range(N + 1)]
+    lb = [np.zeros(nx) for _ in range(N + 1)]
+    assert solver.forward(xs, us, vs, lb)
+    ops = orc.OracleProblem(p)
+    ser = orc.ProximalRiccatiSolver(ops)
+    ser.backward(1e-9)
+    sol = orc.OracleSolution(ops)
+    ser.forward(sol)
+    xs2, us2, _, lb2 = sol.get()
+    assert gen.rel_fro(np.stack(xs), np.stack(xs2)) <= 1e-8 and gen.rel_fro(np.stack(us), np.stack(us2)) <= 1e-8
+    assert gen.rel_fro(np.stack(lb), np.stack(lb2)) <= 1e-8
+    solver.collapseFeedback()
+    assert solver.getFeedback(0).shape == (nu + nx, nx)

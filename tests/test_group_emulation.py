@@ -26,7 +26,8 @@ class SweepParams(C.Structure):
                [("status", C.POINTER(C.c_int)), ("pivstat", C.POINTER(C.c_int)), ("stagger_ns", C.c_int),
                 ("num_sms", C.c_int),
                 ("ctas_per_sm", C.c_int), ("dbg", C.c_int), ("nth", C.c_int)] + \
-               [(n, _dp) for n in ("theta", "fth", "Vxt", "Vtt", "vt", "kkt0fth", "thGrad", "thHess")]
+               [(n, _dp) for n in ("theta", "fth", "Vxt", "Vtt", "vt", "kkt0fth", "thGrad", "thHess")] + \
+               [("legs", C.c_int), ("cond", _dp)]
 
 
 def _lib():
