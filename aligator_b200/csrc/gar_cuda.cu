@@ -46,6 +46,74 @@ __global__ void first_step_policy_kernel(const double *__restrict__ fb, const do
   }
 }
 
+// ---------------------------------------------------------------------------
+// Multi-GPU: pack of the first-step policy FUSED with its all-gather over NVLink peer memory.
+// Every rank owns a receive buffer [2][world][batch][nu][nx+1] (two halves, alternating by
+// step) + flag words, mapped into every peer by CUDA IPC.  Rank r's kernel computes each
+// element of its own block once and STORES it into the slot [half][r] of EVERY rank's buffer
+// (peer stores over NVLink / NVSwitch; no NCCL kernel, no staging copy), then the last CTA
+// to finish publishes the step number in every peer's data flag.  Flow control: at the start
+// of step s a rank tells its peers "everything up to s-1 is consumed" (ack flag; the kernel
+// is stream-ordered behind the consumers) and waits until every peer has acknowledged step
+// s-2, whose data the half it is about to overwrite held.
+// ---------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct PeerPtrs {
+  double *buf[kMaxPeers];               // receive buffer of rank w
+  unsigned long long *data_flag[kMaxPeers]; // [world] of rank w: step of the last block received from each sender
+  unsigned long long *ack_flag[kMaxPeers];  // [world] of rank w: last step each peer has finished consuming
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256)
+    policy_allgather_kernel(const double *__restrict__ fb, const double *__restrict__ ff, const PeerPtrs peers,
+                            const int world, const int rank, const int batch, const int N, const int nr, const int nu,
+                            const int nx, const unsigned long long step, unsigned int *done_counter) {
+  const int per = nu * (nx + 1);
+  const long total = (long)batch * per;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) // this rank is done with every step before `step` (stream order)
+      for (int w = 0; w < world; ++w)
+        st_release_sys(peers.ack_flag[w] + rank, step - 1);
+    if (step >= 3) // the half written now held step-2: every peer must have consumed it
+      for (int w = 0; w < world; ++w)
+        while (ld_acquire_sys(peers.ack_flag[rank] + w) + 2 < step)
+          __nanosleep(64);
+  }
+  __syncthreads();
+  const size_t half = (size_t)(step & 1) * world * total;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per), e = (int)(i % per), r = e / (nx + 1), c = e % (nx + 1);
+    const double v = (c < nx) ? fb[((size_t)b * N * nr + r) * nx + c] : ff[(size_t)b * N * nr + r];
+    for (int w = 0; w < world; ++w) // own buffer first-class: w == rank is a local store
+      peers.buf[w][half + (size_t)rank * total + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(done_counter, 1u);
+    if (prev == gridDim.x - 1) { // every CTA's stores are fenced: publish
+      *done_counter = 0;
+      __threadfence_system();
+      for (int w = 0; w < world; ++w)
+        st_release_sys(peers.data_flag[w] + rank, step);
+    }
+  }
+}
+// the stream waits until the blocks of every sender have arrived for `step`
+__global__ void policy_wait_kernel(const unsigned long long *data_flag, const int world, const unsigned long long step) {
+  const int w = threadIdx.x;
+  if (w < world)
+    while (ld_acquire_sys(data_flag + w) < step)
+      __nanosleep(64);
+}
+
 // row-major fb [nr][nx] + ff [nr]  ->  column-major [nr][nx+1] with column 0 = ff, per (instance, knot)
 __global__ void gains_kernel(const double *__restrict__ fb, const double *__restrict__ ff, double *__restrict__ dst,
                              long nrec, int nr, int nx) {
@@ -106,6 +174,14 @@ struct ab2_gar_solver {
   int rec_nth = 0; // parameter blocks carried by the knot records (0 in leg mode)
   int legs = 0;    // >= 2: gar::ParallelRiccatiSolver (leg mode)
   double *cond = nullptr;
+  // fused pack + all-gather over peer memory (multi-GPU)
+  int pg_world = 0, pg_rank = 0;
+  unsigned long long pg_step = 0;
+  void *pg_local = nullptr;          // cudaMalloc: [2][world][batch][per] doubles, then flags
+  void *pg_peer_base[8] = {};        // IPC-opened bases (own entry = pg_local)
+  ab2::PeerPtrs pg_ptrs{};
+  unsigned int *pg_done = nullptr;
+  size_t pg_buf_doubles = 0;
   double *out[AB2_OUT_COUNT] = {};
   size_t out_doubles[AB2_OUT_COUNT] = {};
   size_t out_rec[AB2_OUT_COUNT] = {};  // doubles per knot (or per instance)
@@ -328,6 +404,13 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
     cudaFree(s->status);
   if (s->pivstat)
     cudaFree(s->pivstat);
+  for (int w = 0; w < s->pg_world; ++w)
+    if (w != s->pg_rank && s->pg_peer_base[w])
+      cudaIpcCloseMemHandle(s->pg_peer_base[w]);
+  if (s->pg_local)
+    cudaFree(s->pg_local);
+  if (s->pg_done)
+    cudaFree(s->pg_done);
   for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev, s->cond})
     if (q)
       cudaFree(q);
@@ -893,6 +976,102 @@ int ab2_gar_synchronize(ab2_gar_solver *s, void *stream) {
   CUDA_TRY(cudaSetDevice(s->d.device));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return AB2_OK;
+}
+
+// ---- multi-GPU: fused pack + all-gather of the first-step policy over NVLink peer memory ----
+int ab2_gar_peer_gather_init(ab2_gar_solver *s, int world, int rank, void *ipc_handle_out) {
+  if (!s || !ipc_handle_out || world < 1 || world > ab2::kMaxPeers || rank < 0 || rank >= world)
+    return fail(AB2_ERR_INVALID, "peer_gather_init: bad argument (world <= 8)");
+  if (s->d.horizon < 1)
+    return fail(AB2_ERR_INVALID, "peer_gather needs horizon >= 1");
+  if (s->pg_local)
+    return fail(AB2_ERR_STATE, "peer_gather_init called twice");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  const size_t per = (size_t)s->d.nu * (s->d.nx + 1);
+  s->pg_buf_doubles = 2 * (size_t)world * s->d.batch * per;
+  const size_t bytes = s->pg_buf_doubles * sizeof(double) + 2 * ab2::kMaxPeers * sizeof(unsigned long long);
+  CUDA_TRY(cudaMalloc(&s->pg_local, bytes));
+  CUDA_TRY(cudaMemset(s->pg_local, 0, bytes));
+  CUDA_TRY(cudaMalloc(&s->pg_done, sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(s->pg_done, 0, sizeof(unsigned int)));
+  s->pg_world = world;
+  s->pg_rank = rank;
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, s->pg_local));
+  static_assert(sizeof(h) == 64, "IPC handle size");
+  std::memcpy(ipc_handle_out, &h, sizeof(h));
+  return AB2_OK;
+}
+
+int ab2_gar_peer_gather_connect(ab2_gar_solver *s, const void *all_handles) {
+  if (!s || !all_handles || !s->pg_local)
+    return fail(AB2_ERR_STATE, "peer_gather_connect before peer_gather_init");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  for (int w = 0; w < s->pg_world; ++w) {
+    void *base = s->pg_local;
+    if (w != s->pg_rank) {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, (const char *)all_handles + 64 * (size_t)w, sizeof(h));
+      CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    s->pg_peer_base[w] = base;
+    s->pg_ptrs.buf[w] = (double *)base;
+    unsigned long long *fl = (unsigned long long *)((double *)base + s->pg_buf_doubles);
+    s->pg_ptrs.data_flag[w] = fl;
+    s->pg_ptrs.ack_flag[w] = fl + ab2::kMaxPeers;
+  }
+  return AB2_OK;
+}
+
+int ab2_gar_policy_allgather(ab2_gar_solver *s, void *stream) {
+  if (!s || !s->pg_peer_base[0])
+    return fail(AB2_ERR_STATE, "policy_allgather before peer_gather_connect");
+  if (!s->have_backward)
+    return fail(AB2_ERR_STATE, "policy_allgather before backward()");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  const long total = (long)s->d.batch * s->d.nu * (s->d.nx + 1);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 2)
+    blocks = 148 * 2; // all resident at once: the last-CTA publication never waits on an unscheduled CTA
+  s->pg_step += 1;
+  ab2::policy_allgather_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      s->out[AB2_OUT_FB], s->out[AB2_OUT_FF], s->pg_ptrs, s->pg_world, s->pg_rank, s->d.batch, s->d.horizon, s->nr,
+      s->d.nu, s->d.nx, s->pg_step, s->pg_done);
+  CUDA_TRY(cudaGetLastError());
+  s->launches += 1;
+  return AB2_OK;
+}
+
+int ab2_gar_policy_allgather_wait(ab2_gar_solver *s, void *stream) {
+  if (!s || !s->pg_peer_base[0] || s->pg_step == 0)
+    return fail(AB2_ERR_STATE, "policy_allgather_wait before policy_allgather");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  ab2::policy_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->pg_ptrs.data_flag[s->pg_rank], s->pg_world, s->pg_step);
+  CUDA_TRY(cudaGetLastError());
+  s->launches += 1;
+  return AB2_OK;
+}
+
+int ab2_gar_peer_gather_buffer(ab2_gar_solver *s, double **out, long *step) {
+  if (!s || !out || !s->pg_local)
+    return fail(AB2_ERR_STATE, "peer_gather_buffer before peer_gather_init");
+  const size_t half = (size_t)(s->pg_step & 1) * s->pg_world * s->d.batch * s->d.nu * (s->d.nx + 1);
+  *out = (double *)s->pg_local + half;
+  if (step)
+    *step = (long)s->pg_step;
+  return AB2_OK;
+}
+
+int ab2_gar_pinned_alloc(size_t bytes, void **out) {
+  if (!out)
+    return fail(AB2_ERR_INVALID, "null argument");
+  *out = nullptr;
+  CUDA_TRY(cudaHostAlloc(out, bytes > 0 ? bytes : 1, cudaHostAllocPortable));
+  return AB2_OK;
+}
+void ab2_gar_pinned_free(void *p) {
+  if (p)
+    cudaFreeHost(p);
 }
 
 long ab2_gar_launch_count(const ab2_gar_solver *s) { return s ? s->launches : 0; }

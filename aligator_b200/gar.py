@@ -94,6 +94,11 @@ def lib():
         L.ab2_gar_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ab2_gar_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_pivot_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_peer_gather_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ab2_gar_peer_gather_connect.argtypes = [C.c_void_p, C.c_void_p]
+        L.ab2_gar_policy_allgather.argtypes = [C.c_void_p, C.c_void_p]
+        L.ab2_gar_policy_allgather_wait.argtypes = [C.c_void_p, C.c_void_p]
+        L.ab2_gar_peer_gather_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ab2_gar_cycle_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_synchronize.argtypes = [C.c_void_p, C.c_void_p]
         L.ab2_gar_kernel_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5
@@ -319,6 +324,33 @@ class CudaRiccatiBatch:
         _check(lib().ab2_gar_status(self.h, _ptr(st), AB2_HOST, C.c_void_p(stream)))
         self.synchronize(stream)
         return st
+
+    # ---- multi-GPU: fused pack + all-gather of [K0 | k0] over NVLink peer memory ----
+    def peer_gather_setup(self, dist, rank, world):
+        """Allocate the receive buffer, exchange the CUDA IPC handles over `dist` (any backend)
+        and map every peer's buffer.  All ranks: same batch."""
+        import torch
+        L = lib()
+        h = (C.c_ubyte * 64)()
+        _check(L.ab2_gar_peer_gather_init(self.h, int(world), int(rank), h))
+        mine = bytes(h)
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(allh))
+        _check(L.ab2_gar_peer_gather_connect(self.h, blob))
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def policy_allgather(self, stream=0):
+        _check(lib().ab2_gar_policy_allgather(self.h, C.c_void_p(stream)))
+
+    def policy_allgather_wait(self, stream=0):
+        _check(lib().ab2_gar_policy_allgather_wait(self.h, C.c_void_p(stream)))
+
+    def peer_gather_buffer(self):
+        p, st = C.c_void_p(), C.c_long()
+        _check(lib().ab2_gar_peer_gather_buffer(self.h, C.byref(p), C.byref(st)))
+        return p.value, st.value
 
     def pivot_stats(self, stream=0):
         """(n_2x2, n_interchanges) per instance of the last backward pass (``ab2_gar_pivot_stats``)."""

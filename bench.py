@@ -149,51 +149,161 @@ def cpu_baseline(stage, term, G0, g0, nx, nu, nc, nct, N, target_s=12.0, max_ins
             "ok": bool((bo.status == 1).all())}, bo
 
 
+def _single_instance_cpu_rows(budget_s=4.0):
+    """single-instance CPU rows -- C1 dims (nx6 nu3 N100) and the reference bench's
+    native shape (nx36 nu12 nc32, bench/gar-riccati.cpp:19-22) serial and leg-split with 2/4/6 threads
+    (bench/gar-riccati.cpp:87-90), timed on the oracle's restatement of both solvers."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gen
+    from oracle import gar_oracle as orc
+    rows = []
+    cases = [("c1 nx6 nu3 N100", 6, 3, 0, 100, 1e-11, "conditioned")]
+    for N in (16, 64, 256, 1024):
+        cases.append(("native nx36 nu12 nc32 N%d" % N, 36, 12, 32, N, 1e-11, "reference"))
+    per = budget_s / (len(cases) * 4)
+    for name, nx, nu, nc, N, mu, style in cases:
+        rng = np.random.default_rng(7)
+        prob = gen.generate_lq_problem(rng, rng.standard_normal(nx), N, nx, nu, 0, nc, singular=(style == "reference"),
+                                       conditioned=(style != "reference"), control_rows=False)
+        for threads in (1, 2, 4, 6):
+            op = orc.OracleProblem(prob.copy())
+            if threads == 1:
+                sv = orc.ProximalRiccatiSolver(op)
+            else:
+                if N + 1 < threads:
+                    continue
+                sv = orc.ParallelRiccatiSolver(op, threads, threaded=True)
+            sol = orc.OracleSolution(op)
+            sv.backward(mu)
+            sv.forward(sol)  # warm-up
+            reps, t0 = 0, time.perf_counter()
+            while True:
+                sv.backward(mu)
+                sv.forward(sol)
+                reps += 1
+                dt = time.perf_counter() - t0
+                if dt >= per or reps >= 2000:
+                    break
+            rows.append({"case": name, "threads": threads, "ms_per_sweep": 1e3 * dt / reps,
+                         "knots_per_s": (N + 1) * reps / dt})
+    return rows
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU algorithm (oracle port; the reference
-    cannot be compiled in this image) on the box's host cores, same workload/metric."""
+    cannot be compiled in this image) on the box's host cores, same workload/metric.
+    One step = one sweep over a bounded sample of the workload (1024 of its instances); the
+    figure is the MEDIAN of 5 timed repeats, each of max(--steps, 0.7 s worth of) steps, so a
+    single slow repeat (thread start-up, a noisy neighbour) does not move it."""
     if rank != 0:
         return
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
-    nb = 256
+    nb = min(1024, BATCH)
     stage, term, G0, g0 = [a.numpy() for a in synth_batch_torch(torch, nb, HORIZON, NX, NU, "cpu", 1234, NC)]
     from oracle import gar_oracle as orc
     bo = orc.BatchedOracle(NX, NU, NC, NCT, NX, HORIZON, nb, stage, term, G0, g0)
     # every host core (torchrun exports OMP_NUM_THREADS=1 to its workers: ask explicitly)
-    threads = max(orc.num_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity")
-                  else (os.cpu_count() or 1))
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(orc.num_threads(), avail)
     # warm-up: W sweeps and at least 1.5 s (the worker threads' first sweeps run far below the
     # sustained pace: thread start-up, allocator arenas, first touch)
     t1, tw, nw = 1e9, 0.0, 0
     while nw < max(args.warmup, 1) or tw < 1.5:
         dt = bo.sweep(MUEQ, reps=1, nthreads=threads)
         t1, tw, nw = min(t1, dt), tw + dt, nw + 1
-    if args.ref_seconds > 0:  # bounded sample sized in seconds (used for cpu_baseline)
-        t, steps = 0.0, 0
-        chunk = max(1, int(1.0 / max(t1, 1e-5)))  # about a second of sweeps at a time
-        while t < args.ref_seconds:  # (the sustained pace is well below a lone sweep's)
-            t += bo.sweep(MUEQ, reps=chunk, nthreads=threads)
-            steps += chunk
-        args.steps = steps
-    else:
-        t = bo.sweep(MUEQ, reps=args.steps, nthreads=threads)
-    knots = nb * (HORIZON + 1) * args.steps
-    v = knots / t
+    repeat_s = max(0.7, args.ref_seconds / 5.0)
+    steps = max(args.steps, int(repeat_s / max(t1, 1e-5)) + 1)
+    rates, total_t = [], 0.0
+    for _ in range(5):
+        t = bo.sweep(MUEQ, reps=steps, nthreads=threads)
+        total_t += t
+        rates.append(nb * (HORIZON + 1) * steps / t)
+    rates.sort()
+    v = rates[2]
+    assert bool((bo.status == 1).all())
+    cpu = {"value": v, "unit": "knots/s", "cores": threads, "kind": "port",
+           "min": rates[0], "max": rates[-1], "repeats": 5,
+           "sample": "%d of %d instances per step, 5 repeats x %d steps (%.1f s in all), OpenMP over instances on %d "
+                     "threads (%d cores visible), median of the repeats" % (nb, BATCH, steps, total_t, threads, avail)}
+    if args.cpu_extra:
+        try:
+            cpu["single_instance"] = _single_instance_cpu_rows()
+        except Exception as e:  # the extra rows never break the arm
+            cpu["single_instance"] = "failed: %r" % (e,)
     line = {"metric": "riccati_knots_per_sec", "value": v, "unit": "knots/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "steps": steps * 5, "warmup": nw, "ms_per_step": 1e3 * total_t / (5 * steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD, "step_sample": "%d instances per step" % nb,
                        "mueq": MUEQ, "note": "reference cannot be built here (no Eigen); "
                        "restated C++ port of gar::ProximalRiccatiSolver, OpenMP over instances"},
-            "cpu_baseline": {"value": v, "unit": "knots/s", "cores": threads, "kind": "port",
-                             "sample": "%d instances x %d sweeps (%.1f s), OpenMP over instances, %d threads"
-                                       % (nb, args.steps, t, threads)},
+            "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": "knots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def parity_sample(gar, solver, stage, term, G0, g0, nsamp=16):
+    """Correctness gate printed with every timing: max over (instance, t) of the
+    relative Frobenius error of K_t, k_t, Vxx_t of `nsamp` instances spread over the batch against the CPU
+    oracle on the same inputs.  Outside the timed region."""
+    import numpy as np
+    from oracle import gar_oracle as orc
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gen
+    B, N = stage.shape[0], HORIZON
+    idx = sorted(set(int(round(i * (B - 1) / max(nsamp - 1, 1))) for i in range(nsamp)))
+    h = [a[idx].cpu().numpy() for a in (stage, term, G0, g0)]
+    bo = orc.BatchedOracle(NX, NU, NC, NCT, NX, N, len(idx), *h)
+    bo.sweep(MUEQ)
+    ref = bo.get()
+    worst = {"K": 0.0, "k": 0.0, "Vxx": 0.0}
+    nr = NU + NC + NX
+    for j, b in enumerate(idx):
+        fb = np.empty(N * nr * NX)
+        ff = np.empty(N * nr)
+        V = np.empty((N + 1) * NX * NX)
+        solver.get_range_into(gar.OUT_FB, b, 1, 0, N, fb, gar.AB2_HOST)
+        solver.get_range_into(gar.OUT_FF, b, 1, 0, N, ff, gar.AB2_HOST)
+        solver.get_range_into(gar.OUT_VXX, b, 1, 0, N + 1, V, gar.AB2_HOST)
+        solver.synchronize()
+        fb, ff = fb.reshape(N, nr, NX), ff.reshape(N, nr)
+        V = V.reshape(N + 1, NX, NX).transpose(0, 2, 1)
+        for t in range(N):
+            worst["K"] = max(worst["K"], gen.rel_fro(fb[t, :NU], ref["fb"][j, t, :NU]))
+            worst["k"] = max(worst["k"], gen.rel_fro(ff[t, :NU], ref["ff"][j, t, :NU]))
+        for t in range(N + 1):
+            worst["Vxx"] = max(worst["Vxx"], gen.rel_fro(V[t], ref["Vxx"][j, t]))
+    tolk = max(1e-10, 2.4e-16 / MUEQ) if NC > 0 else 1e-10
+    worst.update({"instances": len(idx), "tolerance": 1e-10, "tolerance_K_constrained": tolk,
+                  "ok": bool(worst["Vxx"] <= 1e-10 and worst["K"] <= tolk and worst["k"] <= tolk),
+                  "against": "oracle/gar_oracle (CPU restatement of the reference; parity unpinned)"})
+    return worst
+
+
+def bind_to_gpu_numa(local):
+    """Pin this process to the CPUs closest to its GPU (NVML's ideal-CPU mask = the GPU's NUMA node)
+    BEFORE any pinned host memory is allocated, so the e2e staging buffers land on that node (first
+    touch) and the 8 ranks do not all pull through one socket's PCIe root."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1 and 64 * w + b < ncpu]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"bound": True, "cpus": len(cpus), "first": cpus[0], "last": cpus[-1]}
+        return {"bound": False, "why": "empty affinity mask"}
+    except Exception as e:
+        return {"bound": False, "why": repr(e)[:80]}
 
 
 def main():
@@ -213,6 +323,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--ref-seconds", type=float, default=0.0)
+    ap.add_argument("--cpu-extra", action="store_true", help="single-instance CPU rows (BASELINE.md section 4)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--strong", default="c4", help="also time this config's FULL batch split over the ranks (none = skip)")
+    ap.add_argument("--strong-legs", type=int, default=0, help="parallel-in-time legs for the strong-scaling run")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="the one exchange: fused pack + NVLink peer-memory all-gather, or pack kernel + ncclAllGather")
     args = ap.parse_args()
     if args.config != "c2":
         NX, NU, NC, NCT, HORIZON, BATCH, MUEQ, WORKLOAD = CONFIGS[args.config]
@@ -231,6 +347,7 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    numa = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -261,10 +378,26 @@ def main():
     step_no = [0]
 
     from aligator_b200 import sharding
+    peer = world > 1 and args.gather == "peer"
+    if peer:
+        solver.peer_gather_setup(dist, rank, world)
+    waited = [None]
 
     def step():
         solver.sweep(MUEQ, stream=stream)
-        if world > 1:  # the one exchange: all-gather of the first-step policy [K0 | k0]
+        if peer:
+            # the one exchange, fused: the pack kernel stores [K0 | k0] straight into every rank's
+            # receive buffer over NVLink (no NCCL kernel); arrival is awaited on the side stream,
+            # overlapping the next sweep; the next pack waits for that (its ack says "consumed")
+            if waited[0] is not None:
+                main.wait_event(waited[0])
+            solver.policy_allgather(stream=stream)
+            side.wait_stream(main)
+            solver.policy_allgather_wait(stream=side.cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            waited[0] = ev
+        elif world > 1:  # the one exchange: all-gather of the first-step policy [K0 | k0]
             i = step_no[0] & 1
             step_no[0] += 1
             if gathered[i] is not None:
@@ -351,10 +484,67 @@ def main():
                "api": "ab2_gar_sweep_host: upload/sweep/download pipelined over batch slices"}
         s2.close()
 
+    # ---- strong scaling: the FULL batch of BASELINE config 4 (nx14 nu7 N200, 2048 instances) split over
+    # the ranks (2048 -> 1024/512/256 per GPU), same fused exchange; every rank measures ----
+    strong = None
+    if args.strong in CONFIGS:
+        snx, snu, snc, snct, sN, sB, smu, swl = CONFIGS[args.strong]
+        b0, b1 = sharding.shard_range(sB, rank, world)
+        sb = b1 - b0
+        sst = synth_batch_torch(torch, sb, sN, snx, snu, dev, 4321 + rank, snc)
+        s3 = gar.CudaRiccatiBatch(snx, snu, snc, snct, snx, sN, sb, device=local, legs=args.strong_legs)
+        s3.set_problem(*sst, memspace=gar.AB2_DEVICE, stream=stream)
+        speer = world > 1 and args.gather == "peer" and sb * world == sB
+        if speer:
+            s3.peer_gather_setup(dist, rank, world)
+        sw = [None]
+
+        def sstep():
+            s3.sweep(smu, stream=stream)
+            if speer:
+                if sw[0] is not None:
+                    main.wait_event(sw[0])
+                s3.policy_allgather(stream=stream)
+                side.wait_stream(main)
+                s3.policy_allgather_wait(stream=side.cuda_stream)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                sw[0] = ev
+
+        for _ in range(max(args.warmup, 3)):
+            sstep()
+        join()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            sstep()
+        join()
+        f1.record()
+        barrier()
+        t3 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        sms = float(t3.item()) / args.steps
+        ok3 = int(s3.status().max()) == 0
+        strong = {"workload": swl + " -- TOTAL batch %d split over %d GPU(s)" % (sB, world), "scaling": "strong",
+                  "batch_per_gpu": sb, "legs": args.strong_legs, "ms_per_step": sms,
+                  "value": sB * (sN + 1) / (sms * 1e-3), "unit": "knots/s", "ok": ok3,
+                  "exchange": "fused pack + NVLink peer all-gather of [K0|k0]" if speer else ("none" if world == 1 else "nccl/none"),
+                  "kernel": s3.kernel_info()}
+        s3.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_sample(gar, solver, stage, term, G0, g0)
+        except Exception as e:
+            parity = {"ok": False, "error": repr(e)}
 
     # ---- roofline of the (single) kernel ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -365,11 +555,13 @@ def main():
     bpk = bytes_per_knot(NX, NU, NC)
     kernel_ms = ms_per_step  # one launch per step; the all-gather (N>1) is outside this figure at N=1
     achieved = B * (N + 1) * bpk / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = None  # ncu dram bytes per launch of THIS config's kernel (profiles/traffic.json), else null
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            ent = json.load(open(tp)).get(args.config)
+            if ent and ent.get("batch") == B:
+                traffic = ent.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -383,7 +575,7 @@ def main():
         # competes with the oracle's thread pool (measured 5x slower), which would flatter
         # the GPU.  Same code path as `--impl reference`, sized to ~12 s of CPU work.
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
-                            "--config", args.config, "--warmup", "2", "--ref-seconds", "12"],
+                            "--config", args.config, "--warmup", "2", "--ref-seconds", "12", "--cpu-extra"],
                            capture_output=True, text=True)
         try:
             cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
@@ -400,9 +592,11 @@ def main():
                        "generator": "SURVEY 8(d) conditioned variant, counter-seeded per rank",
                        "l2": "inputs+outputs per sweep (%.2f GB) exceed the 126 MB L2; no flush needed"
                              % ((stage.numel() * 8 + B * (N + 1) * 8 * ((NU + NC + NX) * (NX + 1) + NX * NX + NX)) / 1e9),
-                       "kernel": solver.kernel_info(), "variant": args.variant},
+                       "kernel": solver.kernel_info(), "variant": args.variant, "numa": numa,
+                       "exchange": ("fused pack + NVLink peer-memory all-gather of [K0|k0] (no NCCL on the data path)"
+                                    if peer else ("ncclAllGather of [K0|k0]" if world > 1 else "none (1 GPU)"))},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e,
-            "gpu_launches": launches}
+            "gpu_launches": launches, "parity": parity, "strong": strong}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

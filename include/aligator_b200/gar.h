@@ -241,6 +241,23 @@ int ab2_gar_get_gains(ab2_gar_solver *s, double *dst, int memspace, void *stream
  * the device (one warp per (instance, knot)); dst in host or device memory. */
 int ab2_gar_kkt_error(ab2_gar_solver *s, double mueq, double *dst, int memspace, void *stream);
 int ab2_gar_device_ptr(ab2_gar_solver *s, int what, double **out);
+
+/* Multi-GPU (one process per GPU, the batch sharded by instance): the ONE exchange
+ * of a sweep -- the all-gather of the first-step policy [K_0 | k_0] -- fused with its pack kernel over
+ * NVLink peer memory instead of a separate NCCL collective.  Every rank owns a receive buffer
+ * [world][batch][nu][nx+1] (double-buffered by step) that all peers map through CUDA IPC; the pack
+ * kernel of rank r stores each element straight into slot r of every rank's buffer and publishes a
+ * step flag (release/acquire at system scope) when its last CTA is done.
+ *   init:      allocate the local buffer; *ipc_handle_out = 64 bytes to hand to every peer
+ *   connect:   all_handles = world x 64 bytes, rank order (exchange them with any host transport)
+ *   allgather: enqueue pack+scatter of the current factors on `stream` (all ranks, same batch)
+ *   wait:      `stream` waits until the blocks of every rank have arrived for the last allgather
+ *   buffer:    device address of the half holding the last allgather, [world][batch][nu][nx+1] */
+int ab2_gar_peer_gather_init(ab2_gar_solver *s, int world, int rank, void *ipc_handle_out);
+int ab2_gar_peer_gather_connect(ab2_gar_solver *s, const void *all_handles);
+int ab2_gar_policy_allgather(ab2_gar_solver *s, void *stream);
+int ab2_gar_policy_allgather_wait(ab2_gar_solver *s, void *stream);
+int ab2_gar_peer_gather_buffer(ab2_gar_solver *s, double **out, long *step);
 /* Per-instance status words (layout above). */
 int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream);
 /* Pivot statistics of the last backward pass, one int per instance: bits 0-14 = number of
@@ -258,6 +275,11 @@ int ab2_gar_pivot_stats(ab2_gar_solver *s, int *dst, int memspace, void *stream)
 int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace, void *stream);
 
 int ab2_gar_synchronize(ab2_gar_solver *s, void *stream);
+/* Page-locked host memory for the buffers handed to set_problem / get / sweep_host: copies to and
+ * from it are asynchronous (what the reference's mimalloc arena is to its hot loop,
+ * solver-proxddp.hpp:177-178: allocate once, never in the loop).  free(NULL) is a no-op. */
+int ab2_gar_pinned_alloc(size_t bytes, void **out);
+void ab2_gar_pinned_free(void *p);
 /* Kernels launched by this solver since creation (for bench accounting). */
 long ab2_gar_launch_count(const ab2_gar_solver *s);
 /* Shared memory per CTA / registers etc. of the kernel serving this solver

@@ -112,6 +112,44 @@ inline void lqrInitializeSolution(const LqrProblem &p, std::vector<VectorXs> &xs
     us.pop_back();
 }
 
+/// Page-locked host buffer of doubles (ab2_gar_pinned_alloc): copies to / from it are truly
+/// asynchronous, so backward() overlaps its uploads and downloads on the stream.
+class PinnedBuf {
+public:
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf &) = delete;
+  PinnedBuf &operator=(const PinnedBuf &) = delete;
+  ~PinnedBuf() { ab2_gar_pinned_free(p_); }
+  void assign(size_t n, double v) {
+    if (n != n_) {
+      ab2_gar_pinned_free(p_);
+      p_ = nullptr;
+      n_ = 0;
+      if (n) {
+        void *q = nullptr;
+        if (ab2_gar_pinned_alloc(n * sizeof(double), &q) != AB2_OK)
+          throw RuntimeError(std::string("aligator_b200: ") + ab2_gar_last_error());
+        p_ = static_cast<double *>(q);
+        n_ = n;
+      }
+    }
+    for (size_t i = 0; i < n_; ++i)
+      p_[i] = v;
+  }
+  void resize(size_t n) {
+    if (n != n_)
+      assign(n, 0.0);
+  }
+  double *data() const { return p_; }
+  double *begin() const { return p_; }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+
+private:
+  double *p_ = nullptr;
+  size_t n_ = 0;
+};
+
 /// Drop-in for gar::ProximalRiccatiSolver backed by the B200 sweep.  Constructed from
 /// one problem (batch = 1, the reference's use) or from `batch` problems of identical
 /// dimensions.  Keeps NON-owning pointers to the problems and re-reads them at every
@@ -122,6 +160,11 @@ public:
       : CudaRiccatiSolver(std::vector<const LqrProblem *>{&problem}, device) {}
 
   explicit CudaRiccatiSolver(std::vector<const LqrProblem *> problems, int device = 0)
+      : CudaRiccatiSolver(std::move(problems), device, 0) {}
+
+protected:
+  /// num_legs >= 2: the parallel-in-time solver (ab2_gar_create_parallel)
+  CudaRiccatiSolver(std::vector<const LqrProblem *> problems, int device, int num_legs)
       : problems_(std::move(problems)) {
     if (problems_.empty() || problems_[0]->stages.empty())
       throw RuntimeError("empty problem");
@@ -138,7 +181,7 @@ public:
     dims_.horizon = N;
     dims_.batch = (int)problems_.size();
     dims_.device = device;
-    check(ab2_gar_create(&dims_, &h_));
+    check(num_legs ? ab2_gar_create_parallel(&dims_, num_legs, &h_) : ab2_gar_create(&dims_, &h_));
     srec_ = ab2_gar_stage_record_doubles(dims_.nx, dims_.nu, dims_.nc);
     trec_ = ab2_gar_term_record_doubles(dims_.nx, dims_.nct);
     const int nr = dims_.nu + dims_.nc + dims_.nx;
@@ -151,6 +194,8 @@ public:
     ffT_.assign((size_t)dims_.batch * dims_.nct, 0.);
     fbT_.assign((size_t)dims_.batch * dims_.nct * dims_.nx, 0.);
   }
+
+public:
   ~CudaRiccatiSolver() override { ab2_gar_destroy(h_); }
   CudaRiccatiSolver(const CudaRiccatiSolver &) = delete;
   CudaRiccatiSolver &operator=(const CudaRiccatiSolver &) = delete;
@@ -239,7 +284,7 @@ private:
     if (rc != AB2_OK)
       throw RuntimeError(std::string("aligator_b200: ") + ab2_gar_last_error());
   }
-  static double *put(double *dst, const std::vector<double> &src, size_t n, const char *name) {
+  template <class Vec> static double *put(double *dst, const Vec &src, size_t n, const char *name) {
     if (src.size() != n)
       throw RuntimeError(std::string("knot field has the wrong size: ") + name);
     for (size_t i = 0; i < n; ++i)
@@ -292,7 +337,7 @@ private:
     vsT_.resize((size_t)B * dims_.nct);
     l0_.resize((size_t)B * dims_.nc0);
     ls_.resize((size_t)B * N * dims_.nx);
-    auto get = [&](int what, std::vector<double> &v) {
+    auto get = [&](int what, PinnedBuf &v) {
       if (!v.empty())
         check(ab2_gar_get(h_, what, v.data(), AB2_HOST, nullptr));
     };
@@ -322,9 +367,47 @@ private:
   ab2_gar_dims dims_{};
   ab2_gar_solver *h_ = nullptr;
   size_t srec_ = 0, trec_ = 0;
-  std::vector<double> stage_, term_, G0_, g0_;
-  std::vector<double> ff_, fb_, ffT_, fbT_;
-  mutable std::vector<double> xs_, us_, vs_, vsT_, l0_, ls_;
+  // pinned staging: uploads and downloads are asynchronous on the stream, one synchronisation per call
+  PinnedBuf stage_, term_, G0_, g0_;
+  PinnedBuf ff_, fb_, ffT_, fbT_;
+  mutable PinnedBuf xs_, us_, vs_, vsT_, l0_, ls_;
+
+protected:
+  void refetch_gains() {
+    check(ab2_gar_get(h_, AB2_OUT_FF, ff_.data(), AB2_HOST, nullptr));
+    check(ab2_gar_get(h_, AB2_OUT_FB, fb_.data(), AB2_HOST, nullptr));
+    check(ab2_gar_synchronize(h_, nullptr));
+  }
+};
+
+/// Drop-in for gar::ParallelRiccatiSolver (gar/parallel-solver.hpp:21-113): same constructor
+/// (problem, num_threads), same six virtuals.  The legs of the horizon run as work items of one
+/// launch on the device, the condensed block-tridiagonal system is solved there too.  Throws like
+/// the reference for num_threads < 2 (parallel-solver.hxx:42-46).  Unlike the reference it does
+/// not re-parameterise the caller's problem in place.
+class CudaParallelRiccatiSolver : public CudaRiccatiSolver {
+public:
+  CudaParallelRiccatiSolver(const LqrProblem &problem, const uint num_threads, int device = 0)
+      : CudaRiccatiSolver(std::vector<const LqrProblem *>{&problem}, device, check_threads(num_threads)),
+        numThreads_(num_threads) {}
+  CudaParallelRiccatiSolver(std::vector<const LqrProblem *> problems, const uint num_threads, int device = 0)
+      : CudaRiccatiSolver(std::move(problems), device, check_threads(num_threads)), numThreads_(num_threads) {}
+  uint getNumThreads() const noexcept { return numThreads_; }
+  /// parallel-solver.hpp:41-51
+  void collapseFeedback() override {
+    if (ab2_gar_collapse_feedback(handle(), nullptr) != AB2_OK)
+      throw RuntimeError(std::string("aligator_b200: ") + ab2_gar_last_error());
+    refetch_gains();
+  }
+
+private:
+  static int check_threads(uint n) {
+    if (n < 2)
+      throw RuntimeError("(CudaParallelRiccatiSolver) numThreads (" + std::to_string(n) +
+                         ") should be greater than or equal to 2.");
+    return (int)n;
+  }
+  uint numThreads_;
 };
 
 } // namespace gar

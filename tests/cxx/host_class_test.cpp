@@ -100,8 +100,44 @@ static int check_one(unsigned nx, unsigned nu, unsigned nc, int N, double mueq, 
   return worst <= 1e-10 ? 0 : 5;
 }
 
+// tests/gar/parallel.cpp:190-243: serial reference solver vs the parallel solver on the same problem
+static int check_parallel(unsigned nx, unsigned nu, int N, unsigned num_threads, double mueq, unsigned seed) {
+  std::mt19937 rng(seed);
+  ab::LqrProblem prob = random_problem(rng, nx, nu, 0, N);
+  std::vector<ab::VectorXs> xs, us, vs, lbdas, xr, ur, vr, lr;
+  ab::lqrInitializeSolution(prob, xs, us, vs, lbdas);
+  ab::lqrInitializeSolution(prob, xr, ur, vr, lr);
+  ab::CudaRiccatiSolver ref(prob);
+  ref.backward(mueq);
+  ref.forward(xr, ur, vr, lr);
+  ab::CudaParallelRiccatiSolver par(prob, num_threads);
+  if (par.getNumThreads() != num_threads) return 16;
+  par.backward(mueq);
+  par.forward(xs, us, vs, lbdas);
+  double xerr = 0, lerr = 0;
+  for (int t = 0; t <= N; ++t) {
+    for (unsigned i = 0; i < nx; ++i) xerr = std::max(xerr, std::fabs(xs[t][i] - xr[t][i]));
+    for (size_t i = 0; i < lbdas[t].size(); ++i) lerr = std::max(lerr, std::fabs(lbdas[t][i] - lr[t][i]));
+  }
+  orc::Problem op = to_oracle(prob);
+  orc::Solution sol = orc::lqrInitializeSolution(op);
+  sol.xs = xs; sol.us = us; sol.vs = vs; sol.lbdas = lbdas;
+  const orc::KktError e = orc::lqrComputeKktError(op, sol, mueq, nullptr);
+  std::printf("parallel nx=%u nu=%u N=%d legs=%u: xerr %.2e lerr %.2e KKT max %.2e\n", nx, nu, N, num_threads, xerr, lerr,
+              e.max());
+  par.collapseFeedback();
+  try {
+    ab::CudaParallelRiccatiSolver bad(prob, 1); // parallel-solver.hxx:42-46 throws
+    return 32;
+  } catch (const aligator_b200::RuntimeError &) {
+  }
+  return (xerr <= 1e-7 && lerr <= 1e-7 && e.max() <= 1e-7) ? 0 : 8; // TOL of tests/gar/parallel.cpp:193
+}
+
 int main() {
   int rc = 0;
+  rc |= check_parallel(6, 3, 50, 4, 1e-9, 11);
+  rc |= check_parallel(14, 7, 100, 6, 1e-9, 12);
   rc |= check_one(2, 2, 0, 8, 1e-14, 1);
   rc |= check_one(6, 3, 0, 100, 1e-8, 2);
   rc |= check_one(12, 6, 0, 100, 1e-11, 3);

@@ -649,3 +649,20 @@ def test_parallel_solver_python_mirror_and_errors(gar):
     assert gen.rel_fro(np.stack(lb), np.stack(lb2)) <= 1e-8
     solver.collapseFeedback()
     assert solver.getFeedback(0).shape == (nu + nx, nx)
+
+
+def test_peer_memory_policy_allgather_two_gpus(gar):
+    """Fused pack + NVLink peer-memory all-gather (ab2_gar_policy_allgather) == pack + ncclAllGather, on 2
+    ranks (skipped on a single-GPU box; the driver's 1-GPU test run cannot exercise it)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(root, "tools", "gpu", "peer_gather_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER_GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
