@@ -47,7 +47,7 @@ def build(verbose=False, force=False, ptxas_v=False):
     hdrs = [os.path.join(CSRC, f) for f in ("riccati_group.cuh", "riccati_launch.cuh", "riccati_configs.h")]
     hdrs.append(os.path.join(PKG, "..", "include", "aligator_b200", "gar.h"))
     hdrs_block = hdrs + [os.path.join(CSRC, f) for f in ("riccati_block.cuh", "riccati_block_launch.h",
-                                                          "lq_assemble.h", "kkt_error.h")]
+                                                          "lq_assemble.h", "kkt_error.h", "linesearch.h")]
     extra = ["-Xptxas", "-v"] if ptxas_v else []
     jobs = []
     for (nx, nu, nc, g) in configs():
@@ -69,6 +69,9 @@ def build(verbose=False, force=False, ptxas_v=False):
     jobs.append((obj, [NVCC] + ARCH + FLAGS + extra + ["-c", src, "-o", obj]))
     src = os.path.join(CSRC, "lq_assemble.cu")
     obj = os.path.join(OBJ, "assemble_%s.o" % _digest([hdrs[-1], os.path.join(CSRC, "lq_assemble.h"), src], str(extra)))
+    jobs.append((obj, [NVCC] + ARCH + FLAGS + extra + ["-c", src, "-o", obj]))
+    src = os.path.join(CSRC, "linesearch.cu")
+    obj = os.path.join(OBJ, "linesearch_%s.o" % _digest([os.path.join(CSRC, "linesearch.h"), src], str(extra)))
     jobs.append((obj, [NVCC] + ARCH + FLAGS + extra + ["-c", src, "-o", obj]))
     todo = [(o, c) for (o, c) in jobs if force or not os.path.exists(o)]
     logs = []

@@ -16,6 +16,7 @@
 
 #include "../../include/aligator_b200/gar.h"
 #include "kkt_error.h"
+#include "linesearch.h"
 #include "lq_assemble.h"
 #include "riccati_block_launch.h"
 #include "riccati_configs.h"
@@ -23,26 +24,15 @@
 
 namespace ab2 {
 
-// cycleAppend support: shift the per-knot records of every instance one knot left.
-__global__ void shift_left_kernel(double *base, long inst_stride, int nrec, int rec, int last_zero) {
-  double *b = base + (size_t)blockIdx.x * inst_stride;
-  for (int t = 0; t + 1 < nrec; ++t) {
-    for (int i = threadIdx.x; i < rec; i += blockDim.x)
-      b[(size_t)t * rec + i] = b[(size_t)(t + 1) * rec + i];
-    __syncthreads();
-  }
-  if (last_zero && nrec > 0)
-    for (int i = threadIdx.x; i < rec; i += blockDim.x)
-      b[(size_t)(nrec - 1) * rec + i] = 0.0;
-}
-
 // [K_0 | k_0] of every instance -> dst [batch][nu][nx+1]
+// (head: physical slot of stage knot 0 in the factor arrays, non-zero only between a cycleAppend and the next backward)
 __global__ void first_step_policy_kernel(const double *__restrict__ fb, const double *__restrict__ ff,
-                                         double *__restrict__ dst, int batch, int N, int nr, int nu, int nx) {
+                                         double *__restrict__ dst, int batch, int N, int nr, int nu, int nx, int head) {
   const int per = nu * (nx + 1);
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)batch * per; i += (long)gridDim.x * blockDim.x) {
     const int b = (int)(i / per), e = (int)(i % per), r = e / (nx + 1), c = e % (nx + 1);
-    dst[i] = (c < nx) ? fb[((size_t)b * N * nr + r) * nx + c] : ff[(size_t)b * N * nr + r];
+    const size_t k0 = ((size_t)b * N + head) * nr + r;
+    dst[i] = (c < nx) ? fb[k0 * nx + c] : ff[k0];
   }
 }
 
@@ -116,10 +106,15 @@ __global__ void policy_wait_kernel(const unsigned long long *data_flag, const in
 
 // row-major fb [nr][nx] + ff [nr]  ->  column-major [nr][nx+1] with column 0 = ff, per (instance, knot)
 __global__ void gains_kernel(const double *__restrict__ fb, const double *__restrict__ ff, double *__restrict__ dst,
-                             long nrec, int nr, int nx) {
+                             long nrec, int nr, int nx, int N, int head) {
   const int per = nr * (nx + 1);
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nrec * per; i += (long)gridDim.x * blockDim.x) {
-    const long rec = i / per;
+    long rec = i / per; // logical (instance, knot) -> physical slot
+    if (head) {
+      const long b = rec / N;
+      const int t = (int)(rec % N) + head;
+      rec = b * N + (t >= N ? t - N : t);
+    }
     const int e = (int)(i % per), c = e / nr, r = e % nr; // destination is column-major
     dst[i] = (c == 0) ? ff[rec * nr + r] : fb[(rec * nr + r) * nx + (c - 1)];
   }
@@ -169,10 +164,15 @@ struct ab2_gar_solver {
   ab2::SweepParams p;
   // owned device storage
   double *own_stage = nullptr, *own_term = nullptr, *own_G0 = nullptr, *own_g0 = nullptr;
-  double *gains_tmp = nullptr, *kkt_tmp = nullptr, *theta_dev = nullptr;
+  double *gains_tmp = nullptr, *kkt_tmp = nullptr, *theta_dev = nullptr, *ls_tmp = nullptr;
   int nth = 0;  // parameter dimension of the value function outputs (= nx in leg mode)
   int rec_nth = 0; // parameter blocks carried by the knot records (0 in leg mode)
   int legs = 0;    // >= 2: gar::ParallelRiccatiSolver (leg mode)
+  // O(1) cycleAppend: ring heads.  fac_head: physical slot of stage knot 0 in the per-knot FACTOR arrays
+  // (FF, FB, VXX, VX) -- non-zero only between a cycle_append and the next backward, which rewrites every slot
+  // in place; seen by the getters only.  p.stage_head: the same for the solver-owned copy of the stage records,
+  // read by the kernels through stage_slot().
+  int fac_head = 0;
   double *cond = nullptr;
   // fused pack + all-gather over peer memory (multi-GPU)
   int pg_world = 0, pg_rank = 0;
@@ -411,7 +411,7 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
     cudaFree(s->pg_local);
   if (s->pg_done)
     cudaFree(s->pg_done);
-  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev, s->cond})
+  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev, s->cond, s->ls_tmp})
     if (q)
       cudaFree(q);
   for (int i = 0; i < ab2_gar_solver::kPipeStreams; ++i) {
@@ -450,8 +450,10 @@ int ab2_gar_set_problem(ab2_gar_solver *s, const double *stage, const double *te
   const size_t n_stage = stage_total(s), n_term = (size_t)s->d.batch * s->trec,
                n_G0 = (size_t)s->d.batch * s->d.nc0 * s->d.nx, n_g0 = (size_t)s->d.batch * s->d.nc0;
   if (memspace == AB2_DEVICE) {
-    if (stage)
+    if (stage) {
       s->p.stage = stage;
+      s->p.stage_head = 0; // a caller-owned array is in knot order (the caller rotates it itself)
+    }
     if (term)
       s->p.term = term;
     if (G0)
@@ -472,6 +474,8 @@ int ab2_gar_set_problem(ab2_gar_solver *s, const double *stage, const double *te
     int rc;
     if ((rc = up(s->own_stage, stage, n_stage, s->p.stage)) != AB2_OK)
       return rc;
+    if (stage)
+      s->p.stage_head = 0;
     if ((rc = up(s->own_term, term, n_term, s->p.term)) != AB2_OK)
       return rc;
     if ((rc = up(s->own_G0, G0, n_G0, s->p.G0)) != AB2_OK)
@@ -578,8 +582,10 @@ static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream
   s->p.do_fwd = fwd;
   if (int rc = run_kernels(s, s->p, bwd, fwd, (cudaStream_t)stream))
     return rc;
-  if (bwd)
+  if (bwd) {
     s->have_backward = true;
+    s->fac_head = 0; // every factor slot was rewritten in knot order
+  }
   s->have_forward = fwd != 0; // a backward-only launch invalidates the previous trajectory
   return AB2_OK;
 }
@@ -639,12 +645,16 @@ int ab2_gar_assemble(ab2_gar_solver *s, const ab2_lq_inputs *in, void *stream) {
                                    d.nu, d.nc, d.nct, d.nc0, s->srec, s->trec, (cudaStream_t)stream));
   s->launches += d.horizon > 0 ? 2 : 1;
   s->p.stage = s->own_stage;
+  s->p.stage_head = 0;
   s->p.term = s->own_term;
   s->p.G0 = s->own_G0;
   s->p.g0 = s->own_g0;
   s->have_problem = true;
   return AB2_OK;
 }
+
+static int copy_ring(const double *base, size_t rec, int knots, int nring, int head, int b0, int nb, int t0, int nt,
+                     double *dst, cudaMemcpyKind kind, cudaStream_t st);
 
 int ab2_gar_problem_ptr(ab2_gar_solver *s, int what, const double **out) {
   if (!s || !out || what < 0 || what > 3)
@@ -663,6 +673,10 @@ int ab2_gar_get_problem(ab2_gar_solver *s, int what, double *dst, int memspace, 
   const size_t n[4] = {stage_total(s), (size_t)s->d.batch * s->trec, (size_t)s->d.batch * s->d.nc0 * s->d.nx,
                        (size_t)s->d.batch * s->d.nc0};
   CUDA_TRY(cudaSetDevice(s->d.device));
+  if (what == 0 && s->p.stage_head != 0 && n[0]) // the solver-owned copy after cycle_append: knot order through the head
+    return copy_ring(s->p.stage, (size_t)s->srec, s->d.horizon, s->d.horizon, s->p.stage_head, 0, s->d.batch, 0,
+                     s->d.horizon, dst, memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                     (cudaStream_t)stream);
   if (n[what])
     CUDA_TRY(cudaMemcpyAsync(dst, ptrs[what], n[what] * sizeof(double),
                              memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
@@ -700,6 +714,7 @@ int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *ter
       (rc = own(s->own_G0, (size_t)B * nc0 * nx)) != AB2_OK || (rc = own(s->own_g0, (size_t)B * nc0)) != AB2_OK)
     return rc;
   s->p.stage = s->own_stage;
+  s->p.stage_head = 0;
   s->p.term = s->own_term;
   s->p.G0 = s->own_G0;
   s->p.g0 = s->own_g0;
@@ -752,6 +767,7 @@ int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *ter
   }
   s->have_backward = true;
   s->have_forward = true;
+  s->fac_head = 0;
   return AB2_OK;
 }
 
@@ -761,12 +777,44 @@ size_t ab2_gar_output_doubles(const ab2_gar_solver *s, int what) {
   return s->out_doubles[what];
 }
 
+// Dense copy of knots [t0, t0 + nt) of instances [b0, b0 + nb) of a per-knot array whose first `nring` knots
+// are ring-indexed with head `head` (knot t in slot (t + head) mod nring; knots >= nring -- the terminal
+// entry of VXX / VX -- stay in place): at most three strided copies.
+static int copy_ring(const double *base, size_t rec, int knots, int nring, int head, int b0, int nb, int t0, int nt,
+                     double *dst, cudaMemcpyKind kind, cudaStream_t st) {
+  auto piece = [&](int lt, int pt, int len) -> int { // logical start, physical start, length
+    if (len <= 0)
+      return AB2_OK;
+    CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)(lt - t0) * rec, (size_t)nt * rec * sizeof(double),
+                               base + ((size_t)b0 * knots + pt) * rec, (size_t)knots * rec * sizeof(double),
+                               (size_t)len * rec * sizeof(double), (size_t)nb, kind, st));
+    return AB2_OK;
+  };
+  const int t1 = t0 + nt;
+  auto clip = [&](int lo, int hi, int shift) { // logical [lo, hi) of the ring, physical = logical + shift
+    const int a = t0 > lo ? t0 : lo, b = t1 < hi ? t1 : hi;
+    return piece(a, a + shift, b - a);
+  };
+  int rc;
+  if ((rc = clip(0, nring - head, head)) != AB2_OK || (rc = clip(nring - head, nring, head - nring)) != AB2_OK ||
+      (rc = clip(nring, knots, 0)) != AB2_OK)
+    return rc;
+  return AB2_OK;
+}
+static bool ring_indexed(const ab2_gar_solver *s, int what) {
+  return s->fac_head != 0 && (what == AB2_OUT_FF || what == AB2_OUT_FB || what == AB2_OUT_VXX || what == AB2_OUT_VX);
+}
+
 int ab2_gar_get(ab2_gar_solver *s, int what, double *dst, int memspace, void *stream) {
   if (!s || !dst || what < 0 || what >= AB2_OUT_COUNT)
     return fail(AB2_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(s->d.device));
   if (s->out_doubles[what] == 0)
     return AB2_OK;
+  if (ring_indexed(s, what)) // between a cycle_append and the next backward: knot order through the ring head
+    return copy_ring(s->out[what], s->out_rec[what], s->out_knots[what], s->d.horizon, s->fac_head, 0, s->d.batch, 0,
+                     s->out_knots[what], dst, memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                     (cudaStream_t)stream);
   CUDA_TRY(cudaMemcpyAsync(dst, s->out[what], s->out_doubles[what] * sizeof(double),
                            memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                            (cudaStream_t)stream));
@@ -784,6 +832,9 @@ int ab2_gar_get_range(ab2_gar_solver *s, int what, int b0, int nb, int t0, int n
   const size_t rec = s->out_rec[what];
   if (rec == 0 || nb == 0 || nt == 0)
     return AB2_OK;
+  if (ring_indexed(s, what))
+    return copy_ring(s->out[what], rec, knots, s->d.horizon, s->fac_head, b0, nb, t0, nt, dst,
+                     memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   const double *src = s->out[what] + ((size_t)b0 * knots + t0) * rec;
   CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)nt * rec * sizeof(double), src, (size_t)knots * rec * sizeof(double),
                              (size_t)nt * rec * sizeof(double), (size_t)nb,
@@ -806,7 +857,7 @@ int ab2_gar_first_step_policy(ab2_gar_solver *s, double *dst, void *stream) {
   if (blocks > 148 * 8)
     blocks = 148 * 8;
   ab2::first_step_policy_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(
-      s->out[AB2_OUT_FB], s->out[AB2_OUT_FF], dst, s->d.batch, s->d.horizon, s->nr, s->d.nu, s->d.nx);
+      s->out[AB2_OUT_FB], s->out[AB2_OUT_FF], dst, s->d.batch, s->d.horizon, s->nr, s->d.nu, s->d.nx, s->fac_head);
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;
   return AB2_OK;
@@ -832,7 +883,7 @@ int ab2_gar_get_gains(ab2_gar_solver *s, double *dst, int memspace, void *stream
   if (blocks > 148 * 8)
     blocks = 148 * 8;
   ab2::gains_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(s->out[AB2_OUT_FB], s->out[AB2_OUT_FF], out, nrec,
-                                                                    s->nr, s->d.nx);
+                                                                    s->nr, s->d.nx, s->d.horizon, s->fac_head);
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;
   if (memspace != AB2_DEVICE)
@@ -860,6 +911,7 @@ int ab2_gar_kkt_error(ab2_gar_solver *s, double mueq, double *dst, int memspace,
   a.nc0 = s->d.nc0;
   a.srec = s->srec;
   a.trec = s->trec;
+  a.stage_head = s->p.stage_head;
   a.mueq = mueq;
   a.stage = s->p.stage;
   a.term = s->p.term;
@@ -894,6 +946,90 @@ int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream) {
   CUDA_TRY(cudaMemcpyAsync(dst, s->status, sizeof(int) * s->d.batch,
                            memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                            (cudaStream_t)stream));
+  return AB2_OK;
+}
+
+// ---- line-search consumers (linesearch.cu) ----
+static ab2::LineSearchArgs ls_args(const ab2_gar_solver *s) {
+  ab2::LineSearchArgs a;
+  a.batch = s->d.batch;
+  a.N = s->d.horizon;
+  a.nx = s->d.nx;
+  a.nu = s->d.nu;
+  a.nc = s->d.nc;
+  a.nct = s->d.nct;
+  a.nc0 = s->d.nc0;
+  a.dxs = s->out[AB2_OUT_XS];
+  a.dus = s->out[AB2_OUT_US];
+  a.dvs = s->out[AB2_OUT_VS];
+  a.dvsT = s->out[AB2_OUT_VST];
+  a.dlam0 = s->out[AB2_OUT_LBD0];
+  a.dlams = s->out[AB2_OUT_LBDAS];
+  return a;
+}
+static int ls_result(ab2_gar_solver *s, double *dst, int memspace, cudaStream_t st, double **dev) {
+  if (memspace == AB2_DEVICE) {
+    *dev = dst;
+    return AB2_OK;
+  }
+  if (!s->ls_tmp)
+    CUDA_TRY(cudaMalloc(&s->ls_tmp, (size_t)s->d.batch * sizeof(double)));
+  *dev = s->ls_tmp;
+  (void)st;
+  return AB2_OK;
+}
+int ab2_gar_linear_step(ab2_gar_solver *s, double alpha, const ab2_ls_iterate *cur, const ab2_ls_trial *trial,
+                        void *stream) {
+  if (!s || !cur || !trial)
+    return fail(AB2_ERR_INVALID, "null argument");
+  if (!s->have_forward)
+    return fail(AB2_ERR_STATE, "linear_step needs the step of a forward pass");
+  const ab2_gar_dims &d = s->d;
+  const bool ok = cur->xs && trial->xs && (d.horizon == 0 || (cur->us && trial->us && cur->lams && trial->lams)) &&
+                  (d.nc == 0 || d.horizon == 0 || (cur->vs && trial->vs)) && (d.nct == 0 || (cur->vsT && trial->vsT)) &&
+                  (d.nc0 == 0 || (cur->lam0 && trial->lam0));
+  if (!ok)
+    return fail(AB2_ERR_INVALID, "linear_step: a required array is NULL for these dimensions");
+  CUDA_TRY(cudaSetDevice(d.device));
+  ab2::LinearStepIO io{cur->xs, cur->us, cur->vs, cur->vsT, cur->lam0, cur->lams,
+                       trial->xs, trial->us, trial->vs, trial->vsT, trial->lam0, trial->lams};
+  CUDA_TRY(ab2::launch_linear_step(ls_args(s), io, alpha, (cudaStream_t)stream));
+  s->launches += 1;
+  return AB2_OK;
+}
+int ab2_gar_directional_derivative(ab2_gar_solver *s, const double *Lxs, const double *Lus, double *dst, int memspace,
+                                   void *stream) {
+  if (!s || !Lxs || !dst || (s->d.horizon > 0 && !Lus))
+    return fail(AB2_ERR_INVALID, "null argument");
+  if (!s->have_forward)
+    return fail(AB2_ERR_STATE, "directional_derivative needs the step of a forward pass");
+  CUDA_TRY(cudaSetDevice(s->d.device));
+  double *dev = nullptr;
+  if (int rc = ls_result(s, dst, memspace, (cudaStream_t)stream, &dev))
+    return rc;
+  CUDA_TRY(ab2::launch_directional_derivative(ls_args(s), Lxs, Lus, dev, (cudaStream_t)stream));
+  s->launches += 1;
+  if (memspace != AB2_DEVICE)
+    CUDA_TRY(cudaMemcpyAsync(dst, dev, (size_t)s->d.batch * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return AB2_OK;
+}
+int ab2_gar_al_value(ab2_gar_solver *s, const ab2_ls_iterate *plus, const double *cost, double mudyn, double mucstr,
+                     double *dst, int memspace, void *stream) {
+  if (!s || !plus || !dst)
+    return fail(AB2_ERR_INVALID, "null argument");
+  const ab2_gar_dims &d = s->d;
+  if ((d.nc0 > 0 && !plus->lam0) || (d.horizon > 0 && !plus->lams) || (d.nc > 0 && d.horizon > 0 && !plus->vs) ||
+      (d.nct > 0 && !plus->vsT))
+    return fail(AB2_ERR_INVALID, "al_value: a required multiplier array is NULL for these dimensions");
+  CUDA_TRY(cudaSetDevice(d.device));
+  double *dev = nullptr;
+  if (int rc = ls_result(s, dst, memspace, (cudaStream_t)stream, &dev))
+    return rc;
+  CUDA_TRY(ab2::launch_al_value(d.batch, d.horizon, d.nx, d.nc, d.nct, d.nc0, plus->lam0, plus->lams, plus->vs, plus->vsT,
+                                cost, mudyn, mucstr, dev, (cudaStream_t)stream));
+  s->launches += 1;
+  if (memspace != AB2_DEVICE)
+    CUDA_TRY(cudaMemcpyAsync(dst, dev, (size_t)d.batch * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return AB2_OK;
 }
 
@@ -941,25 +1077,29 @@ int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace
       if (s->out_doubles[w])
         CUDA_TRY(cudaMemsetAsync(s->out[w], 0, s->out_doubles[w] * sizeof(double), st));
   }
-  const int whats[4] = {AB2_OUT_FF, AB2_OUT_FB, AB2_OUT_VXX, AB2_OUT_VX};
-  for (int w : whats) {
-    if (s->legs > 1)
-      break;
-    const int rec = (int)s->out_rec[w];
-    if (rec == 0)
-      continue;
-    ab2::shift_left_kernel<<<B, 128, 0, st>>>(s->out[w], (long)s->out_knots[w] * rec, N, rec, 1);
-    s->launches += 1;
+  // O(1) in the horizon: nothing moves.  The per-knot factor arrays and the solver-owned stage records are rings;
+  // rotating left = advancing the head by one.  What is touched is ONE knot slot per instance and array:
+  // the factor slot of the new last knot is zeroed (datas[N-1] re-created, :82-83), its record is written.
+  if (s->legs <= 1) {
+    s->fac_head = (s->fac_head + 1) % N;
+    const int slot = (N - 1 + s->fac_head) % N; // physical slot of the new stage knot N-1 (= the old knot 0's)
+    for (int w : {AB2_OUT_FF, AB2_OUT_FB, AB2_OUT_VXX, AB2_OUT_VX}) {
+      const size_t rec = s->out_rec[w];
+      if (rec == 0)
+        continue;
+      CUDA_TRY(cudaMemset2DAsync(s->out[w] + (size_t)slot * rec, (size_t)s->out_knots[w] * rec * sizeof(double), 0,
+                                 rec * sizeof(double), (size_t)B, st));
+    }
   }
   // kkt0 zeroed (:84-86)
   if (s->out_doubles[AB2_OUT_KKT0])
     CUDA_TRY(cudaMemsetAsync(s->out[AB2_OUT_KKT0], 0, s->out_doubles[AB2_OUT_KKT0] * sizeof(double), st));
-  // the problem itself: rotate our own device copy (host-fed problems); a device-resident
-  // caller rotates its own buffers, like cycleProblem does for the reference's problem.
+  // the problem itself: our own device copy (host-fed problems) rotates the same way; a device-resident
+  // caller rotates its own buffers, like cycleProblem does for the reference's problem (solver-proxddp.hxx:202-209).
   if (s->own_stage && s->p.stage == s->own_stage) {
-    ab2::shift_left_kernel<<<B, 128, 0, st>>>(s->own_stage, (long)N * s->srec, N, s->srec, 0);
-    s->launches += 1;
-    CUDA_TRY(cudaMemcpy2DAsync(s->own_stage + (size_t)(N - 1) * s->srec, (size_t)N * s->srec * sizeof(double),
+    s->p.stage_head = (s->p.stage_head + 1) % N;
+    const int slot = (N - 1 + s->p.stage_head) % N;
+    CUDA_TRY(cudaMemcpy2DAsync(s->own_stage + (size_t)slot * s->srec, (size_t)N * s->srec * sizeof(double),
                                new_last, (size_t)s->srec * sizeof(double), (size_t)s->srec * sizeof(double),
                                (size_t)B,
                                memspace == AB2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
@@ -967,6 +1107,16 @@ int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace
   CUDA_TRY(cudaGetLastError());
   s->have_backward = false;
   s->have_forward = false;
+  return AB2_OK;
+}
+
+int ab2_gar_ring_heads(const ab2_gar_solver *s, int *factor_head, int *stage_head) {
+  if (!s)
+    return fail(AB2_ERR_INVALID, "null solver");
+  if (factor_head)
+    *factor_head = s->fac_head;
+  if (stage_head)
+    *stage_head = s->p.stage_head;
   return AB2_OK;
 }
 

@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256) kkt_error_kernel(const KktErrorArgs a) {
     const double *u = term ? nullptr : a.us + (b * N + t) * nu;
     const int ncc = term ? nct : nc, nuu = term ? 0 : nu;
     const double *v = term ? a.vsT + b * nct : a.vs + (b * N + t) * nc;
-    const double *rec = term ? a.term + b * a.trec : a.stage + (b * N + t) * a.srec;
+    const int slot = term ? 0 : ((t + a.stage_head) >= N ? t + a.stage_head - N : t + a.stage_head);
+    const double *rec = term ? a.term + b * a.trec : a.stage + (b * N + slot) * a.srec;
     // block pointers inside the record
     const double *A = rec, *B = rec + nxx, *f = B + nxu;
     const double *Q = term ? rec : f + nx, *S = Q + nxx, *R = S + nxu;

@@ -385,7 +385,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
     int pv = 0; // pivot statistics (threads 0..bk_threads-1 all see the same decisions)
     const int t_first = last_leg ? N - 1 : t_hi - 1; // first stage knot of the (descending) loop
     if (t_first >= t_lo) {
-      const double *src = stage_b + (size_t)t_first * d.srec_pad;
+      const double *src = stage_b + (size_t)stage_slot(p, t_first) * d.srec_pad;
       ctx.issue_copy(0, rec, src, d.split);
       if (two_parts)
         ctx.issue_copy(1, rec + d.split, src + d.split, d.srec_pad - d.split);
@@ -586,7 +586,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       ctx.sync();
       // the tail of the record (cost blocks, C, D, d) is consumed: fetch the next knot's
       if (two_parts && t > t_lo) {
-        const double *src = stage_b + (size_t)(t - 1) * d.srec_pad;
+        const double *src = stage_b + (size_t)stage_slot(p, t - 1) * d.srec_pad;
         ctx.issue_copy(1, rec + d.split, src + d.split, d.srec_pad - d.split);
       }
       // Unconstrained knots (SPD Rhat): the branch-free warp LDL^T; anything that needs an
@@ -772,7 +772,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
         ctx.sync();
       }
       if (t > t_lo) {
-        const double *src = stage_b + (size_t)(t - 1) * d.srec_pad;
+        const double *src = stage_b + (size_t)stage_slot(p, t - 1) * d.srec_pad;
         ctx.issue_copy(0, rec, src, d.split);
         double *Vt = Vxx_b + (size_t)t * nx * nx; // symmetric Vxx_t, as the next step leaves it
         for (int e = tid; e < nx * nx; e += T)

@@ -81,6 +81,7 @@ struct SweepParams {
   int stagger_ns;  // start-up delay per resident warp slot: de-phases the warps of an SM
   int num_sms;
   int ctas_per_sm; // host-side launch hint: resident CTAs per SM wanted (0 = whatever fits)
+  int stage_head;  // ring head of the stage records: knot t lives in slot (t + stage_head) mod N (O(1) cycleAppend)
   int dbg;         // experiment switches (env AB2_DEBUG_FLAGS): 1 = no register fast path for the initial system, 2 = no proxy fence before the forward ring
   // parametric problems (nth > 0; CTA-per-instance kernel only): riccati-kernel.hxx:185-192, 278-311
   int nth;
@@ -102,6 +103,11 @@ struct SweepParams {
 // status bits: see ST_*; in leg mode several CTAs report on one instance
 enum : int { ST_CONDENSED_FACTOR_FAILED = 4 };
 
+// physical slot of stage knot t in the (ring-indexed) stage-record array
+AB2_HD int stage_slot(const SweepParams &p, int t) {
+  const int s = t + p.stage_head;
+  return s >= p.N ? s - p.N : s;
+}
 // leg i of T over a horizon of N stage knots + the terminal knot (get_work, parallel-solver.hxx:23-28)
 AB2_HD int leg_begin(int N, int i, int T) { return (int)((long long)i * (N + 1) / T); }
 // doubles before block b of the condensed vector: blocks [nc0, nx, nx, nx, ...]
@@ -1066,11 +1072,11 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     if (C::DB) {
       if (t > 0)
         ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::RSTRIDE,
-                       AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
+                       AB2_STAGE_B + (size_t)stage_slot(p, t - 1) * C::SREC_PAD, C::SREC_PAD);
       cur ^= 1;
     }
     if (t >= 4) { // and pull the record of 4 knots ahead into L2 (one 128-byte line per lane)
-      const char *nxt = reinterpret_cast<const char *>(AB2_STAGE_B + (size_t)(t - 4) * C::SREC_PAD);
+      const char *nxt = reinterpret_cast<const char *>(AB2_STAGE_B + (size_t)stage_slot(p, t - 4) * C::SREC_PAD);
       for (int o = lane * 128; o < C::SREC_PAD * 8; o += C::G * 128)
         prefetch_l2(nxt + o);
     }
@@ -1149,7 +1155,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     // (3) control rows of H: [Shat^T | rhat] -> X, Rhat -> KKT matrix (:232-257)
     ctx.sync(); // every lane has its W fragments: the storage becomes X / KK
     if (!C::DB && t > 0) // ... and its H0 entries: the cost blocks of knot t-1 may land
-      ctx.issue_copy(1, rec + C::SPLIT, AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD + C::SPLIT,
+      ctx.issue_copy(1, rec + C::SPLIT, AB2_STAGE_B + (size_t)stage_slot(p, t - 1) * C::SREC_PAD + C::SPLIT,
                      C::SREC_PAD - C::SPLIT);
     AB2_UNROLL
     for (int mt = 0; mt < NT; ++mt) {
@@ -1259,7 +1265,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
         // single buffer: [A|B|f] of this knot now lives in the accumulators and fragments of every
         // lane (the products above consumed the loads): refill it while the results are stored
         ctx.sync();
-        ctx.issue_copy(0, rec, AB2_STAGE_B + (size_t)(t - 1) * C::SREC_PAD, C::SPLIT);
+        ctx.issue_copy(0, rec, AB2_STAGE_B + (size_t)stage_slot(p, t - 1) * C::SREC_PAD, C::SPLIT);
       }
       if (C::VXX_BULK && t > 0)
         ctx.bulk_store_wait_read(); // the previous knot's Vxx store has finished reading V'
@@ -1384,7 +1390,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
   if (p.do_bwd) {
     // prefetch the last stage knot while the terminal knot is processed
     if (N > 0) {
-      const double *src = stage_b + (size_t)(N - 1) * C::SREC_PAD;
+      const double *src = stage_b + (size_t)stage_slot(p, N - 1) * C::SREC_PAD;
       if (C::DB) {
         ctx.issue_copy(0, rec, src, C::SREC_PAD);
       } else {
@@ -1460,7 +1466,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
         rec = sm + C::S_REC + cur * C::RSTRIDE;
         if (t > 0) // stream the next knot into the other buffer during this step
           ctx.issue_copy(cur ^ 1, sm + C::S_REC + (cur ^ 1) * C::RSTRIDE,
-                         stage_b + (size_t)(t - 1) * C::SREC_PAD, C::SREC_PAD);
+                         stage_b + (size_t)stage_slot(p, t - 1) * C::SREC_PAD, C::SREC_PAD);
         cur ^= 1;
       } else {
         ctx.wait_copy(0);
@@ -1549,7 +1555,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       }
       ctx.sync();
       if (!C::DB && t > 0) // part 1 of the record (Q..d) is consumed: fetch the next knot's
-        ctx.issue_copy(1, rec + C::SPLIT, stage_b + (size_t)(t - 1) * C::SREC_PAD + C::SPLIT,
+        ctx.issue_copy(1, rec + C::SPLIT, stage_b + (size_t)stage_slot(p, t - 1) * C::SREC_PAD + C::SPLIT,
                        C::SREC_PAD - C::SPLIT);
       // (C) Bunch-Kaufman of the reduced KKT matrix, (D) solve + closed loop (:259-267)
       double kz[NK];
@@ -1629,7 +1635,7 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
       if (!C::DB) {
         ctx.sync();
         if (t > 0) // part 0 ([A|B|f]) is consumed
-          ctx.issue_copy(0, rec, stage_b + (size_t)(t - 1) * C::SREC_PAD, C::SPLIT);
+          ctx.issue_copy(0, rec, stage_b + (size_t)stage_slot(p, t - 1) * C::SREC_PAD, C::SPLIT);
       }
       // (E) cost-to-go: [Vxx vx] = [Qhat qhat] + [Shat C^T][K k; Z z]   (:270-277)
       if (colA || colF) {

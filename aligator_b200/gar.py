@@ -38,6 +38,13 @@ class LqInputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _LQ_PTRS] + [("preg", C.c_double), ("mu_inv", C.c_double)]
 
 
+_LS_KEYS = ("xs", "us", "vs", "vsT", "lam0", "lams")
+
+
+class LsIterate(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in _LS_KEYS]
+
+
 class GarTuning(C.Structure):
     _fields_ = [("variant", C.c_int), ("stagger_ns", C.c_int), ("ctas_per_sm", C.c_int)]
 
@@ -94,6 +101,9 @@ def lib():
         L.ab2_gar_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ab2_gar_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_pivot_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_linear_step.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ab2_gar_directional_derivative.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_gar_al_value.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_peer_gather_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ab2_gar_peer_gather_connect.argtypes = [C.c_void_p, C.c_void_p]
         L.ab2_gar_policy_allgather.argtypes = [C.c_void_p, C.c_void_p]
@@ -351,6 +361,29 @@ class CudaRiccatiBatch:
         p, st = C.c_void_p(), C.c_long()
         _check(lib().ab2_gar_peer_gather_buffer(self.h, C.byref(p), C.byref(st)))
         return p.value, st.value
+
+    # ---- line-search consumers (device tensors in, device tensors / host scalars out) ----
+    def linear_step(self, alpha, current, trial, stream=0):
+        """trial = current + alpha * step (tryLinearStep's vector part); `current` / `trial`: dicts with keys
+        xs, us, vs, vsT, lam0, lams of device tensors laid out like the solver's outputs."""
+        cur = LsIterate(*[_ptr(current.get(k)).value if current.get(k) is not None else None for k in _LS_KEYS])
+        tr = LsIterate(*[_ptr(trial.get(k)).value if trial.get(k) is not None else None for k in _LS_KEYS])
+        self._keep_ls = (current, trial)
+        _check(lib().ab2_gar_linear_step(self.h, C.c_double(alpha), C.byref(cur), C.byref(tr), C.c_void_p(stream)))
+
+    def directional_derivative(self, Lxs, Lus, stream=0):
+        out = np.empty(self.dims.batch, dtype=np.float64)
+        _check(lib().ab2_gar_directional_derivative(self.h, _ptr(Lxs), _ptr(Lus), _ptr(out), AB2_HOST, C.c_void_p(stream)))
+        self.synchronize(stream)
+        return out
+
+    def al_value(self, plus, cost, mudyn, mucstr, stream=0):
+        it = LsIterate(*[_ptr(plus.get(k)).value if plus.get(k) is not None else None for k in _LS_KEYS])
+        out = np.empty(self.dims.batch, dtype=np.float64)
+        _check(lib().ab2_gar_al_value(self.h, C.byref(it), _ptr(cost), C.c_double(mudyn), C.c_double(mucstr), _ptr(out),
+                                      AB2_HOST, C.c_void_p(stream)))
+        self.synchronize(stream)
+        return out
 
     def pivot_stats(self, stream=0):
         """(n_2x2, n_interchanges) per instance of the last backward pass (``ab2_gar_pivot_stats``)."""

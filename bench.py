@@ -484,6 +484,50 @@ def main():
                "api": "ab2_gar_sweep_host: upload/sweep/download pipelined over batch slices"}
         s2.close()
 
+    # ---- e2e_device: the device-resident inner loop: the knots are ASSEMBLED on the
+    # device from resident derivative buffers (updateLQSubproblem), swept, and the line-search consumers
+    # (directional derivative, linear step) run there too; only [batch] scalars cross PCIe per iteration ----
+    e2e_device = None
+    if not args.no_e2e and NC == 0:
+        o = 0
+        fld = {}
+        for name, n in (("Jx", NX * NX), ("Ju", NX * NU), ("slack", NX), ("Lxx", NX * NX), ("Lxu", NX * NU),
+                        ("Luu", NU * NU), ("Lx", NX), ("Lu", NU)):
+            fld[name] = stage[:, :, o:o + n].contiguous()
+            o += n
+        fld.update(Lxx_N=term[:, :NX * NX].contiguous(), Lx_N=term[:, NX * NX:NX * NX + NX].contiguous(), G0=G0, g0=g0)
+        s4 = gar.CudaRiccatiBatch(NX, NU, NC, NCT, NX, N, B, device=local, variant=args.variant)
+        Lxs = torch.randn(B, N + 1, NX, dtype=torch.float64, device=dev)
+        Lus = torch.randn(B, N, NU, dtype=torch.float64, device=dev)
+        cur = {k: torch.zeros(solver.out_shape(w), dtype=torch.float64, device=dev)
+               for k, w in dict(xs=gar.OUT_XS, us=gar.OUT_US, vs=gar.OUT_VS, vsT=gar.OUT_VST, lam0=gar.OUT_LBD0,
+                                lams=gar.OUT_LBDAS).items()}
+        trial = {k: torch.empty_like(v) for k, v in cur.items()}
+
+        def dev_step():
+            s4.assemble(fld, 0.0, 1.0, stream=stream)
+            s4.sweep(MUEQ, stream=stream)
+            s4.linear_step(1.0, cur, trial, stream=stream)
+            return s4.directional_derivative(Lxs, Lus, stream=stream)  # [batch] doubles to the host, synchronises
+
+        dev_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            d1 = dev_step()
+        barrier()
+        dtd = (time.perf_counter() - t0) / args.e2e_steps
+        td = torch.tensor([dtd], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dtd = float(td.item())
+        e2e_device = {"value": knots / dtd, "unit": "knots/s", "ms_per_step": dtd * 1e3, "h2d_bytes_per_step": 0,
+                      "d2h_bytes_per_step": B * 8, "steps": args.e2e_steps,
+                      "pipeline": "ab2_gar_assemble (updateLQSubproblem on device) -> ab2_gar_sweep -> ab2_gar_linear_step "
+                                  "-> ab2_gar_directional_derivative; only the [batch] directional derivatives return",
+                      "finite": bool(np.isfinite(d1).all())}
+        s4.close()
+
     # ---- strong scaling: the FULL batch of BASELINE config 4 (nx14 nu7 N200, 2048 instances) split over
     # the ranks (2048 -> 1024/512/256 per GPU), same fused exchange; every rank measures ----
     strong = None
@@ -596,7 +640,7 @@ def main():
                        "exchange": ("fused pack + NVLink peer-memory all-gather of [K0|k0] (no NCCL on the data path)"
                                     if peer else ("ncclAllGather of [K0|k0]" if world > 1 else "none (1 GPU)"))},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e,
-            "gpu_launches": launches, "parity": parity, "strong": strong}
+            "gpu_launches": launches, "parity": parity, "strong": strong, "e2e_device": e2e_device}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -268,11 +268,47 @@ int ab2_gar_status(ab2_gar_solver *s, int *dst, int memspace, void *stream);
  * lets a caller (and the tests) see that the pivoted code paths actually ran. */
 int ab2_gar_pivot_stats(ab2_gar_solver *s, int *dst, int memspace, void *stream);
 
+/* The consumers of the step inside the caller's line search, batched over the
+ * instances so that SolverProxDDP's inner loop (solver-proxddp.hxx:605-660) can stay on the device between
+ * the sweep and the next model evaluation; the step (dxs, dus, dvs, dlams) is the solver's own last forward
+ * pass.  All array arguments are DEVICE pointers laid out like the solver's outputs: xs [batch][N+1][nx],
+ * us [batch][N][nu], vs [batch][N][nc], vsT [batch][nct], lam0 [batch][nc0], lams [batch][N][nx]. */
+typedef struct ab2_ls_iterate {
+  const double *xs, *us, *vs, *vsT, *lam0, *lams;
+} ab2_ls_iterate;
+typedef struct ab2_ls_trial {
+  double *xs, *us, *vs, *vsT, *lam0, *lams;
+} ab2_ls_trial;
+/* Replaces: the vector part of SolverProxDDP::tryLinearStep, solver-proxddp.hxx:111-155: trial = results +
+ * alpha * step for lams, vs (math::vectorMultiplyAdd, :121-124) and for xs, us with the vector-space
+ * integrate (:139-150); a manifold's integrate and problem.evaluate() stay with the modelling library. */
+int ab2_gar_linear_step(ab2_gar_solver *s, double alpha, const ab2_ls_iterate *current, const ab2_ls_trial *trial,
+                        void *stream);
+/* Replaces: ALFunction::directionalDerivative, merit-function.hxx:68-104 (Lxs [batch][N+1][nx], Lus [batch][N][nu]
+ * = the Lagrangian gradients) and costDirectionalDerivative, :13-31 (pass the cost gradients): dst[batch] =
+ * sum_t Lxs_t . dxs_t + sum_t Lus_t . dus_t.  dst in host or device memory. */
+int ab2_gar_directional_derivative(ab2_gar_solver *s, const double *Lxs, const double *Lus, double *dst, int memspace,
+                                   void *stream);
+/* Replaces: ALFunction::evaluate, merit-function.hxx:33-66: dst[batch] = cost[batch] (NULL = 0) + 1/2 (mucstr
+ * |lam0|^2 + mudyn sum |lams_t|^2 + mucstr sum |vs_t|^2 + mucstr |vsT|^2) of the multiplier estimates `plus`
+ * (only lam0, lams, vs, vsT are read). */
+int ab2_gar_al_value(ab2_gar_solver *s, const ab2_ls_iterate *plus, const double *cost, double mudyn, double mucstr,
+                     double *dst, int memspace, void *stream);
+
 /* Replaces: cycleAppend(knot), proximal-riccati.hxx:79-86 + the problem rotation the
  * caller performs (solver-proxddp.hxx:202-209): factors and stage knots of every
  * instance shift one knot to the left; `new_last` ([batch][stage_record], memspace)
- * becomes stage knot N-1; its factor slot and kkt0 are zeroed. */
+ * becomes stage knot N-1; its factor slot and kkt0 are zeroed.
+ * O(1) in the horizon: the per-knot factor arrays and the solver-owned copy of the stage records are
+ * rings -- the call advances a head index, zeroes ONE factor slot and writes ONE record per instance; the
+ * getters (ab2_gar_get / get_range / get_gains / get_problem / first_step_policy) and the kernels apply the
+ * head, and the next backward() rewrites the factors in plain knot order.  Raw device pointers
+ * (ab2_gar_device_ptr, ab2_gar_problem_ptr) see the physical layout: stage knot t sits in slot
+ * (t + head) mod N, heads from ab2_gar_ring_heads (0 except after a cycle).  The parallel solver drops
+ * every factor instead (parallel-solver.hxx:246-258). */
 int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace, void *stream);
+
+int ab2_gar_ring_heads(const ab2_gar_solver *s, int *factor_head, int *stage_head);
 
 int ab2_gar_synchronize(ab2_gar_solver *s, void *stream);
 /* Page-locked host memory for the buffers handed to set_problem / get / sweep_host: copies to and

@@ -260,6 +260,58 @@ def test_cycle_append(gar):
         assert gen.rel_fro(solver.getFeedback(t, 2), ref["fb"][2, t]) <= TOL
 
 
+def test_cycle_append_is_a_ring_shift(gar):
+    """O(1) cycle_append: three cycles in a row WITHOUT re-uploading the problem.  The getters (whole arrays,
+    sub-ranges, gains layout, the solver-owned problem) return knot order through the ring heads; a sweep on
+    the cycled device copy equals the oracle on the rotated problem; the next backward resets the factor head."""
+    nx, nu, N, B = 6, 3, 9, 4
+    mueq = 1e-8
+    probs = gen.generate_batch(33, B, N, nx, nu, 0, 0)
+    stage, term, G0, g0 = gar.pack_problems(probs)
+    s = gar.CudaRiccatiBatch(nx, nu, 0, 0, nx, N, B)
+    s.set_problem(stage, term, G0, g0)
+    s.sweep(mueq)
+    fb0, ff0, V0, vx0 = (s.get(w).copy() for w in (gar.OUT_FB, gar.OUT_FF, gar.OUT_VXX, gar.OUT_VX))
+    gains0 = s.get_gains().copy()
+    rng = np.random.default_rng(1)
+    cur = [list(p.stages) for p in probs]
+    for cyc in range(1, 4):
+        new = [gen.generate_knot(rng, nx, nu, 0, conditioned=True) for _ in range(B)]
+        s.cycle_append(np.stack([gar.pack_stage_knot(k, s.srec) for k in new]))
+        fb, ff, V, vx = (s.get(w) for w in (gar.OUT_FB, gar.OUT_FF, gar.OUT_VXX, gar.OUT_VX))
+        # factors: rotated left `cyc` times, the last `cyc` stage slots zero, the terminal entry in place
+        assert np.array_equal(fb[:, :N - cyc], fb0[:, cyc:]) and np.all(fb[:, N - cyc:] == 0)
+        assert np.array_equal(ff[:, :N - cyc], ff0[:, cyc:]) and np.all(ff[:, N - cyc:] == 0)
+        assert np.array_equal(V[:, :N - cyc], V0[:, cyc:N]) and np.all(V[:, N - cyc:N] == 0) and np.array_equal(V[:, N], V0[:, N])
+        assert np.array_equal(vx[:, N], vx0[:, N])
+        # sub-range straddling the wrap point
+        buf = np.empty(2 * 4 * (nu + nx) * nx)
+        s.get_range_into(gar.OUT_FB, 1, 2, N - cyc - 2, 4, buf, gar.AB2_HOST)
+        s.synchronize()
+        assert np.array_equal(buf.reshape(2, 4, nu + nx, nx), fb[1:3, N - cyc - 2:N - cyc + 2])
+        for p, c, k in zip(probs, cur, new):
+            c[:] = c[1:N] + [k] + [c[N]]
+        # the solver-owned problem in knot order
+        st2 = s.get_problem(0).reshape(B, N, -1)
+        for b in range(B):
+            for t in (0, N - cyc, N - 1):
+                assert np.array_equal(st2[b, t], gar.pack_stage_knot(cur[b][t], s.srec))
+    # sweep straight from the cycled device copy (no set_problem): equals the oracle on the rotated problems
+    s.sweep(mueq)
+    from aligator_b200.lqr import LqrProblem
+    rot = []
+    for p, c in zip(probs, cur):
+        q = p.copy()
+        q.stages = c
+        rot.append(q)
+    packed = gar.pack_problems(rot)
+    ref = oracle_batch(rot, packed, nx, nu, 0, 0, N, mueq)
+    for key, what in (("fb", gar.OUT_FB), ("Vxx", gar.OUT_VXX), ("xs", gar.OUT_XS), ("lbdas", gar.OUT_LBDAS)):
+        assert gen.rel_fro(s.get(what), ref[key]) <= TOL, key
+    assert s.kkt_error(mueq).max() <= 1e-9
+    s.close()
+
+
 def test_full_size_properties_config2(gar):
     """BASELINE config 2 at full size (nx12 nu6 N100 batch4096): size-independent
     properties -- KKT residual of sampled instances within the reference thresholds,

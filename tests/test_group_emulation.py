@@ -25,7 +25,7 @@ class SweepParams(C.Structure):
                                    "fbT", "kkt0", "xs", "us", "vs", "vsT", "lbd0", "lbdas")] + \
                [("status", C.POINTER(C.c_int)), ("pivstat", C.POINTER(C.c_int)), ("stagger_ns", C.c_int),
                 ("num_sms", C.c_int),
-                ("ctas_per_sm", C.c_int), ("dbg", C.c_int), ("nth", C.c_int)] + \
+                ("ctas_per_sm", C.c_int), ("stage_head", C.c_int), ("dbg", C.c_int), ("nth", C.c_int)] + \
                [(n, _dp) for n in ("theta", "fth", "Vxt", "Vtt", "vt", "kkt0fth", "thGrad", "thHess")] + \
                [("legs", C.c_int), ("cond", _dp)]
 
