@@ -42,10 +42,12 @@ __global__ void first_step_policy_kernel(const double *__restrict__ fb, const do
 // step) + flag words, mapped into every peer by CUDA IPC.  Rank r's kernel computes each
 // element of its own block once and STORES it into the slot [half][r] of EVERY rank's buffer
 // (peer stores over NVLink / NVSwitch; no NCCL kernel, no staging copy), then the last CTA
-// to finish publishes the step number in every peer's data flag.  Flow control: at the start
-// of step s a rank tells its peers "everything up to s-1 is consumed" (ack flag; the kernel
-// is stream-ordered behind the consumers) and waits until every peer has acknowledged step
-// s-2, whose data the half it is about to overwrite held.
+// to finish publishes the step number in every peer's data flag.  Flow control: the WAIT
+// kernel of step s (stream-ordered behind the consumers of step s-1 on the consumer's stream)
+// first tells every peer "everything up to s-1 is consumed here" (ack flag), then waits for
+// the data flags of step s; the pack kernel of step s waits until every peer has acknowledged
+// step s-2, whose data the half it is about to overwrite held.  A rank may thus run two steps
+// ahead of the slowest consumer -- the same slack a double-buffered NCCL gather has.
 // ---------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 struct PeerPtrs {
@@ -68,9 +70,6 @@ __global__ void __launch_bounds__(256)
   const int per = nu * (nx + 1);
   const long total = (long)batch * per;
   if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) // this rank is done with every step before `step` (stream order)
-      for (int w = 0; w < world; ++w)
-        st_release_sys(peers.ack_flag[w] + rank, step - 1);
     if (step >= 3) // the half written now held step-2: every peer must have consumed it
       for (int w = 0; w < world; ++w)
         while (ld_acquire_sys(peers.ack_flag[rank] + w) + 2 < step)
@@ -96,12 +95,16 @@ __global__ void __launch_bounds__(256)
     }
   }
 }
-// the stream waits until the blocks of every sender have arrived for `step`
-__global__ void policy_wait_kernel(const unsigned long long *data_flag, const int world, const unsigned long long step) {
+// the stream waits until the blocks of every sender have arrived for `step`; before that it
+// acknowledges to every peer that this rank is done with step-1 (everything enqueued earlier on
+// this stream -- the consumers of step-1 -- has completed)
+__global__ void policy_wait_kernel(const PeerPtrs peers, const int world, const int rank, const unsigned long long step) {
   const int w = threadIdx.x;
-  if (w < world)
-    while (ld_acquire_sys(data_flag + w) < step)
+  if (w < world) {
+    st_release_sys(peers.ack_flag[w] + rank, step - 1);
+    while (ld_acquire_sys(peers.data_flag[rank] + w) < step)
       __nanosleep(64);
+  }
 }
 
 // row-major fb [nr][nx] + ff [nr]  ->  column-major [nr][nx+1] with column 0 = ff, per (instance, knot)
@@ -1196,7 +1199,7 @@ int ab2_gar_policy_allgather_wait(ab2_gar_solver *s, void *stream) {
   if (!s || !s->pg_peer_base[0] || s->pg_step == 0)
     return fail(AB2_ERR_STATE, "policy_allgather_wait before policy_allgather");
   CUDA_TRY(cudaSetDevice(s->d.device));
-  ab2::policy_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->pg_ptrs.data_flag[s->pg_rank], s->pg_world, s->pg_step);
+  ab2::policy_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->pg_ptrs, s->pg_world, s->pg_rank, s->pg_step);
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;
   return AB2_OK;

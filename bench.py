@@ -389,14 +389,15 @@ def main():
             # the one exchange, fused: the pack kernel stores [K0 | k0] straight into every rank's
             # receive buffer over NVLink (no NCCL kernel); arrival is awaited on the side stream,
             # overlapping the next sweep; the next pack waits for that (its ack says "consumed")
-            if waited[0] is not None:
-                main.wait_event(waited[0])
+            if len(waited) >= 3 and waited[-2] is not None:
+                main.wait_event(waited[-2])  # the arrival (and consumption) of the gather TWO steps back
             solver.policy_allgather(stream=stream)
             side.wait_stream(main)
             solver.policy_allgather_wait(stream=side.cuda_stream)
             ev = torch.cuda.Event()
             ev.record(side)
-            waited[0] = ev
+            waited.append(ev)
+            del waited[:-3]
         elif world > 1:  # the one exchange: all-gather of the first-step policy [K0 | k0]
             i = step_no[0] & 1
             step_no[0] += 1
@@ -546,14 +547,15 @@ def main():
         def sstep():
             s3.sweep(smu, stream=stream)
             if speer:
-                if sw[0] is not None:
-                    main.wait_event(sw[0])
+                if len(sw) >= 3 and sw[-2] is not None:
+                    main.wait_event(sw[-2])
                 s3.policy_allgather(stream=stream)
                 side.wait_stream(main)
                 s3.policy_allgather_wait(stream=side.cuda_stream)
                 ev = torch.cuda.Event()
                 ev.record(side)
-                sw[0] = ev
+                sw.append(ev)
+                del sw[:-3]
 
         for _ in range(max(args.warmup, 3)):
             sstep()

@@ -286,9 +286,9 @@ def test_cycle_append_is_a_ring_shift(gar):
         assert np.array_equal(vx[:, N], vx0[:, N])
         # sub-range straddling the wrap point
         buf = np.empty(2 * 4 * (nu + nx) * nx)
-        s.get_range_into(gar.OUT_FB, 1, 2, N - cyc - 2, 4, buf, gar.AB2_HOST)
+        s.get_range_into(gar.OUT_FB, 1, 2, N - cyc - 3, 4, buf, gar.AB2_HOST)
         s.synchronize()
-        assert np.array_equal(buf.reshape(2, 4, nu + nx, nx), fb[1:3, N - cyc - 2:N - cyc + 2])
+        assert np.array_equal(buf.reshape(2, 4, nu + nx, nx), fb[1:3, N - cyc - 3:N - cyc + 1])
         for p, c, k in zip(probs, cur, new):
             c[:] = c[1:N] + [k] + [c[N]]
         # the solver-owned problem in knot order
