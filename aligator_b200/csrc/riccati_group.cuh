@@ -155,6 +155,13 @@ template <int NX_, int NU_, int NC_, int G_, bool DB_ = false, bool RB_ = true, 
   // Vxx_t via a TMA bulk store straight from V' in shared memory: measured SLOWER than
   // LDS.128+STG.128 (the proxy fence every lane must execute costs more than it saves).
   static constexpr bool VXX_BULK = false;
+  // [Qhat | qhat] waits in V''s storage during the factorisation and the solves (frees 16 registers where the
+  // pressure peaks).  Pays where the double-buffered build spills (measured: C2 1.015 -> 0.985 ms); the
+  // single-buffer build of wider shapes has the registers and only pays the round trip (C4 1.409 -> 1.445 ms).
+#ifndef AB2_PARK
+#define AB2_PARK 1
+#endif
+  static constexpr bool PARK = MMA_ && DB_ && (AB2_PARK != 0);
   static constexpr int LUT_INTS = MMA ? 32 * (NT + NT * NT) : 0; // per-CTA table of per-lane constants
   // stage record offsets (doubles) -- the reference's 11 buffers, concatenated
   static constexpr int OFF_A = 0;
@@ -1174,6 +1181,26 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
         }
       }
     }
+    // The state rows of H ([Qhat | qhat], the initial value of the accumulators of (5)) wait in
+    // shared memory while the factorisation and the solves run: V' and vx' are dead since (1),
+    // their storage is exactly the right shape, and 16 registers are free when the register
+    // pressure peaks (the spills this avoids went to local memory, which has no L1 behind it here).
+    if (C::PARK) {
+      AB2_UNROLL
+      for (int mt = 0; mt < MTX; ++mt) {
+        const int i = 8 * mt + g;
+        if (i < NX) {
+          AB2_UNROLL
+          for (int nt = 0; nt < NT2; ++nt) {
+            const int j0 = 8 * nt + 2 * q;
+            if (j0 + 1 < NX)
+              sts2(Vn + i * VS + j0, H[mt][nt][0], H[mt][nt][1]);
+            else if (j0 == NX)
+              vxn[i] = H[mt][nt][0];
+          }
+        }
+      }
+    }
     ctx.sync();
     double *fbt = AB2_FB_B + (size_t)t * NR * NX;
     double *fft = AB2_FF_B + (size_t)t * NR;
@@ -1224,7 +1251,27 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
     // All operand fragments are fetched first and the two products are interleaved with the
     // contraction outermost: 2*MTX*NT2 independent DMMAs per k-step.
     {
-      double EA[MTX][NT2][2], Bf[MTX][KT2], Xf[MTX][KT2];
+      double EA[MTX][NT2][2], VV[MTX][NT2][2], Bf[MTX][KT2], Xf[MTX][KT2];
+      AB2_UNROLL
+      for (int mt = 0; mt < MTX; ++mt) { // [Qhat | qhat] back from where it waited (entries nobody stores: any finite value)
+        const int i = 8 * mt + g;
+        const int ic2 = i < NX ? i : 0;
+        AB2_UNROLL
+        for (int nt = 0; nt < NT2; ++nt) {
+          const int j0 = 8 * nt + 2 * q;
+          if (!C::PARK) {
+            VV[mt][nt][0] = H[mt][nt][0];
+            VV[mt][nt][1] = H[mt][nt][1];
+          } else if (j0 + 1 < NX) {
+            const D2 v = lds2(Vn + ic2 * VS + j0);
+            VV[mt][nt][0] = v.x;
+            VV[mt][nt][1] = v.y;
+          } else {
+            VV[mt][nt][0] = vxn[ic2];
+            VV[mt][nt][1] = 0.0;
+          }
+        }
+      }
       AB2_UNROLL
       for (int mt = 0; mt < MTX; ++mt) {
         const int i = 8 * mt + g;
@@ -1257,7 +1304,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
           AB2_UNROLL
           for (int nt = 0; nt < NT2; ++nt) {
             ctx.mma(EA[mt][nt], Bf[mt][k2], KKf[k2][nt]);
-            ctx.mma(H[mt][nt], Xf[mt][k2], KKf[k2][nt]);
+            ctx.mma(VV[mt][nt], Xf[mt][k2], KKf[k2][nt]);
           }
         }
       }
@@ -1297,7 +1344,7 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
             AB2_UNROLL
             for (int e = 0; e < 2; ++e) {
               const int jj = 8 * nt + 2 * q + e;
-              const double v = H[mt][nt][e];
+              const double v = VV[mt][nt][e];
               if (jj < NX) {
                 if (t == 0)
                   AB2_VXX_B[i + jj * NX] = v; // datas[0].Vxx is left unsymmetrised (A1)
