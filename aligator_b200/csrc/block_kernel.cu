@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "riccati_block.cuh"
+#include "riccati_dense.cuh"
 #include "riccati_block_launch.h"
 #include "riccati_launch.cuh"
 
@@ -112,6 +113,23 @@ __global__ void __launch_bounds__(256) condensed_kernel(const SweepParams p, con
   }
 }
 
+// The stage-dense solver (riccati_dense.cuh): one CTA per instance, persistent over the batch.
+__global__ void __launch_bounds__(256) riccati_dense_kernel(const SweepParams p, const DenseDims d) {
+  extern __shared__ __align__(16) double smem[];
+  BlockDevCtx ctx;
+  ctx.tid = threadIdx.x;
+  ctx.nthreads = blockDim.x;
+  ctx.warp = threadIdx.x >> 5;
+  ctx.lane = threadIdx.x & 31;
+  ctx.nwarps = blockDim.x >> 5;
+  ctx.bar0 = 0;
+  ctx.phase = 0;
+  for (int inst = blockIdx.x; inst < p.batch; inst += gridDim.x) {
+    riccati_dense_sweep(ctx, p, d, inst, smem);
+    __syncthreads();
+  }
+}
+
 __global__ void collapse_kernel(const SweepParams p, const int nx, const int nu, const int nc) {
   BlockDevCtx ctx;
   ctx.tid = threadIdx.x;
@@ -215,6 +233,37 @@ cudaError_t launch_condensed(const SweepParams &p, int nx, cudaStream_t st) {
 cudaError_t launch_collapse(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st) {
   int grid = p.batch < 148 * 8 ? p.batch : 148 * 8;
   collapse_kernel<<<grid, 128, 0, st>>>(p, nx, nu, nc);
+  return cudaGetLastError();
+}
+
+static int dense_threads(const DenseDims &d) {
+  int need = d.n > d.nx + d.nc0 ? d.n : d.nx + d.nc0;
+  if (d.nx + 1 > need)
+    need = d.nx + 1;
+  return need > 256 ? 0 : 32 * ((need + 31) / 32);
+}
+bool dense_supported(int nx, int nu, int nc, int nct, int nc0) {
+  const DenseDims d = make_dense_dims(nx, nu, nc, nct, nc0);
+  return dense_threads(d) > 0 && (size_t)d.s_end * sizeof(double) <= (size_t)227 * 1024;
+}
+cudaError_t launch_dense(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st) {
+  const DenseDims d = make_dense_dims(nx, nu, nc, p.nct, p.nc0);
+  const int threads = dense_threads(d);
+  const size_t smem = (size_t)d.s_end * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(riccati_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return e;
+  int nb = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, riccati_dense_kernel, threads, smem);
+  if (e != cudaSuccess)
+    return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms * (nb > 0 ? nb : 1);
+  if (grid > p.batch)
+    grid = p.batch;
+  riccati_dense_kernel<<<grid, threads, smem, st>>>(p, d);
   return cudaGetLastError();
 }
 

@@ -123,6 +123,52 @@ __global__ void gains_kernel(const double *__restrict__ fb, const double *__rest
   }
 }
 
+// ---- FDDP backwardPass bookkeeping around the sweep (solver-fddp.hxx:204-277) ----
+// before: slack_t = fs[t+1] (the knot's affine term), G0 = -I, g0 = fs[0]
+__global__ void fddp_prep_kernel(const double *__restrict__ fs, double *__restrict__ slack, double *__restrict__ G0,
+                                 double *__restrict__ g0, int batch, int N, int nx) {
+  const long nS = (long)batch * N * nx, nG = (long)batch * nx * nx, ng = (long)batch * nx;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nS + nG + ng; i += (long)gridDim.x * blockDim.x) {
+    if (i < nS) {
+      const long b = i / ((long)N * nx), r = i % ((long)N * nx);
+      slack[i] = fs[b * (N + 1) * nx + nx + r];
+    } else if (i < nS + nG) {
+      const long e = (i - nS) % ((long)nx * nx);
+      G0[i - nS] = (e % nx == e / nx) ? -1.0 : 0.0;
+    } else {
+      const long j = i - nS - nG, b = j / nx, c = j % nx;
+      g0[j] = fs[b * (N + 1) * nx + c];
+    }
+  }
+}
+// after: Vx_i = vx_i + sym(Vxx_i) fs[i] (:219-220, 272-276), then Quuks_i = -(Lu_i + Ju_i^T Vx_{i+1}) = Quu_i k_i (:264)
+__global__ void fddp_vx_kernel(const double *__restrict__ Vxx, const double *__restrict__ vx, const double *__restrict__ fs,
+                               double *__restrict__ Vx_out, int batch, int N, int nx) {
+  const long total = (long)batch * (N + 1) * nx;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long kn = i / nx;
+    const int r = (int)(i % nx);
+    const double *V = Vxx + kn * nx * nx, *f = fs + kn * nx;
+    double acc = 0.0;
+    for (int c = 0; c < nx; ++c) // the lower triangle mirrored (selfadjointView<Lower>, :272)
+      acc += (r >= c ? V[r + (size_t)c * nx] : V[c + (size_t)r * nx]) * f[c];
+    Vx_out[i] = vx[i] + acc;
+  }
+}
+__global__ void fddp_quuks_kernel(const double *__restrict__ Ju, const double *__restrict__ Lu, const double *__restrict__ Vx,
+                                  double *__restrict__ out, int batch, int N, int nx, int nu) {
+  const long total = (long)batch * N * nu;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long kn = i / nu, b = kn / N, t = kn % N;
+    const int c = (int)(i % nu);
+    const double *B = Ju + kn * nx * nu + (size_t)c * nx, *v = Vx + (b * (N + 1) + t + 1) * nx;
+    double acc = Lu[i];
+    for (int r = 0; r < nx; ++r)
+      acc += B[r] * v[r];
+    out[i] = -acc;
+  }
+}
+
 // one KernelEntry per compile-time shape, each defined in its own object file
 // (kernel_inst.cu compiled with -DAB2_NX=.. -DAB2_NU=.. -DAB2_NC=.. -DAB2_G=..)
 #define X(NX, NU, NC, G) extern const KernelEntry kEntry_##NX##_##NU##_##NC;
@@ -168,9 +214,11 @@ struct ab2_gar_solver {
   // owned device storage
   double *own_stage = nullptr, *own_term = nullptr, *own_G0 = nullptr, *own_g0 = nullptr;
   double *gains_tmp = nullptr, *kkt_tmp = nullptr, *theta_dev = nullptr, *ls_tmp = nullptr;
+  double *fddp_slack = nullptr, *fddp_G0 = nullptr, *fddp_g0 = nullptr, *fddp_vx = nullptr;
   int nth = 0;  // parameter dimension of the value function outputs (= nx in leg mode)
   int rec_nth = 0; // parameter blocks carried by the knot records (0 in leg mode)
   int legs = 0;    // >= 2: gar::ParallelRiccatiSolver (leg mode)
+  bool dense = false; // gar::RiccatiSolverDense (one CTA per instance, stage-dense KKT): FF/FB have nu+nc+2nx rows
   // O(1) cycleAppend: ring heads.  fac_head: physical slot of stage knot 0 in the per-knot FACTOR arrays
   // (FF, FB, VXX, VX) -- non-zero only between a cycle_append and the next backward, which rewrites every slot
   // in place; seen by the getters only.  p.stage_head: the same for the solver-owned copy of the stage records,
@@ -240,6 +288,7 @@ int ab2_gar_create(const ab2_gar_dims *dims, ab2_gar_solver **out) { return crea
 int ab2_gar_create_parametric(const ab2_gar_dims *dims, int nth, ab2_gar_solver **out) {
   return create_impl(dims, nth, 0, out);
 }
+int ab2_gar_create_dense(const ab2_gar_dims *dims, ab2_gar_solver **out) { return create_impl(dims, 0, -1, out); }
 int ab2_gar_create_parallel(const ab2_gar_dims *dims, int num_legs, ab2_gar_solver **out) {
   if (num_legs < 2) // parallel-solver.hxx:42-46 throws "numThreads should be greater than or equal to 2"
     return fail(AB2_ERR_INVALID, "num_legs (" + std::to_string(num_legs) + ") should be greater than or equal to 2");
@@ -254,7 +303,12 @@ static int create_impl(const ab2_gar_dims *dims, int nth, int legs, ab2_gar_solv
   const ab2_gar_dims &d = *dims;
   if (d.nx < 1 || d.nu < 1 || d.nc < 0 || d.nct < 0 || d.nc0 < 0 || d.horizon < 0 || d.batch < 1 || nth < 0)
     return fail(AB2_ERR_INVALID, "bad dimensions");
+  const bool dense = legs < 0; // (legs = -1 selects the stage-dense solver)
+  if (dense)
+    legs = 0;
   const int rec_nth = legs > 1 ? 0 : nth; // leg mode: plain records, the parameterisation is implicit
+  if (dense && !ab2::dense_supported(d.nx, d.nu, d.nc, d.nct, d.nc0))
+    return fail(AB2_ERR_UNSUPPORTED, "the stage-dense KKT system (nu + nc + 2 nx rows) does not fit one CTA");
   // compile-time shapes run one warp (or part of one) per instance; every other shape runs
   // the CTA-per-instance kernel with run-time dimensions (block_kernel.cu)
   const ab2::KernelEntry *k = ab2::find_kernel(d.nx, d.nu, d.nc);
@@ -285,8 +339,13 @@ static int create_impl(const ab2_gar_dims *dims, int nth, int legs, ab2_gar_solv
   }
   s->trec = (int)ab2_gar_term_record_doubles_th(d.nx, d.nct, rec_nth);
   s->nr = d.nu + d.nc + d.nx;
-  if (k)
-    k->group_doubles(d.nc0, s->group_doubles);
+  s->dense = dense;
+  if (dense) {
+    s->k = nullptr;
+    s->nr = d.nu + d.nc + 2 * d.nx; // rows of ff / fb: [k; z; l; y] (dense-kernel.hpp:28-31)
+  }
+  if (s->k)
+    s->k->group_doubles(d.nc0, s->group_doubles);
   const int N = d.horizon, B = d.batch, nx = d.nx;
   auto setup = [&](int what, size_t rec, int knots) {
     s->out_rec[what] = rec;
@@ -414,7 +473,8 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
     cudaFree(s->pg_local);
   if (s->pg_done)
     cudaFree(s->pg_done);
-  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev, s->cond, s->ls_tmp})
+  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev, s->cond, s->ls_tmp, s->fddp_slack, s->fddp_G0,
+                    s->fddp_g0, s->fddp_vx})
     if (q)
       cudaFree(q);
   for (int i = 0; i < ab2_gar_solver::kPipeStreams; ++i) {
@@ -562,7 +622,9 @@ static int run_kernels(ab2_gar_solver *s, ab2::SweepParams q, int bwd, int fwd, 
   }
   q.do_bwd = bwd;
   q.do_fwd = fwd;
-  if (s->k && s->variant != 9)
+  if (s->dense)
+    CUDA_TRY(ab2::launch_dense(q, s->d.nx, s->d.nu, s->d.nc, st));
+  else if (s->k && s->variant != 9)
     CUDA_TRY(s->k->launch(q, s->variant, s->group_doubles, st, nullptr));
   else
     CUDA_TRY(ab2::launch_block(q, s->d.nx, s->d.nu, s->d.nc, st, nullptr));
@@ -851,6 +913,8 @@ int ab2_gar_first_step_policy(ab2_gar_solver *s, double *dst, void *stream) {
     return fail(AB2_ERR_INVALID, "bad argument");
   if (s->d.horizon < 1)
     return fail(AB2_ERR_INVALID, "first_step_policy needs horizon >= 1");
+  if (s->dense)
+    return fail(AB2_ERR_UNSUPPORTED, "first_step_policy: not offered by the stage-dense solver");
   if (!s->have_backward)
     return fail(AB2_ERR_STATE, "first_step_policy before backward()");
   CUDA_TRY(cudaSetDevice(s->d.device));
@@ -871,6 +935,8 @@ int ab2_gar_get_gains(ab2_gar_solver *s, double *dst, int memspace, void *stream
     return fail(AB2_ERR_INVALID, "bad argument");
   if (!s->have_backward)
     return fail(AB2_ERR_STATE, "get_gains before backward()");
+  if (s->dense)
+    return fail(AB2_ERR_UNSUPPORTED, "get_gains: the results_.gains_ layout is the proximal solver's");
   CUDA_TRY(cudaSetDevice(s->d.device));
   const long nrec = (long)s->d.batch * s->d.horizon;
   const size_t total = (size_t)nrec * s->nr * (s->d.nx + 1);
@@ -1033,6 +1099,61 @@ int ab2_gar_al_value(ab2_gar_solver *s, const ab2_ls_iterate *plus, const double
   s->launches += 1;
   if (memspace != AB2_DEVICE)
     CUDA_TRY(cudaMemcpyAsync(dst, dev, (size_t)d.batch * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return AB2_OK;
+}
+
+int ab2_fddp_backward_pass(ab2_gar_solver *s, const ab2_fddp_inputs *in, double *Vx_out, double *Quuks_out, void *stream) {
+  if (!s || !in)
+    return fail(AB2_ERR_INVALID, "null argument");
+  const ab2_gar_dims &d = s->d;
+  if (d.nc != 0 || d.nct != 0 || d.nc0 != d.nx || s->rec_nth != 0 || s->legs > 1 || d.horizon < 1)
+    return fail(AB2_ERR_INVALID, "fddp_backward_pass needs a serial solver with nc = nct = 0, nc0 = nx, horizon >= 1");
+  if (!in->Jx || !in->Ju || !in->fs || !in->Lxx || !in->Lxu || !in->Luu || !in->Lx || !in->Lu || !in->Lxx_N || !in->Lx_N)
+    return fail(AB2_ERR_INVALID, "ab2_fddp_inputs: a required array is NULL");
+  CUDA_TRY(cudaSetDevice(d.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = d.batch, N = d.horizon, nx = d.nx, nu = d.nu;
+  auto own = [&](double *&buf, size_t n) -> int {
+    if (!buf)
+      CUDA_TRY(cudaMalloc(&buf, (n > 0 ? n : 1) * sizeof(double)));
+    return AB2_OK;
+  };
+  int rc;
+  if ((rc = own(s->fddp_slack, (size_t)B * N * nx)) != AB2_OK || (rc = own(s->fddp_G0, (size_t)B * nx * nx)) != AB2_OK ||
+      (rc = own(s->fddp_g0, (size_t)B * nx)) != AB2_OK || (rc = own(s->fddp_vx, (size_t)B * (N + 1) * nx)) != AB2_OK)
+    return rc;
+  ab2::fddp_prep_kernel<<<148 * 4, 256, 0, st>>>(in->fs, s->fddp_slack, s->fddp_G0, s->fddp_g0, B, N, nx);
+  CUDA_TRY(cudaGetLastError());
+  s->launches += 1;
+  ab2_lq_inputs lq;
+  std::memset(&lq, 0, sizeof(lq));
+  lq.Jx = in->Jx;
+  lq.Ju = in->Ju;
+  lq.slack = s->fddp_slack;
+  lq.Lxx = in->Lxx;
+  lq.Lxu = in->Lxu;
+  lq.Luu = in->Luu;
+  lq.Lx = in->Lx;
+  lq.Lu = in->Lu;
+  lq.Lxx_N = in->Lxx_N;
+  lq.Lx_N = in->Lx_N;
+  lq.G0 = s->fddp_G0;
+  lq.g0 = s->fddp_g0;
+  lq.preg = in->preg; // Q, R and the terminal Q carry + preg I (:217, :246, :273)
+  lq.mu_inv = 1.0;
+  if ((rc = ab2_gar_assemble(s, &lq, stream)) != AB2_OK)
+    return rc;
+  if ((rc = ab2_gar_backward(s, 1.0, stream)) != AB2_OK) // (mueq is unused without constraints)
+    return rc;
+  double *vxo = Vx_out ? Vx_out : s->fddp_vx;
+  ab2::fddp_vx_kernel<<<148 * 4, 256, 0, st>>>(s->out[AB2_OUT_VXX], s->out[AB2_OUT_VX], in->fs, vxo, B, N, nx);
+  CUDA_TRY(cudaGetLastError());
+  s->launches += 1;
+  if (Quuks_out) {
+    ab2::fddp_quuks_kernel<<<148 * 4, 256, 0, st>>>(in->Ju, in->Lu, vxo, Quuks_out, B, N, nx, nu);
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+  }
   return AB2_OK;
 }
 

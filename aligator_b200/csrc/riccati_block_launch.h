@@ -16,5 +16,8 @@ cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStrea
 // leg mode (gar::ParallelRiccatiSolver): condensed block-tridiagonal solve per instance, collapseFeedback
 bool condensed_supported(int nx, int nc0, int legs);
 cudaError_t launch_condensed(const SweepParams &p, int nx, cudaStream_t st);
+// the stage-dense solver (gar::RiccatiSolverDense, riccati_dense.cuh)
+bool dense_supported(int nx, int nu, int nc, int nct, int nc0);
+cudaError_t launch_dense(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st);
 cudaError_t launch_collapse(const SweepParams &p, int nx, int nu, int nc, cudaStream_t st);
 } // namespace ab2

@@ -38,6 +38,13 @@ class LqInputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _LQ_PTRS] + [("preg", C.c_double), ("mu_inv", C.c_double)]
 
 
+_FDDP_KEYS = ("Jx", "Ju", "fs", "Lxx", "Lxu", "Luu", "Lx", "Lu", "Lxx_N", "Lx_N")
+
+
+class FddpInputs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in _FDDP_KEYS] + [("preg", C.c_double)]
+
+
 _LS_KEYS = ("xs", "us", "vs", "vsT", "lam0", "lams")
 
 
@@ -82,6 +89,7 @@ def lib():
         L.ab2_gar_sweep.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.ab2_gar_create_parametric.argtypes = [C.POINTER(GarDims), C.c_int, C.POINTER(C.c_void_p)]
         L.ab2_gar_create_parallel.argtypes = [C.POINTER(GarDims), C.c_int, C.POINTER(C.c_void_p)]
+        L.ab2_gar_create_dense.argtypes = [C.POINTER(GarDims), C.POINTER(C.c_void_p)]
         L.ab2_gar_collapse_feedback.argtypes = [C.c_void_p, C.c_void_p]
         L.ab2_gar_stage_record_doubles_th.restype = C.c_size_t
         L.ab2_gar_term_record_doubles_th.restype = C.c_size_t
@@ -101,6 +109,7 @@ def lib():
         L.ab2_gar_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ab2_gar_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_pivot_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ab2_fddp_backward_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ab2_gar_linear_step.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ab2_gar_directional_derivative.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_al_value.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
@@ -153,14 +162,17 @@ class CudaRiccatiBatch:
     identical dimensions (stage knots (nx,nu,nc), terminal knot (nx,0,nct))."""
 
     def __init__(self, nx, nu, nc, nct, nc0, horizon, batch, device=0, variant=-1, stagger_ns=0,
-                 ctas_per_sm=0, nth=0, legs=0):
+                 ctas_per_sm=0, nth=0, legs=0, dense=False):
         """``legs >= 2``: the parallel-in-time solver (``ab2_gar_create_parallel`` =
         gar::ParallelRiccatiSolver): plain records, value-function parameters nth = nx."""
         self.dims = GarDims(nx, nu, nc, nct, nc0, horizon, batch, device)
         self.legs = int(legs)
+        self.dense = bool(dense)
         self.nth = int(nx) if self.legs else int(nth)
         self.h = C.c_void_p()
-        if self.legs:
+        if self.dense:  # gar::RiccatiSolverDense (ab2_gar_create_dense)
+            _check(lib().ab2_gar_create_dense(C.byref(self.dims), C.byref(self.h)))
+        elif self.legs:
             _check(lib().ab2_gar_create_parallel(C.byref(self.dims), self.legs, C.byref(self.h)))
         else:
             _check(lib().ab2_gar_create_parametric(C.byref(self.dims), self.nth, C.byref(self.h)))
@@ -233,7 +245,7 @@ class CudaRiccatiBatch:
     # ---- results ------------------------------------------------------------
     def out_shape(self, what):
         d = self.dims
-        nr = d.nu + d.nc + d.nx
+        nr = d.nu + d.nc + d.nx + (d.nx if getattr(self, "dense", False) else 0)
         return {
             OUT_FF: (d.batch, d.horizon, nr), OUT_FB: (d.batch, d.horizon, nr, d.nx),
             OUT_VXX: (d.batch, d.horizon + 1, d.nx, d.nx), OUT_VX: (d.batch, d.horizon + 1, d.nx),
@@ -384,6 +396,13 @@ class CudaRiccatiBatch:
                                       AB2_HOST, C.c_void_p(stream)))
         self.synchronize(stream)
         return out
+
+    def fddp_backward_pass(self, arrays, preg, Vx_out=None, Quuks_out=None, stream=0):
+        """SolverFDDP::backwardPass on the device (``ab2_fddp_backward_pass``); ``arrays``: dict of device
+        tensors Jx, Ju, fs, Lxx, Lxu, Luu, Lx, Lu, Lxx_N, Lx_N."""
+        inp = FddpInputs(*[_ptr(arrays[k]).value for k in _FDDP_KEYS], float(preg))
+        self._keep = (arrays, Vx_out, Quuks_out)
+        _check(lib().ab2_fddp_backward_pass(self.h, C.byref(inp), _ptr(Vx_out), _ptr(Quuks_out), C.c_void_p(stream)))
 
     def pivot_stats(self, stream=0):
         """(n_2x2, n_interchanges) per instance of the last backward pass (``ab2_gar_pivot_stats``)."""

@@ -133,6 +133,13 @@ int ab2_gar_forward_theta(ab2_gar_solver *s, const double *theta, int memspace, 
 int ab2_gar_destroy(ab2_gar_solver *s);
 int ab2_gar_set_tuning(ab2_gar_solver *s, const ab2_gar_tuning *t);
 
+/* Replaces: RiccatiSolverDense(const LqrProblemTpl&), gar/dense-riccati.hxx:13-45 -- the reference's second solver
+ * (LQSolverChoice::STAGEDENSE): per knot ONE Bunch-Kaufman factorisation of the (nu + nc + 2 nx)^2 matrix
+ * [[R, D^T, B^T, 0],[D, -mu I, 0, 0],[B, 0, 0, -I],[0, 0, -I, P']] (gar/dense-kernel.hpp:98-113), one CTA per
+ * instance.  Same problem layout and call sequence as ab2_gar_create; FF / FB have nu + nc + 2 nx rows
+ * [k; z; l; y] / [K; Z; L; Y] (dense-kernel.hpp:28-31: u = k + K x, v = z + Z x, lbda' = l + L x, x' = y + Y x),
+ * VXX / VX hold Pxx / px (not symmetrised).  Not the fast path: an independent algorithm on the device. */
+int ab2_gar_create_dense(const ab2_gar_dims *dims, ab2_gar_solver **out);
 /* Replaces: ParallelRiccatiSolver(LqrProblemTpl&, num_threads), gar/parallel-solver.hxx:32-82 -- the
  * parallel-in-time variant.  The horizon of EVERY instance is cut into `num_legs` legs
  * [i(N+1)/T, (i+1)(N+1)/T) (get_work, :23-28); backward() runs the legs of all instances as the work
@@ -294,6 +301,22 @@ int ab2_gar_directional_derivative(ab2_gar_solver *s, const double *Lxs, const d
  * (only lam0, lams, vs, vsT are read). */
 int ab2_gar_al_value(ab2_gar_solver *s, const ab2_ls_iterate *plus, const double *cost, double mudyn, double mucstr,
                      double *dst, int memspace, void *stream);
+
+/* SolverFDDPTpl::backwardPass, solvers/fddp/solver-fddp.hxx:204-277, for a batch: the
+ * unconstrained recursion is the sweep's own stage step with A = Jx, B = Ju, f_i = fs[i+1], Q = Lxx + preg I,
+ * S = Lxu, R = Luu + preg I, q = Lx, r = Lu (nc = 0; the LLT of Quu (:259-260) is the Bunch-Kaufman factorisation
+ * on its all-1x1-pivots path), so this assembles the knots from FDDP's buffers on the device, runs backward()
+ * and adds FDDP's own bookkeeping: Vx_i += Vxx_i fs[i] (:219-220, 274-276) and Quuks_i = Quu_i k_i (:264).
+ * DEVICE pointers: Jx [batch][N][nx*nx], Ju [batch][N][nx*nu] (column-major), fs [batch][N+1][nx], Lxx, Lxu, Luu,
+ * Lx, Lu per stage, Lxx_N [batch][nx*nx], Lx_N [batch][nx].  The solver must have nc = nct = 0, nc0 = nx.
+ * After the call: K_i, k_i = the first nu rows of FB / FF (kkt_fb, kkt_ff), Vxx_i = VXX (symmetric from the lower
+ * triangle, + preg on the diagonal carried by Q); Vx_out [batch][N+1][nx] and Quuks_out [batch][N][nu] (device,
+ * may be NULL) receive FDDP's Vx_ (with the defect term) and Quuks_. */
+typedef struct ab2_fddp_inputs {
+  const double *Jx, *Ju, *fs, *Lxx, *Lxu, *Luu, *Lx, *Lu, *Lxx_N, *Lx_N;
+  double preg;
+} ab2_fddp_inputs;
+int ab2_fddp_backward_pass(ab2_gar_solver *s, const ab2_fddp_inputs *in, double *Vx_out, double *Quuks_out, void *stream);
 
 /* Replaces: cycleAppend(knot), proximal-riccati.hxx:79-86 + the problem rotation the
  * caller performs (solver-proxddp.hxx:202-209): factors and stage knots of every

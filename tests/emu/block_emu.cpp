@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../aligator_b200/csrc/riccati_block.cuh"
+#include "../../aligator_b200/csrc/riccati_dense.cuh"
 
 namespace {
 struct HostBlockCtx {
@@ -160,5 +161,16 @@ extern "C" int emu_block_legs(int nx, int nu, int nc, int nwarps, int mode, cons
     if (int rc = run_block(d, nwarps, p))
       return rc;
   }
+  return 0;
+}
+
+// The stage-dense solver (riccati_dense.cuh) on emulated CTAs.
+extern "C" int emu_dense_sweep(int nx, int nu, int nc, int nwarps, const ab2::SweepParams *pp) {
+  const ab2::DenseDims d = ab2::make_dense_dims(nx, nu, nc, pp->nct, pp->nc0);
+  const int T = 32 * nwarps;
+  if (d.n > T || nx + pp->nc0 > T || nx + 1 > T)
+    return 2;
+  for (int inst = 0; inst < pp->batch; ++inst)
+    run_cta(nwarps, (size_t)d.s_end, [&](HostBlockCtx &ctx, double *sm) { ab2::riccati_dense_sweep(ctx, *pp, d, inst, sm); });
   return 0;
 }

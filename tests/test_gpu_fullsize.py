@@ -300,3 +300,53 @@ def test_cuda_matches_the_stage_dense_algorithm(env, shape):
         assert gen.rel_fro(X[b], np.stack(xs)) <= 1e-9
         assert gen.rel_fro(U[b], np.stack(us)) <= 1e-9
         assert gen.rel_fro(L[b], np.stack(lb[1:])) <= 1e-9
+
+
+@pytest.mark.parametrize("shape", [(12, 6, 0, 0, 40, 40, 1e-8), (4, 2, 2, 0, 30, 300, 1e-3), (14, 7, 3, 2, 20, 7, 1e-3),
+                                   (6, 3, 0, 0, 1, 3, 1e-8)])
+def test_stage_dense_solver_on_device(env, shape):
+    """gar::RiccatiSolverDense on the device (ab2_gar_create_dense, riccati_dense.cuh) against the oracle's
+    restatement of the same algorithm, against the device's own proximal sweep (the two algorithms agree), and
+    through the KKT residuals of every instance."""
+    gar, bench, torch = env
+    from aligator_b200.lqr import LqrKnot
+    nx, nu, nc, nct, N, B, mueq = shape
+    probs = gen.generate_batch(400 + nx, B, N, nx, nu, nc, nct)
+    packed = gar.pack_problems(probs)
+    s = gar.CudaRiccatiBatch(nx, nu, nc, nct, nx, N, B, dense=True)
+    s.set_problem(*packed)
+    s.sweep(mueq)
+    assert np.all(s.status() == 0)
+    assert s.kkt_error(mueq).max() <= 1e-9
+    fb, ff, P, px, X, U, L = (s.get(w) for w in (gar.OUT_FB, gar.OUT_FF, gar.OUT_VXX, gar.OUT_VX, gar.OUT_XS, gar.OUT_US,
+                                                  gar.OUT_LBDAS))
+    assert fb.shape == (B, N, nu + nc + 2 * nx, nx)
+    s2 = gar.CudaRiccatiBatch(nx, nu, nc, nct, nx, N, B)
+    s2.set_problem(*packed)
+    s2.sweep(mueq)
+    fbp, Vp, Xp = s2.get(gar.OUT_FB), s2.get(gar.OUT_VXX), s2.get(gar.OUT_XS)
+    il = np.tril_indices(nx)
+    tolk = max(TOL, 2.4e-16 / mueq) if nc else TOL
+    for b in sorted({0, B // 2, B - 1}):
+        q = probs[b].copy()
+        kt = q.stages[-1]
+        k0 = LqrKnot(nx, 0, nct, 0)
+        k0.Q[:], k0.q[:], k0.C[:], k0.d[:] = kt.Q, kt.q, kt.C, kt.d
+        q.stages[-1] = k0
+        op = orc.OracleProblem(q)
+        dn = orc.RiccatiSolverDense(op)
+        assert dn.backward(mueq)
+        sol = orc.OracleSolution(op)
+        dn.forward(sol)
+        for t in range(N):
+            f = dn.factor(t)
+            assert gen.rel_fro(fb[b, t], f["fb"]) <= tolk and gen.rel_fro(ff[b, t], f["ff"]) <= tolk
+            assert gen.rel_fro(fb[b, t, :nu], fbp[b, t, :nu]) <= tolk            # K: dense == proximal
+            assert gen.rel_fro(P[b, t][il], Vp[b, t][il]) <= TOL                  # Pxx == Vxx (lower)
+        for t in range(N + 1):
+            assert gen.rel_fro(P[b, t], dn.factor(t)["Pxx"]) <= TOL
+        xs, us, vs, lb = sol.get()
+        assert gen.rel_fro(X[b], np.stack(xs)) <= TOL and gen.rel_fro(L[b], np.stack(lb[1:])) <= TOL
+        assert gen.rel_fro(X[b], Xp[b]) <= 1e-9
+    s.close()
+    s2.close()
