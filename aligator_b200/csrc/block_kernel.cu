@@ -17,6 +17,8 @@ struct BlockDevCtx {
   uint32_t phase; // bit p = parity to wait for on barrier p
 
   __device__ __forceinline__ void sync() { __syncthreads(); }
+  // CTA barrier that also ORs a flag over all threads
+  __device__ __forceinline__ int sync_or(int v) { return __syncthreads_or(v); }
   // barrier over the first `nth` threads (whole warps) of the CTA: named barrier 1
   __device__ __forceinline__ void sync_sub(int nth) { asm volatile("bar.sync 1, %0;" ::"r"(nth) : "memory"); }
   __device__ __forceinline__ void wsync() { __syncwarp(); }
@@ -273,8 +275,11 @@ cudaError_t launch_block(const SweepParams &p, int nx, int nu, int nc, cudaStrea
   const size_t smem = block_smem_bytes(nx, nu, nc, p.nc0, p.nth);
   // BASELINE config 5 (Talos whole-body walk, nx 57 nu 28, initial condition on the full state):
   // the same code specialised at compile time
-  if (nx == 57 && nu == 28 && nc == 0 && p.nc0 == 57 && p.nth == 0)
+  if (nx == 57 && nu == 28 && nc == 0 && p.nc0 == 57 && p.nth == 0 && p.legs <= 1)
     return launch_block_t<255>(p, StaticBlockDims<57, 28, 0, 57>{}, threads, smem, st, info);
+  // ... and the reference-faithful Talos dims of SURVEY 0.4 (ndx 56, nu 22)
+  if (nx == 56 && nu == 22 && nc == 0 && p.nc0 == 56 && p.nth == 0 && p.legs <= 1)
+    return launch_block_t<255>(p, StaticBlockDims<56, 22, 0, 56>{}, threads, smem, st, info);
   // one CTA per SM anyway (shared memory): let it use the whole register file
   if (2 * (smem + 1024) > (size_t)227 * 1024)
     return launch_block_t<255>(p, d, threads, smem, st, info);

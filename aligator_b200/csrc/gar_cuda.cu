@@ -451,6 +451,10 @@ static int create_impl(const ab2_gar_dims *dims, int nth, int legs, ab2_gar_solv
   }
   if (const char *f = std::getenv("AB2_DEBUG_FLAGS")) // experiment switches, see SweepParams::dbg
     p.dbg = std::atoi(f);
+  if (std::getenv("AB2_PHASE_CLOCKS")) { // profiling aid of the CTA-per-instance kernel: 16 phase counters
+    cudaMalloc(&p.clk, 16 * sizeof(long long));
+    cudaMemset(p.clk, 0, 16 * sizeof(long long));
+  }
   *out = s;
   return AB2_OK;
 }
@@ -1231,6 +1235,14 @@ int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace
   CUDA_TRY(cudaGetLastError());
   s->have_backward = false;
   s->have_forward = false;
+  return AB2_OK;
+}
+
+int ab2_gar_phase_clocks(ab2_gar_solver *s, long long *dst16) { // AB2_PHASE_CLOCKS=1: cycles per phase, instance 0
+  if (!s || !dst16 || !s->p.clk)
+    return fail(AB2_ERR_STATE, "phase clocks are off (set AB2_PHASE_CLOCKS=1 before create)");
+  CUDA_TRY(cudaMemcpy(dst16, s->p.clk, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(s->p.clk, 0, 16 * sizeof(long long)));
   return AB2_OK;
 }
 

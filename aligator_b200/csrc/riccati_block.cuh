@@ -22,6 +22,7 @@
 namespace ab2 {
 
 struct BlockDims {
+  static constexpr int static_nk = 0; // run-time dimensions: no register-resident factorisation
   int nx, nu, nc; // stage knots
   int nk, nr, nj, mtx, kt, nt, nt2, kt2, njp;
   int off_b, off_f, off_q, off_s, off_r, off_qv, off_rv, off_c, off_d, off_dv, srec_pad;
@@ -91,7 +92,7 @@ AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0, int 
   d.split = (d.off_q % 2 == 0 && rec_nth == 0) ? d.off_q : d.srec_pad;
   d.vs = blk_fstride(4 * d.kt);
   d.vrows = 8 * d.mtx;
-  d.sw = blk_s8(d.njp);
+  d.sw = blk_fstride(d.njp); // (W is read as the B operand of (2): row stride 4 or 12 mod 16, conflict-free)
   d.wrows = 4 * d.kt;
   d.sh = blk_s8(d.njp);
   d.sx = blk_fstride(8 * d.nt2);
@@ -151,6 +152,8 @@ AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0, int 
 // for one shape (loops unroll, addresses fold) behind the same code.
 template <int NX, int NU, int NC, int NC0> struct StaticBlockDims {
   static constexpr BlockDims v = make_block_dims(NX, NU, NC, NC0);
+  // KKT size known at compile time and <= 32 rows: the LDL^T runs from the registers of one warp
+  static constexpr int static_nk = (NC == 0 && NU <= 32) ? NU : 0;
 #define AB2_SD(f) static constexpr int f = v.f;
   AB2_SD(nx) AB2_SD(nu) AB2_SD(nc) AB2_SD(nk) AB2_SD(nr) AB2_SD(nj) AB2_SD(mtx) AB2_SD(kt) AB2_SD(nt) AB2_SD(nt2)
   AB2_SD(kt2) AB2_SD(njp) AB2_SD(off_b) AB2_SD(off_f) AB2_SD(off_q) AB2_SD(off_s) AB2_SD(off_r) AB2_SD(off_qv)
@@ -317,6 +320,192 @@ AB2_D bool ldlt_fast_warp(Ctx &ctx, double *a, const int n, double *dd, double *
   return true;
 }
 
+// phase clocks (profiling aid): thread 0 of the CTA that owns instance 0 accumulates clock64() deltas
+#if defined(__CUDA_ARCH__)
+#define AB2_CLK_INIT long long clk_t0 = (p.clk && inst == 0 && tid == 0) ? clock64() : 0
+#define AB2_CLK(ph)                                                        \
+  do {                                                                     \
+    if (p.clk && inst == 0 && tid == 0) {                                  \
+      const long long now_ = clock64();                                    \
+      p.clk[ph] += now_ - clk_t0;                                          \
+      clk_t0 = now_;                                                       \
+    }                                                                      \
+  } while (0)
+#else
+#define AB2_CLK_INIT (void)0
+#define AB2_CLK(ph) (void)0
+#endif
+
+// LDL^T by the WHOLE CTA of a matrix on which every pivot test of the Bunch-Kaufman algorithm picks
+// the 1x1 pivot in place by its first test (|a_kk| >= alpha*colmax, core/bunchkaufman.hpp:61).  Same
+// arithmetic as bk_factor_group / ldlt_fast_warp on that path, but one thread per ELEMENT of the
+// trailing triangle instead of one lane per row: per column one barrier (which carries the vote),
+// three loads, two flops and a store per thread -- the single-warp routine spent 940 cycles per
+// column at n = 28 walking its row in rounds of four.  Matrix in shared memory (column-major, lda = n);
+// leaves L / dd / sd / perm / kind in bk_factor_group's format.  Returns false at the first failing test
+// (uniform over the CTA) with the matrix partly updated: the caller restores its copy.
+template <class Ctx>
+AB2_D bool ldlt_fast_cta(Ctx &ctx, double *a, const int n, double *dd, double *sd, int *perm, int *kind) {
+  const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
+  const int tid = ctx.tid, lane = ctx.lane, warp = ctx.warp, NW = ctx.nwarps;
+  // n <= 32.  Columns stay UNSCALED during the elimination (the update multiplies by d on the fly,
+  // exactly the reference's (a_jk d) a_ik) and are scaled in one pass at the end.  ONE barrier per
+  // column: warp 0, which produces the next pivot column, tests it from its registers (pivot by
+  // shuffle) and the barrier carries that vote to the CTA.
+  bool bad = false;
+  if (warp == 0) { // test of column 0
+    const double v = lane < n ? a[lane] : 0.0;
+    const double piv = ctx.shfl(v, 0);
+    bad = (lane >= 1 && lane < n && !(fabs(v) * alpha <= fabs(piv))) || (lane == 0 && !(fabs(piv) > 0.0));
+  }
+  if (ctx.sync_or(bad ? 1 : 0))
+    return false;
+  for (int k = 0; k < n; ++k) {
+    const double akk = a[k + k * n];
+    const double d = rcp_fast(akk); // (as FastFactor: within an ulp of 1/akk)
+    if (tid == k) {
+      dd[k] = d;
+      sd[k] = 0.0;
+      kind[k] = 0;
+      perm[k] = k;
+    }
+    // trailing triangle i >= j > k: lane = row offset, the warps deal out the columns; every access
+    // is a broadcast or unit-stride over the lanes
+    const int m = n - k - 1;
+    double mycol = 0.0; // warp 0: the new entry of column k+1 in this lane's row
+    if (lane < m) {
+      const int i = k + 1 + lane;
+      const double aik = a[i + k * n];
+      for (int jj = warp; jj <= lane; jj += NW) {
+        const int j = k + 1 + jj;
+        const double v = a[i + j * n] - (a[j + k * n] * d) * aik;
+        a[i + j * n] = v;
+        if (jj == 0)
+          mycol = v;
+      }
+    }
+    bad = false;
+    if (warp == 0 && m > 0) { // pivot test of column k+1 (rows k+1+lane, lane < m; its pivot sits in lane 0)
+      const double piv = ctx.shfl(mycol, 0);
+      bad = (lane >= 1 && lane < m && !(fabs(mycol) * alpha <= fabs(piv))) || (lane == 0 && !(fabs(piv) > 0.0));
+    }
+    if (ctx.sync_or(bad ? 1 : 0))
+      return false;
+  }
+  for (int e = tid; e < n * n; e += ctx.nthreads) { // L = unscaled columns times d_k
+    const int i = e % n, kcol = e / n;
+    if (i > kcol)
+      a[e] *= dd[kcol];
+  }
+  ctx.sync();
+  return true;
+}
+
+// The same factorisation by ONE warp with the row in REGISTERS (N compile-time, <= 32): lane = row;
+// per column the pivot by shuffle, the test by a vote, then every later column of the row updated
+// with the multiplier shuffled from its own row -- independent shuffles and FMAs, no shared-memory
+// round trip and no CTA barrier inside the elimination (the CTA-wide version above spends ~740
+// cycles per column at n = 28, most of it in its barrier).  Reads the lower triangle from `a`
+// (column-major, lda = N), writes L / dd / sd / perm / kind in bk_factor_group's format.  Returns
+// false at the first failing test WITHOUT having written anything.
+template <int N, int K, class Ctx>
+AB2_D bool ldlt_regs_col(Ctx &ctx, double (&r)[N], double &myd) { // column K, compile-time: static register indices
+  const double alpha = 0.6403882032022076; // (1+sqrt(17))/8
+  const int lane = ctx.lane;
+  const double akk = ctx.shfl(r[K], K);
+  const double my = (lane > K) ? r[K] : 0.0; // a(lane, K) below the diagonal
+  const bool ok = (fabs(my) * alpha <= fabs(akk)) && (fabs(akk) > 0.0);
+  if (!ctx.all(ok))
+    return false;
+  const double d = rcp_fast(akk);
+  if (lane == K)
+    myd = d;
+  const double lk = my * d; // L(lane, K)
+  AB2_UNROLL
+  for (int j = K + 1; j < N; ++j) {
+    const double ljk = ctx.shfl(lk, j); // L(j, K)
+    if (lane >= j)
+      r[j] -= ljk * my; // a_ij -= (a_jk d) a_ik
+  }
+  if (lane > K)
+    r[K] = lk;
+  return true;
+}
+template <int N, class Ctx, int... Ks>
+AB2_D bool ldlt_regs_cols(Ctx &ctx, double (&r)[N], double &myd, std::integer_sequence<int, Ks...>) {
+  return (ldlt_regs_col<N, Ks>(ctx, r, myd) && ...); // stops at the first failing pivot test
+}
+template <int N, class Ctx>
+AB2_D bool ldlt_regs_warp(Ctx &ctx, double *a, double *dd, double *sd, int *perm, int *kind) {
+  const int lane = ctx.lane;
+  double r[N]; // row `lane`: r[j] = a(lane, j), j <= lane
+  AB2_UNROLL
+  for (int j = 0; j < N; ++j)
+    r[j] = (lane < N && j <= lane) ? a[lane + j * N] : 0.0;
+  double myd = 0.0;
+  if (!ldlt_regs_cols<N>(ctx, r, myd, std::make_integer_sequence<int, N>{}))
+    return false;
+  if (lane < N) {
+    AB2_UNROLL
+    for (int j = 0; j < N; ++j)
+      if (j < lane)
+        a[lane + j * N] = r[j];
+    dd[lane] = myd;
+    sd[lane] = 0.0;
+    kind[lane] = 0;
+    perm[lane] = lane;
+  }
+  ctx.wsync();
+  return true;
+}
+
+// [K k] = -(L D L^T)^-1 X for a factor with identity interchanges and 1x1 pivots (what ldlt_fast_cta
+// leaves), n <= 32: one warp per chunk of 8 right-hand-side columns, lane = ROW, the 8 entries of the
+// row in registers.  Per elimination column c the pivot entries travel by shuffle and L(lane, c) is
+// read ONCE for all 8 columns (conflict-free: consecutive lanes, consecutive addresses); the 8
+// chains are independent, so shuffle and FMA latencies overlap.  (The thread-per-column routine
+// re-read x from shared memory behind every store: 31 000 cycles per knot at n = 28 with 58
+// columns on two warps; this uses all the CTA's warps.)  Same substitutions in the same order as
+// bunch_kaufman_solve_in_place on that path (core/bunchkaufman.hpp:472-504).
+// X, K: nk x ncols, row r at r*sx.
+template <class Ctx>
+AB2_D void ldlt_solve_rows_warp(Ctx &ctx, const double *a, const int n, const double *dd, const double *X, double *K,
+                                const int sx, const int ncols) {
+  constexpr int CW = 8; // columns per chunk
+  const int lane = ctx.lane;
+  const bool in = lane < n;
+  const int row = in ? lane : 0;
+  const double myd = in ? dd[row] : 0.0;
+  for (int ch = ctx.warp; ch * CW < ncols; ch += ctx.nwarps) {
+    const int j0 = ch * CW;
+    double x[CW];
+    AB2_UNROLL
+    for (int u = 0; u < CW; ++u)
+      x[u] = (in && j0 + u < ncols) ? X[row * sx + j0 + u] : 0.0;
+    for (int c = 0; c + 1 < n; ++c) { // unit lower, column-oriented
+      const double l = (in && lane > c) ? a[row + c * n] : 0.0;
+      AB2_UNROLL
+      for (int u = 0; u < CW; ++u)
+        x[u] -= l * ctx.shfl(x[u], c);
+    }
+    AB2_UNROLL
+    for (int u = 0; u < CW; ++u)
+      x[u] *= myd;
+    for (int i = n - 1; i >= 1; --i) { // unit upper (L^T)
+      const double l = (in && lane < i) ? a[i + row * n] : 0.0;
+      AB2_UNROLL
+      for (int u = 0; u < CW; ++u)
+        x[u] -= l * ctx.shfl(x[u], i);
+    }
+    if (in) {
+      AB2_UNROLL
+      for (int u = 0; u < CW; ++u)
+        if (j0 + u < ncols)
+          K[row * sx + j0 + u] = -x[u];
+    }
+  }
+}
+
 constexpr int BLK_CH = 4; // n-tiles accumulated together by one warp (one work item)
 
 // ---------------------------------------------------------------------------
@@ -381,6 +570,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
   const bool two_parts = d.split < d.srec_pad;
 
   if (p.do_bwd) {
+    AB2_CLK_INIT;
     int st = ST_OK;
     int pv = 0; // pivot statistics (threads 0..bk_threads-1 all see the same decisions)
     const int t_first = last_leg ? N - 1 : t_hi - 1; // first stage knot of the (descending) loop
@@ -476,50 +666,58 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       const int gmode = !legmode ? 0 : (legl ? 2 : 1); // parametric blocks: record / zero / leg-last
       double *fbt = fb_b + (size_t)t * nr * nx;
       double *fft = ff_b + (size_t)t * nr;
+      AB2_CLK(9);
       ctx.wait_copy(0);
-      // (1) W = V' M (+ vx' on the affine column), :216-224.  Work item = (m-tile, chunk).
-      // No predicates inside: padding columns of M point at the zeroed slack, padding rows
-      // of the contraction meet the zero columns of V'.
-      for (int it = warp; it < d.mtx * nchunk; it += NW) {
-        const int mt = it / nchunk, n0 = (it % nchunk) * BLK_CH;
-        const int ncol = d.nt - n0; // warp-uniform
+      AB2_CLK(0);
+      // (1) W = V' M (+ vx' on the affine column), :216-224, computed as W^T = M^T V' (V' symmetric):
+      // the operand with the awkward shared-memory stride -- a column of M, nx doubles apart in the
+      // record, 2-way bank conflicts for odd and for 8-aligned nx alike -- is then the A operand,
+      // loaded ONCE per k-step, and the four B operands are rows of V' (stride 4 or 12 mod 16:
+      // conflict-free).  Work item = (n-tile of M's columns, chunk of four m-tiles of state rows).
+      // No predicates inside: padding columns of M point at the zeroed slack, padding rows of the
+      // contraction meet the zero columns of V'.
+      const int nchunk_m = (d.mtx + BLK_CH - 1) / BLK_CH;
+      for (int it = warp; it < d.nt * nchunk_m; it += NW) {
+        const int nt = it / nchunk_m, m0 = (it % nchunk_m) * BLK_CH;
+        const int nrow = d.mtx - m0; // warp-uniform
         double acc[BLK_CH][2];
-        const double *mp[BLK_CH];
+        const double *vp[BLK_CH];
         AB2_UNROLL
         for (int c = 0; c < BLK_CH; ++c) {
           acc[c][0] = acc[c][1] = 0.0;
-          mp[c] = rec + blk_col_offset(d, 8 * (n0 + c) + g) + q;
+          vp[c] = Vn + (8 * (m0 + (c < nrow ? c : 0)) + g) * d.vs + q;
         }
-        const double *vp = Vn + (8 * mt + g) * d.vs + q;
-        if (ncol >= BLK_CH) {
+        const double *mp = rec + blk_col_offset(d, 8 * nt + g) + q;
+        if (nrow >= BLK_CH) {
           for (int kt = 0; kt < d.kt; ++kt) {
-            const double va = vp[4 * kt];
+            const double ma = mp[4 * kt];
             AB2_UNROLL
             for (int c = 0; c < BLK_CH; ++c)
-              ctx.mma(acc[c], va, mp[c][4 * kt]);
+              ctx.mma(acc[c], ma, vp[c][4 * kt]);
           }
         } else {
           for (int kt = 0; kt < d.kt; ++kt) {
-            const double va = vp[4 * kt];
+            const double ma = mp[4 * kt];
             AB2_UNROLL
             for (int c = 0; c < BLK_CH; ++c)
-              if (c < ncol)
-                ctx.mma(acc[c], va, mp[c][4 * kt]);
+              if (c < nrow)
+                ctx.mma(acc[c], ma, vp[c][4 * kt]);
           }
         }
-        const int i = 8 * mt + g;
+        const int jp = 8 * nt + g; // logical column of W held by this lane
         AB2_UNROLL
         for (int c = 0; c < BLK_CH; ++c)
-          if (c < ncol && i < nx) {
-            const int jp = 8 * (n0 + c) + 2 * q;
-            if (jp == nx)
-              acc[c][0] += vxn[i];
-            if (jp + 1 == nx)
-              acc[c][1] += vxn[i];
-            sts2(Wsm + i * d.sw + jp, acc[c][0], acc[c][1]);
+          if (c < nrow) {
+            AB2_UNROLL
+            for (int e = 0; e < 2; ++e) {
+              const int i = 8 * (m0 + c) + 2 * q + e;
+              if (i < nx)
+                Wsm[i * d.sw + jp] = acc[c][e] + (jp == nx ? vxn[i] : 0.0);
+            }
           }
       }
       ctx.sync();
+      AB2_CLK(1);
       if (two_parts)
         ctx.wait_copy(1);
       // (2) H = H0 + M^T W  -> Hs, :226-241
@@ -562,6 +760,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
             sts2(Hs + (8 * mt + g) * d.sh + 8 * (n0 + c) + 2 * q, acc[c][0], acc[c][1]);
       }
       ctx.sync();
+      AB2_CLK(2);
       // (3) X = [Shat^T rhat; C d] (nk rows, columns 0..nx) and the KKT matrix, :232-257
       for (int e = tid; e < nk * (nx + 1); e += T) {
         const int c = e / (nx + 1), j = e % (nx + 1);
@@ -591,13 +790,31 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       }
       // Unconstrained knots (SPD Rhat): the branch-free warp LDL^T; anything that needs an
       // interchange or a 2x2 pivot falls back to the general cooperative algorithm on a copy.
-      const bool try_fast = nc == 0 && nk <= 32 && nk * nk <= d.xrows * d.sx;
-      if (try_fast)
+      AB2_CLK(3);
+      // unconstrained knots: LDL^T by the whole CTA (vote per column), else the general algorithm on a copy
+      const bool cta_fast = nc == 0 && nk <= 32 && nk * nk <= d.xrows * d.sx;
+      const bool try_fast = !cta_fast && nc == 0 && nk <= 32 && nk * nk <= d.xrows * d.sx;
+      if (try_fast || cta_fast)
         for (int e = tid; e < nk * nk; e += T)
           Ys[e] = kkt[e]; // Y is free until the solves
-      if (try_fast)
+      if (try_fast || cta_fast)
         ctx.sync();
-      if (tid < bk_threads) { // the other warps go straight to the CTA barrier below
+      int fast_regs = 0; // the pivot-free LDL^T succeeded (uniform over the CTA)
+      constexpr int SNK = D::static_nk;
+      if constexpr (SNK > 0) { // compile-time size: one warp, rows in registers; the others wait at the barrier
+        if (warp == 0)
+          fast_regs = ldlt_regs_warp<SNK>(ctx, kkt, dd, sd, perm, kind) ? 1 : 0;
+        fast_regs = ctx.sync_or(fast_regs); // (the matrix is untouched on failure)
+      } else if (cta_fast) {
+        fast_regs = ldlt_fast_cta(ctx, kkt, nk, dd, sd, perm, kind) ? 1 : 0;
+        if (!fast_regs) {
+          for (int e = tid; e < nk * nk; e += T)
+            kkt[e] = Ys[e];
+          ctx.sync();
+        }
+      }
+      const bool need_general = !fast_regs;
+      if (need_general && tid < bk_threads) { // the other warps go straight to the CTA barrier below
         bool done = false;
         if (try_fast) { // (bk_threads == 32: warp 0)
           done = ldlt_fast_warp(ctx, kkt, nk, dd, sd, perm, kind);
@@ -609,12 +826,16 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
           st |= ST_STAGE_FACTOR_FAILED;
       }
       ctx.sync();
+      AB2_CLK(4);
       // column tid of [K k; Z z] = -KKT^-1 X[:, tid]
       // (four lanes per column with butterfly reductions was measured, with run-time and with
       // compile-time dimensions: more instructions, no shorter -- the chains are latency-bound)
-      if (tid <= nx)
+      if (fast_regs && nk <= 32) // identity interchanges, 1x1 pivots: every warp solves a chunk of columns
+        ldlt_solve_rows_warp(ctx, kkt, nk, dd, X, KKs, d.sx, nx + 1);
+      else if (tid <= nx)
         bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, X + tid, Ys + tid, KKs + tid, d.sx);
       ctx.sync();
+      AB2_CLK(5);
       for (int e = tid; e < nk * nx; e += T) // gains K, Z (row-major nk x nx)
         fbt[e] = KKs[(e / nx) * d.sx + (e % nx)];
       for (int c = tid; c < nk; c += T)
@@ -687,6 +908,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
         }
       }
       ctx.sync();
+      AB2_CLK(6);
       if (nth > 0) { // (8) parametric terms, riccati-kernel.hxx:278-311 -- plain thread-parallel loops
         const double *Am = rec, *Bm = rec + d.off_b;
         // parametric blocks of this knot: from the record (gmode 0), zero (inner knot of a leg),
@@ -771,6 +993,7 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
         thcur ^= 1;
         ctx.sync();
       }
+      AB2_CLK(7);
       if (t > t_lo) {
         const double *src = stage_b + (size_t)stage_slot(p, t - 1) * d.srec_pad;
         ctx.issue_copy(0, rec, src, d.split);

@@ -97,6 +97,7 @@ struct SweepParams {
   // legs = T >= 2: the horizon of every instance is cut into T legs [i(N+1)/T, (i+1)(N+1)/T)
   // (:23-28); a work item of the kernel is one (instance, leg).  nth = nx; records are plain.
   int legs;
+  long long *clk; // profiling aid (null = off): per-phase clock64() sums of instance 0's CTA, riccati_block.cuh
   double *cond; // [batch][nc0 + nx*(2T-1)]: condensed solution [lbda0, x0, (theta_i, x_{head i+1})...] (:92-112)
 };
 

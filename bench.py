@@ -614,6 +614,17 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_knot": bpk, "kernel": "riccati_sweep_kernel",
                 "kernel_ms": kernel_ms}
+    if args.config == "c5":
+        # ~11 flop/B: the bound of this shape is the FP64 pipe, not HBM.  Peak = the DFMA / DMMA rate measured on
+        # this GPU with tools/micro/fp64_rates under ncu (profiles/r02_fp64_rates_ncu.csv: 0.24 DMMA m8n8k4 per
+        # clock per SM = 61.4 FMA/clk/SM, tensor pipe 99.8 % active) x 148 SMs x 1.965 GHz = 35.7 TFLOP/s.
+        fpk = 4 * NX ** 3 + 8 * NX * NX * NU + 4 * NX * NU * NU + NU ** 3 / 3.0 + 2 * NU * NU * (NX + 1) \
+            + 2 * (NU + NX) * NX + 2 * NX * NX   # SURVEY 8(d) flops per knot (backward + forward)
+        tf = B * (N + 1) * fpk / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp64", "achieved": tf, "peak": 35.7, "unit": "TFLOP/s", "frac": tf / 35.7,
+                    "traffic": traffic, "peak_source": "measured DFMA = DMMA rate (tools/micro/fp64_rates, profiles/r02_fp64_rates_ncu.csv)",
+                    "algorithmic_flops_per_knot": fpk, "kernel": "riccati_block_kernel (CTA per instance)",
+                    "kernel_ms": kernel_ms, "hbm": {"achieved": achieved, "peak": peak, "frac": achieved / peak}}
 
     cpu = None
     if not args.no_cpu:

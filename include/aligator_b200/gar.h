@@ -332,6 +332,9 @@ int ab2_fddp_backward_pass(ab2_gar_solver *s, const ab2_fddp_inputs *in, double 
 int ab2_gar_cycle_append(ab2_gar_solver *s, const double *new_last, int memspace, void *stream);
 
 int ab2_gar_ring_heads(const ab2_gar_solver *s, int *factor_head, int *stage_head);
+/* Profiling aid (environment AB2_PHASE_CLOCKS=1 at create): clock64() cycles per phase of the CTA-per-instance
+ * kernel, summed over the knots of instance 0 since the last call; 16 counters (csrc/riccati_block.cuh). */
+int ab2_gar_phase_clocks(ab2_gar_solver *s, long long *dst16);
 
 int ab2_gar_synchronize(ab2_gar_solver *s, void *stream);
 /* Page-locked host memory for the buffers handed to set_problem / get / sweep_host: copies to and

@@ -20,6 +20,18 @@ struct HostBlockCtx {
   std::barrier<> *wbar;
   double *xa, *xb; // this warp's exchange slots
   void sync() { cta->arrive_and_wait(); }
+  int *orflag; // shared by the CTA's threads
+  int sync_or(int v) {
+    if (v)
+      __atomic_store_n(orflag, 1, __ATOMIC_SEQ_CST);
+    cta->arrive_and_wait();
+    const int r = __atomic_load_n(orflag, __ATOMIC_SEQ_CST);
+    cta->arrive_and_wait();
+    if (tid == 0)
+      *orflag = 0;
+    cta->arrive_and_wait();
+    return r;
+  }
   void sync_sub(int nth) { sub[nth / 32 - 1]->arrive_and_wait(); }
   void mma(double (&d)[2], double a, double b) {
     xa[lane] = a;
@@ -106,11 +118,12 @@ template <class F> static void run_cta(int nwarps, size_t smem_doubles, F body) 
     subp.push_back(subs.back().get());
   }
   std::vector<double> xa(T), xb(T);
+  int orflag = 0;
   std::vector<std::thread> th;
   for (int t = 0; t < T; ++t)
     th.emplace_back([&, t] {
       HostBlockCtx ctx{t, T, t / 32, t % 32, nwarps, &cta, subp.data(), wb[t / 32].get(),
-                       xa.data() + 32 * (t / 32), xb.data() + 32 * (t / 32)};
+                       xa.data() + 32 * (t / 32), xb.data() + 32 * (t / 32), &orflag};
       body(ctx, sm.data());
     });
   for (auto &t : th)
