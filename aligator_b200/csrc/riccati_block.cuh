@@ -95,7 +95,7 @@ AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0, int 
   d.sw = blk_fstride(d.njp); // (W is read as the B operand of (2): row stride 4 or 12 mod 16, conflict-free)
   d.wrows = 4 * d.kt;
   d.sh = blk_s8(d.njp);
-  d.sx = blk_fstride(8 * d.nt2);
+  d.sx = blk_fstride(8 * d.nt2 + nth); // columns [K | k | theta columns nx+1..nx+nth]
   d.xrows = 4 * d.kt2;
   int o = 0;
   d.s_rec = o;
@@ -132,11 +132,8 @@ AB2_HD constexpr BlockDims make_block_dims(int nx, int nu, int nc, int nc0, int 
   const int k0 = n0 * n0 + 6 * n0 + 2;
   d.s_end = blk_ev(o > k0 ? o : k0);
   d.s_th = d.s_end;
-  if (nth > 0) { // see ThetaWork below
-    const int nk = nu + nc;
-    d.s_end += blk_ev(2 * nx * nth) + blk_ev(2 * nth * nth) + blk_ev(2 * nth) + blk_ev(nx * nx) + blk_ev(nx) +
-               blk_ev(nx * nth) + blk_ev(nu * nth) + 3 * blk_ev((nk > n0 ? nk : n0) * nth) + blk_ev(nx * nth);
-  }
+  if (nth > 0) // theta workspace: Vxt', Vtt', vt' (double-buffered), Gxhat, 3 x the initial-stage theta columns
+    d.s_end += blk_ev(2 * nx * nth) + blk_ev(2 * nth * nth) + blk_ev(2 * nth) + blk_ev(nx * nth) + 3 * blk_ev(n0 * nth);
   // forward: ring of fb records + two state vectors
   d.fwd_slot = blk_ev(d.nr * nx) + 2; // an odd-sized record is fetched from the aligned double before it
   int ring = (d.s_end - 2 * blk_ev(nx)) / d.fwd_slot;
@@ -459,6 +456,35 @@ AB2_D bool ldlt_regs_warp(Ctx &ctx, double *a, double *dd, double *sd, int *perm
   return true;
 }
 
+// Run-time n <= NP: the matrix is padded to NP with an identity block (pivots 1, nothing below them:
+// the padding columns pass every test and change nothing), so the small KKT matrices of the run-time
+// kernel (n <= 16) take the register path too instead of a CTA barrier per column.
+template <int NP, class Ctx>
+AB2_D bool ldlt_regs_warp_pad(Ctx &ctx, double *a, const int n, double *dd, double *sd, int *perm, int *kind) {
+  const int lane = ctx.lane;
+  double r[NP];
+  AB2_UNROLL
+  for (int j = 0; j < NP; ++j) {
+    const double v = a[(lane < n && j <= lane) ? lane + j * n : 0];
+    r[j] = (lane < n && j <= lane) ? v : (j == lane ? 1.0 : 0.0);
+  }
+  double myd = 0.0;
+  if (!ldlt_regs_cols<NP>(ctx, r, myd, std::make_integer_sequence<int, NP>{}))
+    return false;
+  if (lane < n) {
+    AB2_UNROLL
+    for (int j = 0; j < NP; ++j)
+      if (j < lane)
+        a[lane + j * n] = r[j];
+    dd[lane] = myd;
+    sd[lane] = 0.0;
+    kind[lane] = 0;
+    perm[lane] = lane;
+  }
+  ctx.wsync();
+  return true;
+}
+
 // [K k] = -(L D L^T)^-1 X for a factor with identity interchanges and 1x1 pivots (what ldlt_fast_cta
 // leaves), n <= 32: one warp per chunk of 8 right-hand-side columns, lane = ROW, the 8 entries of the
 // row in registers.  Per elimination column c the pivot entries travel by shuffle and L(lane, c) is
@@ -553,15 +579,11 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
   double *vxt2 = th;                                  // [2][nx*nth]  Vxt' (current / next), column-major
   double *vtt2 = vxt2 + blk_ev(2 * nx * nth);         // [2][nth*nth]
   double *vtv2 = vtt2 + blk_ev(2 * nth * nth);        // [2][nth]
-  double *ahat = vtv2 + blk_ev(2 * nth);              // Ahat row-major [c*nx + i] (closed-loop rows)
-  double *aff = ahat + blk_ev(nx * nx);               // a (closed-loop feedforward rows)
-  double *gxh = aff + blk_ev(nx);                     // Gxhat nx x nth column-major
-  double *guh = gxh + blk_ev(nx * nth);               // Guhat nu x nth column-major
-  const int thn = (nk > nx + nc0 ? nk : nx + nc0) * nth;
-  double *trhs = guh + blk_ev(nu * nth);              // right-hand sides [row][nth]
+  double *gxh = vtv2 + blk_ev(2 * nth);               // Gxhat nx x nth column-major
+  const int thn = (nx + nc0) * nth;                   // the initial-stage solve of the theta columns
+  double *trhs = gxh + blk_ev(nx * nth);              // right-hand sides [row][nth]
   double *twork = trhs + blk_ev(thn);
   double *tsol = twork + blk_ev(thn);
-  double *yth = tsol + blk_ev(thn);                   // Yth nx x nth row-major
   int thcur = 0;                                      // which half of vxt2 / vtt2 / vtv2 holds V'
   double *fth_b = nth ? p.fth + (size_t)inst * N * nr * nth : nullptr;
   double *Vxt_b = nth ? p.Vxt + (size_t)inst * (N + 1) * nx * nth : nullptr;
@@ -666,6 +688,18 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       const int gmode = !legmode ? 0 : (legl ? 2 : 1); // parametric blocks: record / zero / leg-last
       double *fbt = fb_b + (size_t)t * nr * nx;
       double *fft = ff_b + (size_t)t * nr;
+      // parametric blocks of this knot: from the record (gmode 0), zero (inner knot of a leg),
+      // or Gx = A^T, Gu = B^T, Gth = 0, gamma = f (a leg's last knot, parallel-solver.hxx:136-147)
+      const double *Am = rec, *Bm = rec + d.off_b;
+      const double *Gxr = rec + d.off_gx, *Gur = rec + d.off_gu, *Gvr = rec + d.off_gv, *Gthr = rec + d.off_gth,
+                   *gamr = rec + d.off_gam, *fr = rec + d.off_f;
+      auto gx = [&](int i, int j) { return gmode == 0 ? Gxr[i + j * nx] : (gmode == 2 ? Am[j + i * nx] : 0.0); };
+      auto gu = [&](int c, int j) { return gmode == 0 ? Gur[c + j * nu] : (gmode == 2 ? Bm[j + c * nx] : 0.0); };
+      auto gv = [&](int m, int j) { return gmode == 0 ? Gvr[m + j * nc] : 0.0; };
+      auto gth = [&](int e) { return gmode == 0 ? Gthr[e] : 0.0; };
+      auto gam = [&](int i) { return gmode == 0 ? gamr[i] : (gmode == 2 ? fr[i] : 0.0); };
+      const double *Vxtn = vxt2 + thcur * nx * nth, *Vttn = vtt2 + thcur * nth * nth, *vtn = vtv2 + thcur * nth;
+      const int thc = nx + 1; // first theta column of X / KK
       AB2_CLK(9);
       ctx.wait_copy(0);
       AB2_CLK(0);
@@ -782,6 +816,36 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
           v = (r == c) ? -mueq : 0.0;
         kkt[r + c * nk] = v;
       }
+      if (nth > 0) {
+        // (8a) parametric right-hand sides, riccati-kernel.hxx:284-291: Gxhat = Gx + A^T Vxt',
+        // Guhat = Gu + B^T Vxt'; [Guhat; Gv] become the columns nx+1.. of X, so the solves below produce
+        // [Kth; Zth] together with [K k; Z z] (same factor, same routine, all the CTA's warps)
+        const int nxu = nx + nu;
+        for (int e = tid; e < nxu * nth; e += T) {
+          const int j = e / nxu, r = e - j * nxu;
+          const bool isx = r < nx;
+          const int i = isx ? r : r - nx;
+          const double *Mc = isx ? Am + i * nx : Bm + i * nx; // column i of A / B
+          const double *vc = Vxtn + j * nx;
+          double a0 = 0.0, a1 = 0.0;
+          int c = 0;
+          for (; c + 2 <= nx; c += 2) {
+            a0 += Mc[c] * vc[c];
+            a1 += Mc[c + 1] * vc[c + 1];
+          }
+          if (c < nx)
+            a0 += Mc[c] * vc[c];
+          const double acc = a0 + a1;
+          if (isx)
+            gxh[i + j * nx] = gx(i, j) + acc;
+          else
+            X[i * d.sx + thc + j] = gu(i, j) + acc;
+        }
+        for (int e = tid; e < nc * nth; e += T) {
+          const int m = e / nth, j = e - m * nth;
+          X[(nu + m) * d.sx + thc + j] = gv(m, j);
+        }
+      }
       ctx.sync();
       // the tail of the record (cost blocks, C, D, d) is consumed: fetch the next knot's
       if (two_parts && t > t_lo) {
@@ -794,16 +858,25 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       // unconstrained knots: LDL^T by the whole CTA (vote per column), else the general algorithm on a copy
       const bool cta_fast = nc == 0 && nk <= 32 && nk * nk <= d.xrows * d.sx;
       const bool try_fast = !cta_fast && nc == 0 && nk <= 32 && nk * nk <= d.xrows * d.sx;
-      if (try_fast || cta_fast)
+      constexpr int SNK = D::static_nk;
+      const bool regs_pad = SNK == 0 && cta_fast && nk <= 16; // register path, identity-padded to 8 / 16
+      const bool need_copy = try_fast || (cta_fast && SNK == 0 && !regs_pad);
+      if (need_copy)
         for (int e = tid; e < nk * nk; e += T)
           Ys[e] = kkt[e]; // Y is free until the solves
-      if (try_fast || cta_fast)
+      if (need_copy)
         ctx.sync();
       int fast_regs = 0; // the pivot-free LDL^T succeeded (uniform over the CTA)
-      constexpr int SNK = D::static_nk;
       if constexpr (SNK > 0) { // compile-time size: one warp, rows in registers; the others wait at the barrier
         if (warp == 0)
           fast_regs = ldlt_regs_warp<SNK>(ctx, kkt, dd, sd, perm, kind) ? 1 : 0;
+        fast_regs = ctx.sync_or(fast_regs); // (the matrix is untouched on failure)
+      } else if (regs_pad) {
+        if (warp == 0)
+          fast_regs = (nk <= 8 ? ldlt_regs_warp_pad<8>(ctx, kkt, nk, dd, sd, perm, kind)
+                               : ldlt_regs_warp_pad<16>(ctx, kkt, nk, dd, sd, perm, kind))
+                          ? 1
+                          : 0;
         fast_regs = ctx.sync_or(fast_regs); // (the matrix is untouched on failure)
       } else if (cta_fast) {
         fast_regs = ldlt_fast_cta(ctx, kkt, nk, dd, sd, perm, kind) ? 1 : 0;
@@ -831,9 +904,10 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       // (four lanes per column with butterfly reductions was measured, with run-time and with
       // compile-time dimensions: more instructions, no shorter -- the chains are latency-bound)
       if (fast_regs && nk <= 32) // identity interchanges, 1x1 pivots: every warp solves a chunk of columns
-        ldlt_solve_rows_warp(ctx, kkt, nk, dd, X, KKs, d.sx, nx + 1);
-      else if (tid <= nx)
-        bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, X + tid, Ys + tid, KKs + tid, d.sx);
+        ldlt_solve_rows_warp(ctx, kkt, nk, dd, X, KKs, d.sx, nx + 1 + nth);
+      else
+        for (int col = tid; col < nx + 1 + nth; col += T)
+          bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, X + col, Ys + col, KKs + col, d.sx);
       ctx.sync();
       AB2_CLK(5);
       for (int e = tid; e < nk * nx; e += T) // gains K, Z (row-major nk x nx)
@@ -888,8 +962,6 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
                 if (jj < nx) {
                   // (the third block of a leg's terminal knot is never written by the reference, A6)
                   fbt[(nk + i) * nx + jj] = legl ? 0.0 : EA[c][e];
-                  if (nth > 0)
-                    ahat[i * nx + jj] = EA[c][e];
                   if (t == t_lo) // datas[0].Vxx -- and every leg head -- is left unsymmetrised (A1)
                     Vxx_b[(size_t)t * nx * nx + i + jj * nx] = VV[c][e];
                   if (i >= jj) { // V' = lower triangle mirrored (:216 of the next step)
@@ -898,8 +970,6 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
                   }
                 } else if (jj == nx) {
                   fft[nk + i] = legl ? 0.0 : EA[c][e];
-                  if (nth > 0)
-                    aff[i] = EA[c][e];
                   vx_b[(size_t)t * nx + i] = VV[c][e];
                   vxn[i] = VV[c][e];
                 }
@@ -909,84 +979,53 @@ AB2_D void riccati_block_sweep(Ctx &ctx, const SweepParams &p, const D &d, const
       }
       ctx.sync();
       AB2_CLK(6);
-      if (nth > 0) { // (8) parametric terms, riccati-kernel.hxx:278-311 -- plain thread-parallel loops
-        const double *Am = rec, *Bm = rec + d.off_b;
-        // parametric blocks of this knot: from the record (gmode 0), zero (inner knot of a leg),
-        // or Gx = A^T, Gu = B^T, Gth = 0, gamma = f (a leg's last knot, parallel-solver.hxx:136-147)
-        const double *Gxr = rec + d.off_gx, *Gur = rec + d.off_gu, *Gvr = rec + d.off_gv, *Gthr = rec + d.off_gth,
-                     *gamr = rec + d.off_gam, *fr = rec + d.off_f;
-        auto gx = [&](int i, int j) { return gmode == 0 ? Gxr[i + j * nx] : (gmode == 2 ? Am[j + i * nx] : 0.0); };
-        auto gu = [&](int c, int j) { return gmode == 0 ? Gur[c + j * nu] : (gmode == 2 ? Bm[j + c * nx] : 0.0); };
-        auto gv = [&](int m, int j) { return gmode == 0 ? Gvr[m + j * nc] : 0.0; };
-        auto gth = [&](int e) { return gmode == 0 ? Gthr[e] : 0.0; };
-        auto gam = [&](int i) { return gmode == 0 ? gamr[i] : (gmode == 2 ? fr[i] : 0.0); };
-        const double *Vxtn = vxt2 + thcur * nx * nth, *Vttn = vtt2 + thcur * nth * nth, *vtn = vtv2 + thcur * nth;
+      if (nth > 0) {
+        // (8b) parametric value function, riccati-kernel.hxx:293-311.  With Ahat = A + B K and
+        // a = f + B k the reference's sums regroup exactly into the forms it keeps in comments (:297, :301):
+        //   vt  = (gamma + vt') + Guhat^T k + Vxt'^T f,   Vxt = Gxhat + K^T Guhat,
+        //   Vtt = (Gth + Vtt') + Guhat^T Kth
+        // (Guhat sits in X's theta columns, [Kth; Zth] in KK's): four independent loops, one barrier.
         double *Vxtc = vxt2 + (thcur ^ 1) * nx * nth, *Vttc = vtt2 + (thcur ^ 1) * nth * nth,
                *vtc = vtv2 + (thcur ^ 1) * nth;
-        for (int e = tid; e < (nx + nu) * nth; e += T) { // Gxhat = Gx + A^T Vxt', Guhat = Gu + B^T Vxt'
-          const int j = e / (nx + nu), r = e % (nx + nu);
-          const bool isx = r < nx;
-          const int i = isx ? r : r - nx;
-          const double *Mc = isx ? Am + i * nx : Bm + i * nx; // column i of A / B
-          double acc = 0.0;
-          for (int c = 0; c < nx; ++c)
-            acc += Mc[c] * Vxtn[c + j * nx];
-          if (isx)
-            gxh[i + j * nx] = gx(i, j) + acc;
-          else
-            guh[i + j * nu] = gu(i, j) + acc;
-        }
-        ctx.sync();
-        for (int e = tid; e < nk * nth; e += T) { // right-hand sides [Guhat; Gv] (the solve negates)
-          const int r = e / nth, j = e % nth;
-          trhs[e] = (r < nu) ? guh[r + j * nu] : gv(r - nu, j);
-        }
-        ctx.sync();
-        if (tid < nth)
-          bk_solve_column_rt(kkt, nk, dd, sd, perm, kind, trhs + tid, twork + tid, tsol + tid, nth);
-        ctx.sync();
         double *ftt = fth_b + (size_t)t * nr * nth;
-        for (int e = tid; e < nk * nth; e += T) // fth rows [Kth; Zth]
-          ftt[e] = tsol[e];
+        const double *Gh = X + thc, *Kt = KKs + thc; // Guhat[c][j] = Gh[c*sx + j], Kth[c][j] = Kt[c*sx + j]
+        for (int e = tid; e < nk * nth; e += T) { // fth rows [Kth; Zth]
+          const int r = e / nth, j = e - r * nth;
+          ftt[e] = Kt[r * d.sx + j];
+        }
         for (int e = tid; e < nx * nth; e += T) { // Yth = B Kth
-          const int i = e / nth, j = e % nth;
+          const int i = e / nth, j = e - i * nth;
           double acc = 0.0;
           for (int c = 0; c < nu; ++c)
-            acc += Bm[i + c * nx] * tsol[c * nth + j];
-          yth[e] = acc;
+            acc += Bm[i + c * nx] * Kt[c * d.sx + j];
           ftt[nk * nth + e] = legl ? 0.0 : acc; // (never written on a leg's terminal knot)
         }
-        for (int i = tid; i < nth; i += T) { // vt = (gamma + vt') + Gu^T k + Vxt'^T a
+        for (int i = tid; i < nth; i += T) {
           const double s0 = gam(i) + vtn[i];
           double s1 = 0.0, s2 = 0.0;
           for (int c = 0; c < nu; ++c)
-            s1 += gu(c, i) * KKs[c * d.sx + nx];
+            s1 += Gh[c * d.sx + i] * KKs[c * d.sx + nx];
           for (int c = 0; c < nx; ++c)
-            s2 += Vxtn[c + i * nx] * aff[c];
+            s2 += Vxtn[c + i * nx] * fr[c];
           const double v = (s0 + s1) + s2;
           vtc[i] = v;
           vt_b[(size_t)t * nth + i] = v;
         }
-        for (int e = tid; e < nx * nth; e += T) { // Vxt = (Gx + K^T Gu) + Ahat^T Vxt'
-          const int i = e % nx, j = e / nx;
-          double s1 = 0.0, s2 = 0.0;
+        for (int e = tid; e < nx * nth; e += T) {
+          const int j = e / nx, i = e - j * nx;
+          double s1 = 0.0;
           for (int c = 0; c < nu; ++c)
-            s1 += KKs[c * d.sx + i] * gu(c, j);
-          for (int c = 0; c < nx; ++c)
-            s2 += ahat[c * nx + i] * Vxtn[c + j * nx];
-          const double v = (gx(i, j) + s1) + s2;
+            s1 += KKs[c * d.sx + i] * Gh[c * d.sx + j];
+          const double v = gxh[e] + s1;
           Vxtc[e] = v;
           Vxt_b[(size_t)t * nx * nth + e] = v;
         }
-        ctx.sync(); // Yth complete
-        for (int e = tid; e < nth * nth; e += T) { // Vtt = ((Gth + Vtt') + Gu^T Kth) + Vxt'^T Yth
-          const int i = e % nth, j = e / nth;
-          double s1 = 0.0, s2 = 0.0;
+        for (int e = tid; e < nth * nth; e += T) {
+          const int j = e / nth, i = e - j * nth;
+          double s1 = 0.0;
           for (int c = 0; c < nu; ++c)
-            s1 += gu(c, i) * tsol[c * nth + j];
-          for (int c = 0; c < nx; ++c)
-            s2 += Vxtn[c + i * nx] * yth[c * nth + j];
-          const double v = ((gth(e) + Vttn[e]) + s1) + s2;
+            s1 += Gh[c * d.sx + i] * Kt[c * d.sx + j];
+          const double v = (gth(e) + Vttn[e]) + s1;
           Vttc[e] = v;
           Vtt_b[(size_t)t * nth * nth + e] = v;
         }

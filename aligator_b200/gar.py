@@ -456,6 +456,23 @@ def pack_term_knot(k):
     return rec
 
 
+def _pad_terminal_controls(p):
+    """A problem whose terminal knot has controls -> the equivalent problem in the library's layout
+    (terminal nu = 0): knot N becomes a stage knot with A = B = f = 0 and a null terminal knot is
+    appended.  The null knot's value function is zero, so the stage step at knot N reduces to the
+    reference's terminal solve with controls (riccati-kernel.hxx:150-191): same K, k, Z, z, Vxx, vx;
+    the co-state rows of knot N are exact zeros, the reference never writes them."""
+    from .lqr import LqrKnot
+    N = p.horizon
+    kN = p.stages[N].copy()
+    nx, nth = kN.nx, kN.nth
+    kN.nx2 = nx
+    kN.A, kN.B, kN.f = np.zeros((nx, nx), order="F"), np.zeros((nx, kN.nu), order="F"), np.zeros(nx)
+    q = LqrProblem(list(p.stages[:N]) + [kN, LqrKnot(nx, 0, 0, nx, nth)], p.nc0)
+    q.G0, q.g0 = p.G0, p.g0
+    return q
+
+
 def pack_problems(problems):
     """Uniform-dims problems (terminal knot nu = 0, nth = 0) -> (stage, term, G0, g0)."""
     p0 = problems[0]
@@ -505,8 +522,16 @@ class ProximalRiccatiSolver:
         p0 = self.problems[0]
         N = p0.horizon
         kt = p0.stages[N]
-        if kt.nu != 0:
-            raise GarError("the terminal knot must have nu = 0")
+        # A terminal knot WITH controls (terminalSolve's nu > 0 branch, riccati-kernel.hxx:150-173) is
+        # solved as one more stage knot followed by a null terminal knot: the stage step from the zero
+        # value function, with A = B = f = 0, is that branch exactly (see _pad_terminal_controls).
+        self._term_controls = kt.nu != 0
+        if self._term_controls:
+            if N > 0 and (kt.nu, kt.nc) != (p0.stages[0].nu, p0.stages[0].nc):
+                raise GarError("a terminal knot with controls must have the stage knots' (nu, nc)")
+            p0 = _pad_terminal_controls(p0)
+            N = p0.horizon
+            kt = p0.stages[N]
         if N > 0:
             k0 = p0.stages[0]
             nu, nc = k0.nu, k0.nc
@@ -526,7 +551,8 @@ class ProximalRiccatiSolver:
 
     # -- RiccatiSolverBase ---------------------------------------------------
     def backward(self, mueq):
-        stage, term, G0, g0 = pack_problems(self.problems)
+        probs = [_pad_terminal_controls(p) for p in self.problems] if self._term_controls else self.problems
+        stage, term, G0, g0 = pack_problems(probs)
         self.batch.set_problem(stage, term, G0, g0)
         self.batch.backward(mueq)
         self._cache = {}
@@ -550,6 +576,16 @@ class ProximalRiccatiSolver:
         X, U, V, VT = B.get(OUT_XS), B.get(OUT_US), B.get(OUT_VS), B.get(OUT_VST)
         L0, L = B.get(OUT_LBD0), B.get(OUT_LBDAS)
         sols = [(xs, us, vs, lbdas)] if self._single else list(zip(xs, us, vs, lbdas))
+        if self._term_controls:  # internal horizon N = the caller's + 1; the null terminal knot is dropped
+            for b, (x, u, v, l) in enumerate(sols):
+                for t in range(N):
+                    x[t][:] = X[b, t]
+                    u[t][:] = U[b, t]
+                    v[t][:] = V[b, t]
+                    if t + 1 < N:
+                        l[t + 1][:] = L[b, t]
+                l[0][:] = L0[b]
+            return True
         for b, (x, u, v, l) in enumerate(sols):
             for t in range(N + 1):
                 x[t][:] = X[b, t]
@@ -629,6 +665,7 @@ class ParallelRiccatiSolver(ProximalRiccatiSolver):
         self.nx, self.nu, self.nc, self.nct = kt.nx, k0.nu, k0.nc, kt.nc
         self.nth = self.nx
         self.num_threads = int(num_threads)
+        self._term_controls = False
         self.batch = CudaRiccatiBatch(self.nx, self.nu, self.nc, self.nct, p0.nc0, N, len(self.problems),
                                       device, legs=self.num_threads)
         self._single = isinstance(problem, LqrProblem)

@@ -169,14 +169,24 @@ protected:
     if (problems_.empty() || problems_[0]->stages.empty())
       throw RuntimeError("empty problem");
     const LqrProblem &p0 = *problems_[0];
-    const int N = p0.horizon();
+    int N = p0.horizon();
     const LqrKnot &kt = p0.stages[N];
-    if (kt.nu != 0)
-      throw RuntimeError("the terminal knot must have nu = 0");
+    // A terminal knot WITH controls (terminalSolve's nu > 0 branch, riccati-kernel.hxx:150-173) is
+    // solved as one more stage knot with A = B = f = 0 before a null terminal knot: the stage step
+    // from the zero value function is that branch exactly (tests/test_terminal_controls.py).
+    term_controls_ = kt.nu != 0;
+    if (term_controls_) {
+      if (num_legs)
+        throw RuntimeError("the parallel solver needs a terminal knot with nu = 0");
+      if (N > 0 && (kt.nu != p0.stages[0].nu || kt.nc != p0.stages[0].nc))
+        throw RuntimeError("a terminal knot with controls must have the stage knots' (nu, nc)");
+    }
     dims_.nx = (int)kt.nx;
-    dims_.nu = N > 0 ? (int)p0.stages[0].nu : 2;
-    dims_.nc = N > 0 ? (int)p0.stages[0].nc : 0;
-    dims_.nct = (int)kt.nc;
+    dims_.nu = term_controls_ ? (int)kt.nu : N > 0 ? (int)p0.stages[0].nu : 2;
+    dims_.nc = term_controls_ ? (int)kt.nc : N > 0 ? (int)p0.stages[0].nc : 0;
+    dims_.nct = term_controls_ ? 0 : (int)kt.nc;
+    if (term_controls_)
+      ++N; // the library's horizon: the caller's knots 0..N are its stage knots
     dims_.nc0 = (int)p0.nc0();
     dims_.horizon = N;
     dims_.batch = (int)problems_.size();
@@ -291,13 +301,19 @@ private:
       dst[i] = src[i];
     return dst + n;
   }
-  void pack_stage(const LqrKnot &k, double *o) const {
+  void pack_stage(const LqrKnot &k, double *o, bool last_with_controls = false) const {
     const size_t nx = dims_.nx, nu = dims_.nu, nc = dims_.nc;
-    if (k.nx != nx || k.nu != nu || k.nc != nc || k.nx2 != nx || k.nth != 0)
+    if (k.nx != nx || k.nu != nu || k.nc != nc || (k.nx2 != nx && !last_with_controls) || k.nth != 0)
       throw RuntimeError("stage knot dims differ from the solver's (uniform dims, nx2 = nx, nth = 0)");
-    o = put(o, k.A, nx * nx, "A");
-    o = put(o, k.B, nx * nu, "B");
-    o = put(o, k.f, nx, "f");
+    if (last_with_controls) { // no successor: A = B = f = 0
+      for (size_t i = 0; i < nx * nx + nx * nu + nx; ++i)
+        o[i] = 0.;
+      o += nx * nx + nx * nu + nx;
+    } else {
+      o = put(o, k.A, nx * nx, "A");
+      o = put(o, k.B, nx * nu, "B");
+      o = put(o, k.f, nx, "f");
+    }
     o = put(o, k.Q, nx * nx, "Q");
     o = put(o, k.S, nx * nu, "S");
     o = put(o, k.R, nu * nu, "R");
@@ -312,18 +328,20 @@ private:
     const size_t nx = dims_.nx, nct = dims_.nct;
     for (int b = 0; b < dims_.batch; ++b) {
       const LqrProblem &p = *problems_[b];
-      if (p.horizon() != N || (int)p.nc0() != dims_.nc0)
+      if ((int)p.horizon() + (term_controls_ ? 1 : 0) != N || (int)p.nc0() != dims_.nc0)
         throw RuntimeError("problems of a batch must share horizon and nc0");
       for (int t = 0; t < N; ++t)
-        pack_stage(p.stages[t], stage_.data() + ((size_t)b * N + t) * srec_);
-      const LqrKnot &k = p.stages[N];
-      if (k.nx != nx || k.nu != 0 || k.nc != nct)
-        throw RuntimeError("terminal knot dims differ from the solver's");
-      double *o = term_.data() + (size_t)b * trec_;
-      o = put(o, k.Q, nx * nx, "Q");
-      o = put(o, k.q, nx, "q");
-      o = put(o, k.C, nct * nx, "C");
-      o = put(o, k.d, nct, "d");
+        pack_stage(p.stages[t], stage_.data() + ((size_t)b * N + t) * srec_, term_controls_ && t == N - 1);
+      if (!term_controls_) { // (with terminal controls the library's terminal knot is null: term_ stays zero)
+        const LqrKnot &k = p.stages[N];
+        if (k.nx != nx || k.nu != 0 || k.nc != nct)
+          throw RuntimeError("terminal knot dims differ from the solver's");
+        double *o = term_.data() + (size_t)b * trec_;
+        o = put(o, k.Q, nx * nx, "Q");
+        o = put(o, k.q, nx, "q");
+        o = put(o, k.C, nct * nx, "C");
+        o = put(o, k.d, nct, "d");
+      }
       put(G0_.data() + (size_t)b * dims_.nc0 * nx, p.G0, (size_t)dims_.nc0 * nx, "G0");
       put(g0_.data() + (size_t)b * dims_.nc0, p.g0, (size_t)dims_.nc0, "g0");
     }
@@ -352,6 +370,17 @@ private:
   void scatter(int b, std::vector<VectorXs> &xs, std::vector<VectorXs> &us, std::vector<VectorXs> &vs,
                std::vector<VectorXs> &lbdas) const {
     const int N = dims_.horizon, nx = dims_.nx, nu = dims_.nu, nc = dims_.nc;
+    if (term_controls_) { // the caller's horizon is N-1: N states, N controls, N multipliers; the null knot is dropped
+      for (int t = 0; t < N; ++t) {
+        xs[t].assign(xs_.begin() + ((size_t)b * (N + 1) + t) * nx, xs_.begin() + ((size_t)b * (N + 1) + t + 1) * nx);
+        us[t].assign(us_.begin() + ((size_t)b * N + t) * nu, us_.begin() + ((size_t)b * N + t + 1) * nu);
+        vs[t].assign(vs_.begin() + ((size_t)b * N + t) * nc, vs_.begin() + ((size_t)b * N + t + 1) * nc);
+        if (t + 1 < N)
+          lbdas[t + 1].assign(ls_.begin() + ((size_t)b * N + t) * nx, ls_.begin() + ((size_t)b * N + t + 1) * nx);
+      }
+      lbdas[0].assign(l0_.begin() + (size_t)b * dims_.nc0, l0_.begin() + (size_t)(b + 1) * dims_.nc0);
+      return;
+    }
     for (int t = 0; t <= N; ++t)
       xs[t].assign(xs_.begin() + ((size_t)b * (N + 1) + t) * nx, xs_.begin() + ((size_t)b * (N + 1) + t + 1) * nx);
     for (int t = 0; t < N; ++t) {
@@ -367,6 +396,7 @@ private:
   ab2_gar_dims dims_{};
   ab2_gar_solver *h_ = nullptr;
   size_t srec_ = 0, trec_ = 0;
+  bool term_controls_ = false;
   // pinned staging: uploads and downloads are asynchronous on the stream, one synchronisation per call
   PinnedBuf stage_, term_, G0_, g0_;
   PinnedBuf ff_, fb_, ffT_, fbT_;

@@ -134,8 +134,40 @@ static int check_parallel(unsigned nx, unsigned nu, int N, unsigned num_threads,
   return (xerr <= 1e-7 && lerr <= 1e-7 && e.max() <= 1e-7) ? 0 : 8; // TOL of tests/gar/parallel.cpp:193
 }
 
+// A terminal knot with controls (riccati-kernel.hxx:150-173): the class pads it; against the oracle's
+// restatement of that branch.
+static int check_terminal_controls(unsigned nx, unsigned nu, unsigned nc, int N, double mueq, unsigned seed) {
+  std::mt19937 rng(seed);
+  ab::LqrProblem prob = random_problem(rng, nx, nu, nc, N + 1);
+  prob.stages.pop_back(); // knots 0..N all have controls, knot N is the terminal one
+  ab::CudaRiccatiSolver solver(prob);
+  if (!solver.backward(mueq)) return 128;
+  std::vector<ab::VectorXs> xs, us, vs, lbdas;
+  ab::lqrInitializeSolution(prob, xs, us, vs, lbdas);
+  if (us.size() != (size_t)N + 1) return 129;
+  solver.forward(xs, us, vs, lbdas);
+  orc::Problem op = to_oracle(prob);
+  orc::ProximalRiccatiSolver ref(op);
+  ref.backward(mueq);
+  orc::Solution sol = orc::lqrInitializeSolution(op);
+  ref.forward(sol);
+  double worst = 0;
+  for (int t = 0; t <= N; ++t) {
+    worst = std::max(worst, rel_fro(xs[t].data(), sol.xs[t].data(), nx));
+    worst = std::max(worst, rel_fro(us[t].data(), sol.us[t].data(), nu));
+    if (nc) worst = std::max(worst, rel_fro(vs[t].data(), sol.vs[t].data(), nc));
+    worst = std::max(worst, rel_fro(lbdas[t].data(), sol.lbdas[t].data(), lbdas[t].size()));
+    auto V = solver.Vxx(t);
+    worst = std::max(worst, rel_fro(V.data(), ref.datas[t].vm.Vxx.data(), V.size()));
+  }
+  std::printf("terminal knot with controls nx=%u nu=%u nc=%u N=%d: max rel-Frobenius vs oracle %.2e\n", nx, nu, nc, N, worst);
+  return worst <= 1e-10 ? 0 : 130;
+}
+
 int main() {
   int rc = 0;
+  rc |= check_terminal_controls(6, 3, 0, 10, 1e-8, 21);
+  rc |= check_terminal_controls(4, 2, 2, 7, 1e-3, 22);
   rc |= check_parallel(6, 3, 50, 4, 1e-9, 11);
   rc |= check_parallel(14, 7, 100, 6, 1e-9, 12);
   rc |= check_one(2, 2, 0, 8, 1e-14, 1);

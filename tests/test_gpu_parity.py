@@ -602,6 +602,44 @@ def test_parametric_problems(gar, shape):
         assert gen.rel_fro(L0[b], lb[0]) <= tol and gen.rel_fro(L[b], np.array(lb[1:])) <= tol
 
 
+@pytest.mark.parametrize("shape", [(4, 2, 0, 5, 1e-8), (6, 3, 2, 7, 1e-3), (12, 6, 0, 20, 1e-9), (5, 3, 2, 0, 1e-2)])
+def test_terminal_knot_with_controls(gar, shape):
+    """A terminal knot with nu > 0 (terminalSolve's second branch, riccati-kernel.hxx:150-173; the
+    reference's lqr_initialize_solution then has N+1 controls, gar/utils.hpp:120-131) through the Python
+    mirror: solved as one more stage knot before a null terminal knot; against the oracle, which
+    restates the reference's branch directly."""
+    nx, nu, nc, N, mueq = shape
+    probs = []
+    for b in range(3):
+        rng = np.random.default_rng(900 + b)
+        p = gen.generate_lq_problem(rng, rng.standard_normal(nx), N, nx, nu, nc=nc, singular=False, conditioned=True)
+        p.stages[N] = gen.generate_knot(rng, nx, nu, nc, 0, False, conditioned=True)
+        probs.append(p)
+    solver = gar.ProximalRiccatiSolver(probs)
+    assert solver.backward(mueq)
+    sols = [gar.lqr_initialize_solution(p) for p in probs]
+    assert all(len(s[1]) == N + 1 for s in sols)
+    assert solver.forward(*[list(z) for z in zip(*sols)])
+    for b, p in enumerate(probs):
+        op = orc.OracleProblem(p)
+        ref = orc.ProximalRiccatiSolver(op)
+        assert ref.backward(mueq)
+        for t in range(N + 1):
+            f = ref.factor(t)
+            rows = nu + nc if t == N else nu + nc + nx  # the terminal knot's co-state rows are never written
+            assert gen.rel_fro(solver.getFeedback(t, b)[:rows], f["fb"][:rows]) <= TOL, t
+            assert gen.rel_fro(solver.getFeedforward(t, b)[:rows], f["ff"][:rows]) <= TOL, t
+            assert gen.rel_fro(solver.Vxx(t, b), f["Vxx"]) <= TOL and gen.rel_fro(solver.vx(t, b), f["vx"]) <= TOL
+        assert np.all(solver.getFeedback(N, b)[nu + nc:] == 0.0)
+        sol = orc.OracleSolution(op)
+        assert ref.forward(sol)
+        xs, us, vs, lb = sol.get()
+        mx, mu_, mv, ml = sols[b]
+        assert len(us) == N + 1
+        for mine, theirs in ((mx, xs), (mu_, us), (mv, vs), (ml, lb)):
+            assert gen.rel_fro(np.concatenate(mine), np.concatenate(theirs)) <= TOL
+
+
 PAR_SHAPES = [  # (nx, nu, nc, nct, N, legs, batch, mueq)
     (4, 2, 0, 0, 11, 3, 3, 1e-8), (6, 3, 0, 0, 20, 4, 5, 1e-8), (4, 2, 2, 0, 13, 2, 4, 1e-3),
     (14, 7, 0, 0, 200, 8, 6, 1e-9),   # BASELINE config 4 dims, 8 legs of 25 knots
