@@ -473,6 +473,35 @@ def _pad_terminal_controls(p):
     return q
 
 
+def _pad_knot(k, nu, nc):
+    """Stage knot with (k.nu, k.nc) <= (nu, nc) -> the equivalent knot of dims (nx, nu, nc): the extra
+    controls are decoupled (R = I on their diagonal, zero S / B / r columns: their gains are exact
+    zeros), the extra constraint rows are null (C = D = 0, d = 0: their multipliers are exact zeros).
+    The KKT matrix is block diagonal with the caller's block first, so the factorisation of that block,
+    interchanges included, is the reference's (tests/test_terminal_controls.py)."""
+    from .lqr import LqrKnot
+    if (k.nu, k.nc) == (nu, nc):
+        return k
+    if k.nu > nu or k.nc > nc:
+        raise GarError("knot dims exceed the solver's")
+    q = LqrKnot(k.nx, nu, nc, k.nx2, k.nth)
+    q.Q[:], q.q[:], q.A[:], q.f[:] = k.Q, k.q, k.A, k.f
+    q.S[:, :k.nu], q.B[:, :k.nu], q.r[:k.nu] = k.S, k.B, k.r
+    q.R[:k.nu, :k.nu] = k.R
+    q.R[range(k.nu, nu), range(k.nu, nu)] = 1.0
+    q.C[:k.nc], q.D[:k.nc, :k.nu], q.d[:k.nc] = k.C, k.D, k.d
+    if k.nth:
+        q.Gth[:], q.Gx[:], q.gamma[:] = k.Gth, k.Gx, k.gamma
+        q.Gu[:k.nu], q.Gv[:k.nc] = k.Gu, k.Gv
+    return q
+
+
+def _pad_stage_dims(p, nu, nc):
+    q = LqrProblem([_pad_knot(k, nu, nc) for k in p.stages[:-1]] + [p.stages[-1]], p.nc0)
+    q.G0, q.g0 = p.G0, p.g0
+    return q
+
+
 def pack_problems(problems):
     """Uniform-dims problems (terminal knot nu = 0, nth = 0) -> (stage, term, G0, g0)."""
     p0 = problems[0]
@@ -527,14 +556,15 @@ class ProximalRiccatiSolver:
         # value function, with A = B = f = 0, is that branch exactly (see _pad_terminal_controls).
         self._term_controls = kt.nu != 0
         if self._term_controls:
-            if N > 0 and (kt.nu, kt.nc) != (p0.stages[0].nu, p0.stages[0].nc):
-                raise GarError("a terminal knot with controls must have the stage knots' (nu, nc)")
             p0 = _pad_terminal_controls(p0)
             N = p0.horizon
             kt = p0.stages[N]
+        # Stage knots of different (nu, nc) (gar/lqr-problem.hpp:49-118 lets every knot have its own) are
+        # padded to the largest with decoupled controls / null constraint rows (_pad_knot).
+        self._knot_dims = [(k.nu, k.nc) for k in p0.stages[:N]]
+        self._ragged = len(set(self._knot_dims)) > 1
         if N > 0:
-            k0 = p0.stages[0]
-            nu, nc = k0.nu, k0.nc
+            nu, nc = max(d[0] for d in self._knot_dims), max(d[1] for d in self._knot_dims)
         else:
             nu, nc = 1, 0  # no stage knots: any instantiated shape serves
         self.nth = p0.ntheta  # parametric problems run the CTA-per-instance kernel
@@ -552,6 +582,11 @@ class ProximalRiccatiSolver:
     # -- RiccatiSolverBase ---------------------------------------------------
     def backward(self, mueq):
         probs = [_pad_terminal_controls(p) for p in self.problems] if self._term_controls else self.problems
+        if self._ragged:
+            for p in probs:
+                if [(k.nu, k.nc) for k in p.stages[:-1]] != self._knot_dims:
+                    raise GarError("all problems of a batch must share the per-knot dims")
+            probs = [_pad_stage_dims(p, self.nu, self.nc) for p in probs]
         stage, term, G0, g0 = pack_problems(probs)
         self.batch.set_problem(stage, term, G0, g0)
         self.batch.backward(mueq)
@@ -580,8 +615,8 @@ class ProximalRiccatiSolver:
             for b, (x, u, v, l) in enumerate(sols):
                 for t in range(N):
                     x[t][:] = X[b, t]
-                    u[t][:] = U[b, t]
-                    v[t][:] = V[b, t]
+                    u[t][:] = U[b, t, :len(u[t])]
+                    v[t][:] = V[b, t, :len(v[t])]
                     if t + 1 < N:
                         l[t + 1][:] = L[b, t]
                 l[0][:] = L0[b]
@@ -590,8 +625,8 @@ class ProximalRiccatiSolver:
             for t in range(N + 1):
                 x[t][:] = X[b, t]
             for t in range(N):
-                u[t][:] = U[b, t]
-                v[t][:] = V[b, t]
+                u[t][:] = U[b, t, :len(u[t])]  # (ragged problems: the padding entries are dropped)
+                v[t][:] = V[b, t, :len(v[t])]
                 l[t + 1][:] = L[b, t]
             v[N][:] = VT[b]
             l[0][:] = L0[b]
@@ -605,19 +640,26 @@ class ProximalRiccatiSolver:
             self._cache[what] = self.batch.get(what)
         return self._cache[what]
 
+    def _rows(self, i):
+        """Rows of knot i's [k; z; a] blocks that belong to the caller's knot (all, unless padded)."""
+        if not self._ragged:
+            return slice(None)
+        nu_i, nc_i = self._knot_dims[i]
+        return np.r_[0:nu_i, self.nu:self.nu + nc_i, self.nu + self.nc:self.nu + self.nc + self.nx]
+
     def getFeedforward(self, i, b=0):
         """ff = [k; z; a] of knot i (length nu+nc+nx); the terminal knot's is [z]."""
         N = self.batch.dims.horizon
-        return self._get(OUT_FFT)[b] if i == N else self._get(OUT_FF)[b, i]
+        return self._get(OUT_FFT)[b] if i == N else self._get(OUT_FF)[b, i][self._rows(i)]
 
     def getFeedback(self, i, b=0):
         """fb = [K; Z; Ahat] of knot i, (nu+nc+nx) x nx; the terminal knot's is [Z]."""
         N = self.batch.dims.horizon
-        return self._get(OUT_FBT)[b] if i == N else self._get(OUT_FB)[b, i]
+        return self._get(OUT_FBT)[b] if i == N else self._get(OUT_FB)[b, i][self._rows(i)]
 
     def getFeedbackTheta(self, i, b=0):
         """fth = [Kth; Zth; Yth] of stage knot i, (nu+nc+nx) x nth (StageFactor::fth)."""
-        return self._get(OUT_FTH)[b, i]
+        return self._get(OUT_FTH)[b, i][self._rows(i)]
 
     def kkt0(self, b=0):
         """ff, fth of the initial stage and thGrad, thHess (proximal-riccati.hpp:40-43)."""
@@ -666,6 +708,7 @@ class ParallelRiccatiSolver(ProximalRiccatiSolver):
         self.nth = self.nx
         self.num_threads = int(num_threads)
         self._term_controls = False
+        self._ragged = False
         self.batch = CudaRiccatiBatch(self.nx, self.nu, self.nc, self.nct, p0.nc0, N, len(self.problems),
                                       device, legs=self.num_threads)
         self._single = isinstance(problem, LqrProblem)

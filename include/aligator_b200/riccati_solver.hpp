@@ -17,10 +17,12 @@
 // riccati-kernel.hxx:239-241).  No CPU fallback exists.
 #pragma once
 
+#include <algorithm>
 #include <cstddef>
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "gar.h"
@@ -175,18 +177,27 @@ protected:
     // solved as one more stage knot with A = B = f = 0 before a null terminal knot: the stage step
     // from the zero value function is that branch exactly (tests/test_terminal_controls.py).
     term_controls_ = kt.nu != 0;
-    if (term_controls_) {
-      if (num_legs)
-        throw RuntimeError("the parallel solver needs a terminal knot with nu = 0");
-      if (N > 0 && (kt.nu != p0.stages[0].nu || kt.nc != p0.stages[0].nc))
-        throw RuntimeError("a terminal knot with controls must have the stage knots' (nu, nc)");
-    }
-    dims_.nx = (int)kt.nx;
-    dims_.nu = term_controls_ ? (int)kt.nu : N > 0 ? (int)p0.stages[0].nu : 2;
-    dims_.nc = term_controls_ ? (int)kt.nc : N > 0 ? (int)p0.stages[0].nc : 0;
-    dims_.nct = term_controls_ ? 0 : (int)kt.nc;
+    if (term_controls_ && num_legs)
+      throw RuntimeError("the parallel solver needs a terminal knot with nu = 0");
     if (term_controls_)
       ++N; // the library's horizon: the caller's knots 0..N are its stage knots
+    // Stage knots of different (nu, nc) (gar/lqr-problem.hpp:49-118 lets every knot have its own) are
+    // padded to the largest with decoupled controls (R = I on their diagonal, zero S / B / r columns)
+    // and null constraint rows: the KKT matrix is block diagonal with the caller's block first, so its
+    // factorisation is the reference's; the padding rows of the gains are exact zeros and are dropped.
+    size_t numax = 0, ncmax = 0;
+    for (int t = 0; t < N; ++t) {
+      knot_dims_.emplace_back((int)p0.stages[t].nu, (int)p0.stages[t].nc);
+      numax = std::max<size_t>(numax, p0.stages[t].nu);
+      ncmax = std::max<size_t>(ncmax, p0.stages[t].nc);
+      ragged_ = ragged_ || knot_dims_[t] != knot_dims_[0];
+    }
+    if (ragged_ && num_legs)
+      throw RuntimeError("the parallel solver needs uniform stage dims");
+    dims_.nx = (int)kt.nx;
+    dims_.nu = N > 0 ? (int)numax : 2;
+    dims_.nc = N > 0 ? (int)ncmax : 0;
+    dims_.nct = term_controls_ ? 0 : (int)kt.nc;
     dims_.nc0 = (int)p0.nc0();
     dims_.horizon = N;
     dims_.batch = (int)problems_.size();
@@ -224,6 +235,7 @@ public:
       check(ab2_gar_get(h_, AB2_OUT_FBT, fbT_.data(), AB2_HOST, nullptr));
     }
     check(ab2_gar_synchronize(h_, nullptr));
+    compact_gains();
     for (int b = 0; b < dims_.batch; ++b)
       if (st[b] & 1)
         throw RuntimeError("Failed stage LDL factorization (instance " + std::to_string(b) + ")");
@@ -250,6 +262,8 @@ public:
 
   /// proximal-riccati.hxx:79-86 (same knot appended to every instance)
   void cycleAppend(const LqrKnot &knot) override {
+    if (ragged_ || term_controls_)
+      throw RuntimeError("cycleAppend needs uniform stage dims and a terminal knot with nu = 0");
     std::vector<double> rec((size_t)dims_.batch * srec_, 0.);
     for (int b = 0; b < dims_.batch; ++b)
       pack_stage(knot, rec.data() + (size_t)b * srec_);
@@ -265,12 +279,17 @@ public:
     const int N = dims_.horizon, nr = dims_.nu + dims_.nc + dims_.nx;
     if ((int)i == N)
       return {ffT_.data() + (size_t)b * dims_.nct, dims_.nct};
+    if (ragged_) // compacted in place by compact_gains(): [k; z; a] of the caller's dims
+      return {ff_.data() + ((size_t)b * N + i) * nr, knot_dims_[i].first + knot_dims_[i].second + dims_.nx};
     return {ff_.data() + ((size_t)b * N + i) * nr, nr};
   }
   RowMatrixRef getFeedback(size_t i, int b) {
     const int N = dims_.horizon, nr = dims_.nu + dims_.nc + dims_.nx;
     if ((int)i == N)
       return {fbT_.data() + (size_t)b * dims_.nct * dims_.nx, dims_.nct, dims_.nx};
+    if (ragged_)
+      return {fb_.data() + ((size_t)b * N + i) * nr * dims_.nx, knot_dims_[i].first + knot_dims_[i].second + dims_.nx,
+              dims_.nx};
     return {fb_.data() + ((size_t)b * N + i) * nr * dims_.nx, nr, dims_.nx};
   }
   /// datas[i].vm.Vxx (column-major nx*nx) / vm.vx, fetched on demand
@@ -301,27 +320,59 @@ private:
       dst[i] = src[i];
     return dst + n;
   }
+  /// column-major rows x cols block `src` into a block of leading dimension ld (>= rows); the rest stays as it is
+  template <class Vec>
+  static void put_block(double *dst, size_t ld, const Vec &src, size_t rows, size_t cols, const char *name) {
+    if (src.size() != rows * cols)
+      throw RuntimeError(std::string("knot field has the wrong size: ") + name);
+    for (size_t j = 0; j < cols; ++j)
+      for (size_t i = 0; i < rows; ++i)
+        dst[i + j * ld] = src[i + j * rows];
+  }
   void pack_stage(const LqrKnot &k, double *o, bool last_with_controls = false) const {
     const size_t nx = dims_.nx, nu = dims_.nu, nc = dims_.nc;
-    if (k.nx != nx || k.nu != nu || k.nc != nc || (k.nx2 != nx && !last_with_controls) || k.nth != 0)
-      throw RuntimeError("stage knot dims differ from the solver's (uniform dims, nx2 = nx, nth = 0)");
-    if (last_with_controls) { // no successor: A = B = f = 0
-      for (size_t i = 0; i < nx * nx + nx * nu + nx; ++i)
-        o[i] = 0.;
-      o += nx * nx + nx * nu + nx;
-    } else {
-      o = put(o, k.A, nx * nx, "A");
-      o = put(o, k.B, nx * nu, "B");
-      o = put(o, k.f, nx, "f");
+    if (k.nx != nx || k.nu > nu || k.nc > nc || (k.nx2 != nx && !last_with_controls) || k.nth != 0)
+      throw RuntimeError("stage knot dims differ from the solver's (nx2 = nx, nth = 0)");
+    for (size_t i = 0; i < srec_; ++i)
+      o[i] = 0.;
+    double *A = o, *B = A + nx * nx, *f = B + nx * nu, *Q = f + nx, *S = Q + nx * nx, *R = S + nx * nu,
+           *q = R + nu * nu, *r = q + nx, *C = r + nu, *D = C + nc * nx, *d = D + nc * nu;
+    if (!last_with_controls) { // (a terminal knot with controls has no successor: A = B = f = 0)
+      put_block(A, nx, k.A, nx, nx, "A");
+      put_block(B, nx, k.B, nx, k.nu, "B");
+      put_block(f, nx, k.f, nx, 1, "f");
     }
-    o = put(o, k.Q, nx * nx, "Q");
-    o = put(o, k.S, nx * nu, "S");
-    o = put(o, k.R, nu * nu, "R");
-    o = put(o, k.q, nx, "q");
-    o = put(o, k.r, nu, "r");
-    o = put(o, k.C, nc * nx, "C");
-    o = put(o, k.D, nc * nu, "D");
-    o = put(o, k.d, nc, "d");
+    put_block(Q, nx, k.Q, nx, nx, "Q");
+    put_block(S, nx, k.S, nx, k.nu, "S");
+    put_block(R, nu, k.R, k.nu, k.nu, "R");
+    for (size_t c = k.nu; c < nu; ++c)
+      R[c + c * nu] = 1.0; // padding controls: decoupled, gain rows exactly zero
+    put_block(q, nx, k.q, nx, 1, "q");
+    put_block(r, nu, k.r, k.nu, 1, "r");
+    put_block(C, nc, k.C, k.nc, nx, "C");
+    put_block(D, nc, k.D, k.nc, k.nu, "D");
+    put_block(d, nc, k.d, k.nc, 1, "d");
+  }
+  /// ragged problems: drop the padding rows of every knot's [k; z; a] / [K; Z; Ahat] in the staging buffers
+  void compact_gains() {
+    if (!ragged_)
+      return;
+    const int N = dims_.horizon, nx = dims_.nx, nu = dims_.nu, nc = dims_.nc, nr = nu + nc + nx;
+    for (int b = 0; b < dims_.batch; ++b)
+      for (int t = 0; t < N; ++t) {
+        const int nut = knot_dims_[t].first, nct = knot_dims_[t].second;
+        double *ff = ff_.data() + ((size_t)b * N + t) * nr, *fb = fb_.data() + ((size_t)b * N + t) * nr * nx;
+        int dst = nut;
+        auto move = [&](int src0, int n) {
+          for (int i = 0; i < n; ++i, ++dst) {
+            ff[dst] = ff[src0 + i];
+            for (int j = 0; j < nx; ++j)
+              fb[(size_t)dst * nx + j] = fb[(size_t)(src0 + i) * nx + j];
+          }
+        };
+        move(nu, nct);
+        move(nu + nc, nx);
+      }
   }
   void pack() {
     const int N = dims_.horizon;
@@ -330,8 +381,11 @@ private:
       const LqrProblem &p = *problems_[b];
       if ((int)p.horizon() + (term_controls_ ? 1 : 0) != N || (int)p.nc0() != dims_.nc0)
         throw RuntimeError("problems of a batch must share horizon and nc0");
-      for (int t = 0; t < N; ++t)
+      for (int t = 0; t < N; ++t) {
+        if ((int)p.stages[t].nu != knot_dims_[t].first || (int)p.stages[t].nc != knot_dims_[t].second)
+          throw RuntimeError("problems of a batch must share the per-knot dims");
         pack_stage(p.stages[t], stage_.data() + ((size_t)b * N + t) * srec_, term_controls_ && t == N - 1);
+      }
       if (!term_controls_) { // (with terminal controls the library's terminal knot is null: term_ stays zero)
         const LqrKnot &k = p.stages[N];
         if (k.nx != nx || k.nu != 0 || k.nc != nct)
@@ -373,8 +427,8 @@ private:
     if (term_controls_) { // the caller's horizon is N-1: N states, N controls, N multipliers; the null knot is dropped
       for (int t = 0; t < N; ++t) {
         xs[t].assign(xs_.begin() + ((size_t)b * (N + 1) + t) * nx, xs_.begin() + ((size_t)b * (N + 1) + t + 1) * nx);
-        us[t].assign(us_.begin() + ((size_t)b * N + t) * nu, us_.begin() + ((size_t)b * N + t + 1) * nu);
-        vs[t].assign(vs_.begin() + ((size_t)b * N + t) * nc, vs_.begin() + ((size_t)b * N + t + 1) * nc);
+        us[t].assign(us_.begin() + ((size_t)b * N + t) * nu, us_.begin() + ((size_t)b * N + t) * nu + knot_dims_[t].first);
+        vs[t].assign(vs_.begin() + ((size_t)b * N + t) * nc, vs_.begin() + ((size_t)b * N + t) * nc + knot_dims_[t].second);
         if (t + 1 < N)
           lbdas[t + 1].assign(ls_.begin() + ((size_t)b * N + t) * nx, ls_.begin() + ((size_t)b * N + t + 1) * nx);
       }
@@ -384,8 +438,8 @@ private:
     for (int t = 0; t <= N; ++t)
       xs[t].assign(xs_.begin() + ((size_t)b * (N + 1) + t) * nx, xs_.begin() + ((size_t)b * (N + 1) + t + 1) * nx);
     for (int t = 0; t < N; ++t) {
-      us[t].assign(us_.begin() + ((size_t)b * N + t) * nu, us_.begin() + ((size_t)b * N + t + 1) * nu);
-      vs[t].assign(vs_.begin() + ((size_t)b * N + t) * nc, vs_.begin() + ((size_t)b * N + t + 1) * nc);
+      us[t].assign(us_.begin() + ((size_t)b * N + t) * nu, us_.begin() + ((size_t)b * N + t) * nu + knot_dims_[t].first);
+      vs[t].assign(vs_.begin() + ((size_t)b * N + t) * nc, vs_.begin() + ((size_t)b * N + t) * nc + knot_dims_[t].second);
       lbdas[t + 1].assign(ls_.begin() + ((size_t)b * N + t) * nx, ls_.begin() + ((size_t)b * N + t + 1) * nx);
     }
     vs[N].assign(vsT_.begin() + (size_t)b * dims_.nct, vsT_.begin() + (size_t)(b + 1) * dims_.nct);
@@ -396,7 +450,8 @@ private:
   ab2_gar_dims dims_{};
   ab2_gar_solver *h_ = nullptr;
   size_t srec_ = 0, trec_ = 0;
-  bool term_controls_ = false;
+  bool term_controls_ = false, ragged_ = false;
+  std::vector<std::pair<int, int>> knot_dims_; // (nu, nc) of the caller's stage knots
   // pinned staging: uploads and downloads are asynchronous on the stream, one synchronisation per call
   PinnedBuf stage_, term_, G0_, g0_;
   PinnedBuf ff_, fb_, ffT_, fbT_;
@@ -407,6 +462,7 @@ protected:
     check(ab2_gar_get(h_, AB2_OUT_FF, ff_.data(), AB2_HOST, nullptr));
     check(ab2_gar_get(h_, AB2_OUT_FB, fb_.data(), AB2_HOST, nullptr));
     check(ab2_gar_synchronize(h_, nullptr));
+    compact_gains();
   }
 };
 

@@ -26,40 +26,47 @@ static orc::Problem to_oracle(const ab::LqrProblem &p) {
   return o;
 }
 
-static ab::LqrProblem random_problem(std::mt19937 &rng, unsigned nx, unsigned nu, unsigned nc, int N) {
+static ab::LqrKnot random_knot(std::mt19937 &rng, unsigned nx, unsigned nut, unsigned nct) {
   std::normal_distribution<double> nrm;
   std::uniform_real_distribution<double> uni(-1, 1);
-  std::vector<ab::LqrKnot> knots;
-  for (int t = 0; t <= N; ++t) {
-    const unsigned nut = t < N ? nu : 0, nct = t < N ? nc : 0;
-    ab::LqrKnot k(nx, nut, nct, nx);
-    const unsigned n = nx + nut;
-    std::vector<double> W((size_t)n * (n + 1));
-    for (auto &w : W) w = nrm(rng);
-    auto H = [&](unsigned i, unsigned j) {
-      double s = 0;
-      for (unsigned c = 0; c <= n; ++c) s += W[i + (size_t)c * n] * W[j + (size_t)c * n];
-      return s / std::max(nx, nut);
-    };
-    for (unsigned j = 0; j < nx; ++j)
-      for (unsigned i = 0; i < nx; ++i) k.Q[i + j * nx] = H(i, j);
-    for (unsigned j = 0; j < nut; ++j) {
-      for (unsigned i = 0; i < nx; ++i) k.S[i + j * nx] = H(i, nx + j);
-      for (unsigned i = 0; i < nut; ++i) k.R[i + j * nut] = H(nx + i, nx + j) * (i == j ? 1 + 1e-6 : 1);
-    }
-    for (unsigned j = 0; j < nx; ++j)
-      for (unsigned i = 0; i < nx; ++i) k.A[i + j * nx] = (i == j) + 0.1 * nrm(rng) / std::sqrt((double)nx);
-    for (auto &v : k.B) v = uni(rng);
-    for (auto &v : k.f) v = nrm(rng);
-    for (auto &v : k.q) v = uni(rng);
-    for (auto &v : k.r) v = uni(rng);
-    for (unsigned m = 0; m < nct && m < nut; ++m)
-      if (uni(rng) > 0) { k.D[m + m * nct] = 1.0; k.d[m] = uni(rng); }
-    knots.push_back(k);
+  ab::LqrKnot k(nx, nut, nct, nx);
+  const unsigned n = nx + nut;
+  std::vector<double> W((size_t)n * (n + 1));
+  for (auto &w : W) w = nrm(rng);
+  auto H = [&](unsigned i, unsigned j) {
+    double s = 0;
+    for (unsigned c = 0; c <= n; ++c) s += W[i + (size_t)c * n] * W[j + (size_t)c * n];
+    return s / std::max(nx, nut);
+  };
+  for (unsigned j = 0; j < nx; ++j)
+    for (unsigned i = 0; i < nx; ++i) k.Q[i + j * nx] = H(i, j);
+  for (unsigned j = 0; j < nut; ++j) {
+    for (unsigned i = 0; i < nx; ++i) k.S[i + j * nx] = H(i, nx + j);
+    for (unsigned i = 0; i < nut; ++i) k.R[i + j * nut] = H(nx + i, nx + j) * (i == j ? 1 + 1e-6 : 1);
   }
+  for (unsigned j = 0; j < nx; ++j)
+    for (unsigned i = 0; i < nx; ++i) k.A[i + j * nx] = (i == j) + 0.1 * nrm(rng) / std::sqrt((double)nx);
+  for (auto &v : k.B) v = uni(rng);
+  for (auto &v : k.f) v = nrm(rng);
+  for (auto &v : k.q) v = uni(rng);
+  for (auto &v : k.r) v = uni(rng);
+  for (unsigned m = 0; m < nct && m < nut; ++m)
+    if (uni(rng) > 0) { k.D[m + m * nct] = 1.0; k.d[m] = uni(rng); }
+  return k;
+}
+
+static ab::LqrProblem finish_problem(std::mt19937 &rng, std::vector<ab::LqrKnot> knots, unsigned nx) {
+  std::normal_distribution<double> nrm;
   ab::LqrProblem p(std::move(knots), nx);
   for (unsigned i = 0; i < nx; ++i) { p.G0[i + i * nx] = -1.0; p.g0[i] = nrm(rng); }
   return p;
+}
+
+static ab::LqrProblem random_problem(std::mt19937 &rng, unsigned nx, unsigned nu, unsigned nc, int N) {
+  std::vector<ab::LqrKnot> knots;
+  for (int t = 0; t <= N; ++t)
+    knots.push_back(random_knot(rng, nx, t < N ? nu : 0, t < N ? nc : 0));
+  return finish_problem(rng, std::move(knots), nx);
 }
 
 static double rel_fro(const double *a, const double *b, size_t n) {
@@ -164,8 +171,49 @@ static int check_terminal_controls(unsigned nx, unsigned nu, unsigned nc, int N,
   return worst <= 1e-10 ? 0 : 130;
 }
 
+// Every knot with its own (nu, nc) (gar/lqr-problem.hpp:49-118), terminal knot with controls: the class
+// pads to the largest dims and drops the padding rows again.
+static int check_ragged(unsigned seed) {
+  std::mt19937 rng(seed);
+  const unsigned nx = 6;
+  const double mueq = 1e-4;
+  const std::vector<std::pair<unsigned, unsigned>> dims = {{3, 0}, {2, 2}, {3, 1}, {1, 0}, {3, 2}, {2, 0}, {2, 1}};
+  const int N = (int)dims.size() - 1;
+  std::vector<ab::LqrKnot> knots;
+  for (auto &d : dims)
+    knots.push_back(random_knot(rng, nx, d.first, d.second));
+  ab::LqrProblem prob = finish_problem(rng, std::move(knots), nx);
+  ab::CudaRiccatiSolver solver(prob);
+  if (!solver.backward(mueq)) return 256;
+  std::vector<ab::VectorXs> xs, us, vs, lbdas;
+  ab::lqrInitializeSolution(prob, xs, us, vs, lbdas);
+  solver.forward(xs, us, vs, lbdas);
+  orc::Problem op = to_oracle(prob);
+  orc::ProximalRiccatiSolver ref(op);
+  ref.backward(mueq);
+  orc::Solution sol = orc::lqrInitializeSolution(op);
+  ref.forward(sol);
+  double worst = 0;
+  for (int t = 0; t <= N; ++t) {
+    if (us[t].size() != dims[t].first || vs[t].size() != dims[t].second) return 257;
+    worst = std::max(worst, rel_fro(xs[t].data(), sol.xs[t].data(), nx));
+    worst = std::max(worst, rel_fro(us[t].data(), sol.us[t].data(), us[t].size()));
+    if (!vs[t].empty()) worst = std::max(worst, rel_fro(vs[t].data(), sol.vs[t].data(), vs[t].size()));
+    worst = std::max(worst, rel_fro(lbdas[t].data(), sol.lbdas[t].data(), lbdas[t].size()));
+    auto fb = solver.getFeedback(t);
+    const size_t rows = dims[t].first + dims[t].second + (t < N ? nx : 0); // (the terminal knot's co-state rows are never written)
+    if ((size_t)fb.rows != dims[t].first + dims[t].second + nx) return 258;
+    worst = std::max(worst, rel_fro(fb.data, ref.datas[t].fb.data(), rows * nx));
+    auto ff = solver.getFeedforward(t);
+    worst = std::max(worst, rel_fro(ff.data, ref.datas[t].ff.data(), rows));
+  }
+  std::printf("ragged stage dims + terminal controls: max rel-Frobenius vs oracle %.2e\n", worst);
+  return worst <= 1e-10 ? 0 : 259;
+}
+
 int main() {
   int rc = 0;
+  rc |= check_ragged(31);
   rc |= check_terminal_controls(6, 3, 0, 10, 1e-8, 21);
   rc |= check_terminal_controls(4, 2, 2, 7, 1e-3, 22);
   rc |= check_parallel(6, 3, 50, 4, 1e-9, 11);

@@ -640,6 +640,44 @@ def test_terminal_knot_with_controls(gar, shape):
             assert gen.rel_fro(np.concatenate(mine), np.concatenate(theirs)) <= TOL
 
 
+def test_ragged_stage_dims_and_terminal_controls(gar):
+    """Every knot with its own (nu, nc) (gar/lqr-problem.hpp:49-118) AND a terminal knot with controls,
+    through the Python mirror (padding to the largest dims, gar._pad_knot): factors, value functions and
+    the solution against the oracle on the caller's unpadded problem."""
+    from aligator_b200.lqr import LqrProblem
+    nx, mueq = 6, 1e-4
+    dims = [(3, 0), (2, 2), (3, 1), (1, 0), (3, 2), (2, 0), (2, 1)]  # the last one is the terminal knot
+    N = len(dims) - 1
+    probs = []
+    for b in range(3):
+        rng = np.random.default_rng(40 + b)
+        knots = [gen.generate_knot(rng, nx, nu, nc, 0, False, conditioned=True) for nu, nc in dims]
+        p = LqrProblem(knots, nx)
+        p.G0[:] = -np.eye(nx)
+        p.g0[:] = rng.standard_normal(nx)
+        probs.append(p)
+    solver = gar.ProximalRiccatiSolver(probs)
+    assert solver.backward(mueq)
+    sols = [gar.lqr_initialize_solution(p) for p in probs]
+    assert solver.forward(*[list(z) for z in zip(*sols)])
+    for b, p in enumerate(probs):
+        op = orc.OracleProblem(p)
+        ref = orc.ProximalRiccatiSolver(op)
+        assert ref.backward(mueq)
+        for t, (nu, nc) in enumerate(dims):
+            f = ref.factor(t)
+            rows = nu + nc if t == N else nu + nc + nx
+            assert solver.getFeedback(t, b).shape[0] == nu + nc + nx
+            assert gen.rel_fro(solver.getFeedback(t, b)[:rows], f["fb"][:rows]) <= TOL, t
+            assert gen.rel_fro(solver.getFeedforward(t, b)[:rows], f["ff"][:rows]) <= TOL, t
+            assert gen.rel_fro(solver.Vxx(t, b), f["Vxx"]) <= TOL and gen.rel_fro(solver.vx(t, b), f["vx"]) <= TOL
+        sol = orc.OracleSolution(op)
+        assert ref.forward(sol)
+        for mine, theirs in zip(sols[b], sol.get()):
+            assert [len(m) for m in mine] == [len(r) for r in theirs]
+            assert gen.rel_fro(np.concatenate(mine), np.concatenate(theirs)) <= TOL
+
+
 PAR_SHAPES = [  # (nx, nu, nc, nct, N, legs, batch, mueq)
     (4, 2, 0, 0, 11, 3, 3, 1e-8), (6, 3, 0, 0, 20, 4, 5, 1e-8), (4, 2, 2, 0, 13, 2, 4, 1e-3),
     (14, 7, 0, 0, 200, 8, 6, 1e-9),   # BASELINE config 4 dims, 8 legs of 25 knots

@@ -38,3 +38,37 @@ def test_padding_is_the_terminal_solve_with_controls(shape):
     assert gen.rel_fro(np.concatenate(vb[:N + 1]), np.concatenate(va)) <= 1e-12
     assert gen.rel_fro(np.concatenate(lb[:N + 1]), np.concatenate(la)) <= 1e-12
     assert np.all(xb[N + 1] == 0.0) and np.all(lb[N + 1] == 0.0)
+
+
+def test_padding_of_ragged_stage_dims():
+    """Stage knots of different (nu, nc) padded to the largest (decoupled controls with R = I, null
+    constraint rows): the caller's rows of every factor and the whole solution are the unpadded
+    problem's, the padding rows exact zeros -- oracle on both sides."""
+    from aligator_b200.gar import _pad_stage_dims
+    from aligator_b200.lqr import LqrProblem
+    nx, N, mueq = 5, 6, 1e-4
+    dims = [(3, 0), (2, 2), (3, 1), (1, 0), (3, 2), (2, 0)]
+    rng = np.random.default_rng(3)
+    knots = [gen.generate_knot(rng, nx, nu, nc, 0, False, conditioned=True) for nu, nc in dims]
+    knots.append(gen.generate_knot(rng, nx, 0, 0, 0, False, conditioned=True))
+    p = LqrProblem(knots, nx)
+    p.G0[:] = -np.eye(nx)
+    p.g0[:] = rng.standard_normal(nx)
+    q = _pad_stage_dims(p, 3, 2)
+    a, b = orc.ProximalRiccatiSolver(orc.OracleProblem(p)), orc.ProximalRiccatiSolver(orc.OracleProblem(q))
+    assert a.backward(mueq) and b.backward(mueq)
+    for t, (nu, nc) in enumerate(dims):
+        fa, fb = a.factor(t), b.factor(t)
+        rows = np.r_[0:nu, 3:3 + nc, 5:5 + nx]
+        pad = np.setdiff1d(np.arange(5 + nx), rows)
+        assert gen.rel_fro(fb["fb"][rows], fa["fb"]) <= 1e-13 and gen.rel_fro(fb["ff"][rows], fa["ff"]) <= 1e-13
+        assert np.all(fb["fb"][pad] == 0.0) and np.all(fb["ff"][pad] == 0.0)
+        assert gen.rel_fro(fb["Vxx"], fa["Vxx"]) <= 1e-13
+    sa, sb = orc.OracleSolution(orc.OracleProblem(p)), orc.OracleSolution(orc.OracleProblem(q))
+    assert a.forward(sa) and b.forward(sb)
+    xa, ua, va, la = sa.get()
+    xb, ub, vb, lb = sb.get()
+    assert gen.rel_fro(np.concatenate(xb), np.concatenate(xa)) <= 1e-13
+    for t, (nu, nc) in enumerate(dims):
+        assert gen.rel_fro(ub[t][:nu], ua[t]) <= 1e-13 and np.all(ub[t][nu:] == 0.0)
+        assert gen.rel_fro(vb[t][:nc], va[t]) <= 1e-13 and np.all(vb[t][nc:] == 0.0)
