@@ -12,7 +12,7 @@ import aligator_b200.gar as gar  # noqa: E402
 
 nx, nu, N = 14, 7, 200
 rows = []
-for B in (64, 256, 1024):
+for B in (16, 64, 256):
     stage, term, G0, g0 = bench.synth_batch_torch(torch, B, N, nx, nu, "cuda:0", 7)
     for legs, variant in ((0, -1), (0, 9), (2, -1), (4, -1), (8, -1), (16, -1)):
         s = gar.CudaRiccatiBatch(nx, nu, 0, 0, nx, N, B, 0, variant, legs=legs)
