@@ -1083,8 +1083,9 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
                        AB2_STAGE_B + (size_t)stage_slot(p, t - 1) * C::SREC_PAD, C::SREC_PAD);
       cur ^= 1;
     }
-    if (t >= 4) { // and pull the record of 4 knots ahead into L2 (one 128-byte line per lane)
-      const char *nxt = reinterpret_cast<const char *>(AB2_STAGE_B + (size_t)stage_slot(p, t - 4) * C::SREC_PAD);
+    const int pfd = (p.dbg & 8) ? 2 : 4; // (debug flags 4 / 8: no prefetch / distance 2)
+    if (t >= pfd && !(p.dbg & 4)) { // and pull the record of 4 knots ahead into L2 (one 128-byte line per lane)
+      const char *nxt = reinterpret_cast<const char *>(AB2_STAGE_B + (size_t)stage_slot(p, t - pfd) * C::SREC_PAD);
       for (int o = lane * 128; o < C::SREC_PAD * 8; o += C::G * 128)
         prefetch_l2(nxt + o);
     }
