@@ -37,17 +37,22 @@ __global__ void first_step_policy_kernel(const double *__restrict__ fb, const do
 }
 
 // ---------------------------------------------------------------------------
-// Multi-GPU: pack of the first-step policy FUSED with its all-gather over NVLink peer memory.
-// Every rank owns a receive buffer [2][world][batch][nu][nx+1] (two halves, alternating by
-// step) + flag words, mapped into every peer by CUDA IPC.  Rank r's kernel computes each
-// element of its own block once and STORES it into the slot [half][r] of EVERY rank's buffer
-// (peer stores over NVLink / NVSwitch; no NCCL kernel, no staging copy), then the last CTA
-// to finish publishes the step number in every peer's data flag.  Flow control: the WAIT
-// kernel of step s (stream-ordered behind the consumers of step s-1 on the consumer's stream)
-// first tells every peer "everything up to s-1 is consumed here" (ack flag), then waits for
-// the data flags of step s; the pack kernel of step s waits until every peer has acknowledged
-// step s-2, whose data the half it is about to overwrite held.  A rank may thus run two steps
-// ahead of the slowest consumer -- the same slack a double-buffered NCCL gather has.
+// Multi-GPU: the all-gather of the first-step policy FUSED into the kernel that computes it, over
+// NVLink peer memory.  Every rank owns a receive buffer [3][world][batch][nu][nx+1] (three slots,
+// step s lives in slot s mod 3) + flag words, mapped into every peer by CUDA IPC.
+//  * warp-per-instance sweeps (SweepParams::peer_*): the sweep kernel itself stores an instance's
+//    [K0 | k0] into slot [s mod 3][r] of EVERY rank's buffer the moment its backward pass reaches
+//    knot 0 (posted peer stores over NVLink / NVSwitch that overlap the rest of the sweep; no pack
+//    kernel, no NCCL kernel, no staging copy); ab2_gar_policy_allgather then only publishes the
+//    step number in every peer's data flag (policy_publish_kernel);
+//  * every other kernel (CTA per instance, legs, dense): policy_allgather_kernel packs from the
+//    factor arrays and stores each element into every rank's slot, the last CTA publishes.
+// Flow control: the WAIT kernel of step s (stream-ordered behind the consumers of step s-1 on the
+// consumer's stream) first tells every peer "everything up to s-1 is consumed here" (ack flag),
+// then waits for the data flags of step s; the publish kernel of step s holds the producer's
+// stream until every peer has acknowledged step s-2 -- what the slot of step s+1 held.  A rank may
+// thus run two steps ahead of the slowest consumer, and NO flag is ever awaited inside the
+// persistent sweep (it would starve the kernel that writes the flag of an SM slot).
 // ---------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 struct PeerPtrs {
@@ -70,13 +75,13 @@ __global__ void __launch_bounds__(256)
   const int per = nu * (nx + 1);
   const long total = (long)batch * per;
   if (threadIdx.x == 0) {
-    if (step >= 3) // the half written now held step-2: every peer must have consumed it
+    if (step >= 3) // the slot written now held step-3: every peer has consumed it once it acknowledges step-2
       for (int w = 0; w < world; ++w)
         while (ld_acquire_sys(peers.ack_flag[rank] + w) + 2 < step)
           __nanosleep(64);
   }
   __syncthreads();
-  const size_t half = (size_t)(step & 1) * world * total;
+  const size_t half = (size_t)(step % 3) * world * total; // three slots
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int b = (int)(i / per), e = (int)(i % per), r = e / (nx + 1), c = e % (nx + 1);
     const double v = (c < nx) ? fb[((size_t)b * N * nr + r) * nx + c] : ff[(size_t)b * N * nr + r];
@@ -93,6 +98,23 @@ __global__ void __launch_bounds__(256)
       for (int w = 0; w < world; ++w)
         st_release_sys(peers.data_flag[w] + rank, step);
     }
+  }
+}
+// the sweep kernel stored this rank's blocks into every peer itself (SweepParams::peer_*): order them
+// before the flags (the kernel boundary orders the sweep's stores before this kernel; the fence and the
+// releases carry that to system scope)
+// It also holds the stream until every peer has consumed step - 2: the NEXT sweep stores into the slot that held
+// step - 2 (three slots).  That wait sits here, in a one-warp kernel behind the sweep, never inside the
+// persistent sweep: a kernel that fills every SM and spins on a flag which another kernel of the same GPU must
+// write (this rank's own wait kernel, on the side stream) can starve that kernel of an SM slot for ever.
+__global__ void policy_publish_kernel(const PeerPtrs peers, const int world, const int rank, const unsigned long long step) {
+  const int w = threadIdx.x;
+  __threadfence_system();
+  if (w < world) {
+    st_release_sys(peers.data_flag[w] + rank, step);
+    if (step >= 3)
+      while (ld_acquire_sys(peers.ack_flag[rank] + w) + 2 < step)
+        __nanosleep(64);
   }
 }
 // the stream waits until the blocks of every sender have arrived for `step`; before that it
@@ -228,11 +250,13 @@ struct ab2_gar_solver {
   // fused pack + all-gather over peer memory (multi-GPU)
   int pg_world = 0, pg_rank = 0;
   unsigned long long pg_step = 0;
-  void *pg_local = nullptr;          // cudaMalloc: [2][world][batch][per] doubles, then flags
+  void *pg_local = nullptr;          // cudaMalloc: [3][world][batch][per] doubles, then flags
   void *pg_peer_base[8] = {};        // IPC-opened bases (own entry = pg_local)
   ab2::PeerPtrs pg_ptrs{};
   unsigned int *pg_done = nullptr;
   size_t pg_buf_doubles = 0;
+  unsigned long long pg_pushed_step = 0; // the step whose blocks the last sweep stored into the peers itself
+  bool pg_in_sweep = true;               // env AB2_PEER_IN_SWEEP=0: always use the separate pack + store kernel
   double *out[AB2_OUT_COUNT] = {};
   size_t out_doubles[AB2_OUT_COUNT] = {};
   size_t out_rec[AB2_OUT_COUNT] = {};  // doubles per knot (or per instance)
@@ -449,6 +473,8 @@ static int create_impl(const ab2_gar_dims *dims, int nth, int legs, ab2_gar_solv
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device);
     p.num_sms = sms > 0 ? sms : 148;
   }
+  if (const char *f = std::getenv("AB2_PEER_IN_SWEEP")) // 0: the exchange always runs as its own pack + store kernel
+    s->pg_in_sweep = std::atoi(f) != 0;
   if (const char *f = std::getenv("AB2_DEBUG_FLAGS")) // experiment switches, see SweepParams::dbg
     p.dbg = std::atoi(f);
   if (std::getenv("AB2_PHASE_CLOCKS")) { // profiling aid of the CTA-per-instance kernel: 16 phase counters
@@ -649,7 +675,21 @@ static int launch(ab2_gar_solver *s, double mueq, int bwd, int fwd, void *stream
   s->p.mueq = mueq;
   s->p.do_bwd = bwd;
   s->p.do_fwd = fwd;
-  if (int rc = run_kernels(s, s->p, bwd, fwd, (cudaStream_t)stream))
+  ab2::SweepParams q = s->p;
+  q.peer_world = 0;
+  if (bwd && s->pg_in_sweep && s->pg_peer_base[0] && s->k && s->variant != 9 && s->legs <= 1 && !s->dense &&
+      s->d.horizon > 0) {
+    // sharded batch: the warp-per-instance sweep stores each instance's [K0 | k0] into every rank's receive
+    // buffer as soon as its backward pass is done (the exchange of step pg_step + 1)
+    const unsigned long long step = s->pg_step + 1;
+    const size_t total = (size_t)s->d.batch * s->d.nu * (s->d.nx + 1);
+    q.peer_world = s->pg_world;
+    for (int w = 0; w < s->pg_world; ++w)
+      q.peer_dst[w] = s->pg_ptrs.buf[w];
+    q.peer_off = (long long)((step % 3) * s->pg_world * total + (size_t)s->pg_rank * total);
+    s->pg_pushed_step = step;
+  }
+  if (int rc = run_kernels(s, q, bwd, fwd, (cudaStream_t)stream))
     return rc;
   if (bwd) {
     s->have_backward = true;
@@ -1274,7 +1314,7 @@ int ab2_gar_peer_gather_init(ab2_gar_solver *s, int world, int rank, void *ipc_h
     return fail(AB2_ERR_STATE, "peer_gather_init called twice");
   CUDA_TRY(cudaSetDevice(s->d.device));
   const size_t per = (size_t)s->d.nu * (s->d.nx + 1);
-  s->pg_buf_doubles = 2 * (size_t)world * s->d.batch * per;
+  s->pg_buf_doubles = 3 * (size_t)world * s->d.batch * per; // three slots: step s lives in slot s mod 3
   const size_t bytes = s->pg_buf_doubles * sizeof(double) + 2 * ab2::kMaxPeers * sizeof(unsigned long long);
   CUDA_TRY(cudaMalloc(&s->pg_local, bytes));
   CUDA_TRY(cudaMemset(s->pg_local, 0, bytes));
@@ -1320,9 +1360,12 @@ int ab2_gar_policy_allgather(ab2_gar_solver *s, void *stream) {
   if (blocks > 148 * 2)
     blocks = 148 * 2; // all resident at once: the last-CTA publication never waits on an unscheduled CTA
   s->pg_step += 1;
-  ab2::policy_allgather_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-      s->out[AB2_OUT_FB], s->out[AB2_OUT_FF], s->pg_ptrs, s->pg_world, s->pg_rank, s->d.batch, s->d.horizon, s->nr,
-      s->d.nu, s->d.nx, s->pg_step, s->pg_done);
+  if (s->pg_pushed_step == s->pg_step) // the sweep stored the blocks itself: publish the flags
+    ab2::policy_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->pg_ptrs, s->pg_world, s->pg_rank, s->pg_step);
+  else
+    ab2::policy_allgather_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        s->out[AB2_OUT_FB], s->out[AB2_OUT_FF], s->pg_ptrs, s->pg_world, s->pg_rank, s->d.batch, s->d.horizon, s->nr,
+        s->d.nu, s->d.nx, s->pg_step, s->pg_done);
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;
   return AB2_OK;
@@ -1341,7 +1384,7 @@ int ab2_gar_policy_allgather_wait(ab2_gar_solver *s, void *stream) {
 int ab2_gar_peer_gather_buffer(ab2_gar_solver *s, double **out, long *step) {
   if (!s || !out || !s->pg_local)
     return fail(AB2_ERR_STATE, "peer_gather_buffer before peer_gather_init");
-  const size_t half = (size_t)(s->pg_step & 1) * s->pg_world * s->d.batch * s->d.nu * (s->d.nx + 1);
+  const size_t half = (size_t)(s->pg_step % 3) * s->pg_world * s->d.batch * s->d.nu * (s->d.nx + 1);
   *out = (double *)s->pg_local + half;
   if (step)
     *step = (long)s->pg_step;

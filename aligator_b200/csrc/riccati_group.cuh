@@ -99,6 +99,16 @@ struct SweepParams {
   int legs;
   long long *clk; // profiling aid (null = off): per-phase clock64() sums of instance 0's CTA, riccati_block.cuh
   double *cond; // [batch][nc0 + nx*(2T-1)]: condensed solution [lbda0, x0, (theta_i, x_{head i+1})...] (:92-112)
+  // Sharded batch: the one exchange of the path (first-step policy [K0 | k0] of every instance) fused
+  // into the sweep.  As soon as an instance's backward pass reaches knot 0 its group stores the 
+  // nu x (nx+1) block straight into EVERY rank's receive buffer (NVLink peer memory; posted stores that
+  // overlap the rest of the sweep).  peer_world = 0: off.  Warp-per-instance kernels only.
+  // No flag is awaited inside the sweep (a persistent kernel that spins on something another kernel of the same
+  // GPU must produce can starve that kernel of an SM slot): the host side orders this launch after the peers'
+  // acknowledgements (ab2_gar_policy_allgather of the previous step).
+  int peer_world;
+  double *peer_dst[8]; // receive buffer of rank w (peer-mapped)
+  long long peer_off;  // doubles: slot * world * batch * per + rank * batch * per
 };
 
 // status bits: see ST_*; in leg mode several CTAs report on one instance
@@ -1759,6 +1769,19 @@ AB2_D void riccati_group_sweep(Ctx &ctx, const SweepParams &p, const int inst,
     }
 
     } // lane-per-column stage loop
+
+    // ---------------- sharded batch: this instance's first-step policy goes to every rank now
+    if (p.peer_world > 0 && N > 0) {
+      ctx.sync(); // the group's own stores of K_0, k_0 are ordered before its loads
+      constexpr int PER = NU * (NX + 1);
+      const double *fb0 = p.fb + (size_t)inst * N * NR * NX, *ff0 = p.ff + (size_t)inst * N * NR;
+      for (int e = lane; e < PER; e += C::G) {
+        const int r = e / (NX + 1), c = e - r * (NX + 1);
+        const double v = (c < NX) ? fb0[r * NX + c] : ff0[r];
+        for (int w = 0; w < p.peer_world; ++w)
+          p.peer_dst[w][p.peer_off + (long long)inst * PER + e] = v;
+      }
+    }
 
     // ---------------- initial stage: proximal-riccati.hxx:42-55 (nth = 0)
     {

@@ -250,16 +250,20 @@ int ab2_gar_kkt_error(ab2_gar_solver *s, double mueq, double *dst, int memspace,
 int ab2_gar_device_ptr(ab2_gar_solver *s, int what, double **out);
 
 /* Multi-GPU (one process per GPU, the batch sharded by instance): the ONE exchange
- * of a sweep -- the all-gather of the first-step policy [K_0 | k_0] -- fused with its pack kernel over
+ * of a sweep -- the all-gather of the first-step policy [K_0 | k_0] -- fused into the sweep over
  * NVLink peer memory instead of a separate NCCL collective.  Every rank owns a receive buffer
- * [world][batch][nu][nx+1] (double-buffered by step) that all peers map through CUDA IPC; the pack
- * kernel of rank r stores each element straight into slot r of every rank's buffer and publishes a
- * step flag (release/acquire at system scope) when its last CTA is done.
+ * [world][batch][nu][nx+1] (three slots, alternating by step) that all peers map through CUDA IPC.
+ * Once connected, every warp-per-instance backward / sweep launch stores each instance's block straight
+ * into slot r of every rank's buffer as soon as that instance's backward pass is done (other kernels:
+ * a pack kernel does the same stores); a step flag (release / acquire at system scope) publishes it.
  *   init:      allocate the local buffer; *ipc_handle_out = 64 bytes to hand to every peer
  *   connect:   all_handles = world x 64 bytes, rank order (exchange them with any host transport)
- *   allgather: enqueue pack+scatter of the current factors on `stream` (all ranks, same batch)
- *   wait:      `stream` waits until the blocks of every rank have arrived for the last allgather
- *   buffer:    device address of the half holding the last allgather, [world][batch][nu][nx+1] */
+ *   allgather: after backward / sweep, on the same `stream` (all ranks, same batch): publish the step
+ *              (pack + store first where the sweep has not done it); holds `stream` until every peer
+ *              has consumed what the next step's slot held
+ *   wait:      `stream` acknowledges the previous step as consumed, then waits until the blocks of every
+ *              rank have arrived for the last allgather
+ *   buffer:    device address of the slot holding the last allgather, [world][batch][nu][nx+1] */
 int ab2_gar_peer_gather_init(ab2_gar_solver *s, int world, int rank, void *ipc_handle_out);
 int ab2_gar_peer_gather_connect(ab2_gar_solver *s, const void *all_handles);
 int ab2_gar_policy_allgather(ab2_gar_solver *s, void *stream);

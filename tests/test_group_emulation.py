@@ -27,7 +27,8 @@ class SweepParams(C.Structure):
                 ("num_sms", C.c_int),
                 ("ctas_per_sm", C.c_int), ("stage_head", C.c_int), ("dbg", C.c_int), ("nth", C.c_int)] + \
                [(n, _dp) for n in ("theta", "fth", "Vxt", "Vtt", "vt", "kkt0fth", "thGrad", "thHess")] + \
-               [("legs", C.c_int), ("clk", C.c_void_p), ("cond", _dp)]
+               [("legs", C.c_int), ("clk", C.c_void_p), ("cond", _dp),
+                ("peer_world", C.c_int), ("peer_dst", C.c_void_p * 8), ("peer_off", C.c_longlong)]
 
 
 def _lib():
