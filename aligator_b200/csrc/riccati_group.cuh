@@ -82,7 +82,7 @@ struct SweepParams {
   int num_sms;
   int ctas_per_sm; // host-side launch hint: resident CTAs per SM wanted (0 = whatever fits)
   int stage_head;  // ring head of the stage records: knot t lives in slot (t + stage_head) mod N (O(1) cycleAppend)
-  int dbg;         // experiment switches (env AB2_DEBUG_FLAGS): 1 = no register fast path for the initial system, 2 = no proxy fence before the forward ring
+  int dbg;         // experiment switches (env AB2_DEBUG_FLAGS): 1 = no register fast path for the initial system, 2 = no proxy fence before the forward ring, 4 = L2 prefetch of the records ahead (8: at distance 2)
   // parametric problems (nth > 0; CTA-per-instance kernel only): riccati-kernel.hxx:185-192, 278-311
   int nth;
   const double *theta; // [batch][nth] or null (forward)
@@ -1093,8 +1093,12 @@ AB2_D void stage_loop_mma(Ctx &ctx, const SweepParams &p, double *__restrict__ s
                        AB2_STAGE_B + (size_t)stage_slot(p, t - 1) * C::SREC_PAD, C::SREC_PAD);
       cur ^= 1;
     }
-    const int pfd = (p.dbg & 8) ? 2 : 4; // (debug flags 4 / 8: no prefetch / distance 2)
-    if (t >= pfd && !(p.dbg & 4)) { // and pull the record of 4 knots ahead into L2 (one 128-byte line per lane)
+    // An L2 prefetch of the record 4 knots ahead used to sit here.  ncu: at C4 1.38 GB of the 5.36 GB read per
+    // launch were records fetched TWICE (evicted again before their TMA copy came; 2048 instances x 4 records x
+    // 5.4 KB next to 1.8 GB of streaming output), and the sweep is 1.7 % faster without it; at C2 it re-read
+    // 0.17 GB for no gain.  Off by default; AB2_DEBUG_FLAGS 4 / 12 bring it back at distance 4 / 2.
+    const int pfd = (p.dbg & 8) ? 2 : 4;
+    if (t >= pfd && (p.dbg & 4)) {
       const char *nxt = reinterpret_cast<const char *>(AB2_STAGE_B + (size_t)stage_slot(p, t - pfd) * C::SREC_PAD);
       for (int o = lane * 128; o < C::SREC_PAD * 8; o += C::G * 128)
         prefetch_l2(nxt + o);
