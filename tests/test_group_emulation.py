@@ -56,7 +56,7 @@ def _block_lib():
     return C.CDLL(BLOCK_LIB)
 
 
-def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0, block=0):
+def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0, block=0, peers=None):
     """block = 0: the warp-per-instance group program; block = NW > 0: the
     CTA-per-instance program of riccati_block.cuh with NW emulated warps."""
     lib = _block_lib() if block else _lib()
@@ -82,6 +82,12 @@ def run_emulated(nx, nu, nc, nct, N, probs, mueq, db=0, block=0):
     p.status = status.ctypes.data_as(C.POINTER(C.c_int))
     pivstat = np.zeros(B, dtype=np.int32)
     p.pivstat = pivstat.ctypes.data_as(C.POINTER(C.c_int))
+    if peers is not None:  # sharded batch: (receive buffers of every rank, offset in doubles) -- SweepParams::peer_*
+        bufs, off = peers
+        p.peer_world = len(bufs)
+        for w, b in enumerate(bufs):
+            p.peer_dst[w] = b.ctypes.data
+        p.peer_off = off
     if block < 0:  # compile-time specialisation of the block program (StaticBlockDims)
         rc = lib.emu_block_sweep_static(nx, nu, nc, int(-block), C.byref(p))
     elif block:
@@ -224,3 +230,25 @@ def test_pivot_statistics_and_initial_fast_path():
     ref = bo.get()
     for k in ("fb", "ff", "Vxx", "xs", "us", "vs", "lbdas"):
         assert gen.rel_fro(got[k], ref[k]) <= 1e-10, k
+
+
+@pytest.mark.parametrize("shape,db", [((12, 6, 0, 0, 6), 2), ((6, 3, 0, 0, 5), 0), ((4, 2, 2, 0, 4), 1)])
+def test_in_sweep_exchange_of_the_first_step_policy(shape, db):
+    """Sharded batch (SURVEY 8e): with SweepParams::peer_* set, the sweep itself stores every instance's
+    [K_0 | k_0] (nu x (nx+1), row-major) into slot [rank] of EVERY rank's receive buffer at peer_off --
+    here three host buffers stand in for the peer-mapped ones.  Everything else in the buffers stays
+    untouched, and the sweep's own outputs are unchanged."""
+    nx, nu, nc, nct, N = shape
+    B, world, rank, slot = 3, 3, 1, 2
+    probs = gen.generate_batch(5, B, N, nx, nu, nc, nct)
+    per = nu * (nx + 1)
+    total = B * per
+    bufs = [np.full(3 * world * total, -7.0) for _ in range(world)]
+    off = slot * world * total + rank * total
+    out = run_emulated(nx, nu, nc, nct, N, probs, 1e-6, db=db, peers=(bufs, off))
+    ref = run_emulated(nx, nu, nc, nct, N, probs, 1e-6, db=db)
+    assert np.array_equal(out["fb"], ref["fb"]) and np.array_equal(out["xs"], ref["xs"])
+    want = np.concatenate([out["fb"][:, 0, :nu, :], out["ff"][:, 0, :nu, None]], axis=2).ravel()
+    for b in bufs:
+        assert np.array_equal(b[off:off + total], want)
+        assert np.all(b[:off] == -7.0) and np.all(b[off + total:] == -7.0)
