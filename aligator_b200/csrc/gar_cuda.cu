@@ -235,6 +235,7 @@ struct ab2_gar_solver {
   ab2::SweepParams p;
   // owned device storage
   double *own_stage = nullptr, *own_term = nullptr, *own_G0 = nullptr, *own_g0 = nullptr;
+  double *own_stage_sym = nullptr; // triangle-packed stage records as uploaded by ab2_gar_sweep_host_sym
   double *gains_tmp = nullptr, *kkt_tmp = nullptr, *theta_dev = nullptr, *ls_tmp = nullptr;
   double *fddp_slack = nullptr, *fddp_G0 = nullptr, *fddp_g0 = nullptr, *fddp_vx = nullptr;
   int nth = 0;  // parameter dimension of the value function outputs (= nx in leg mode)
@@ -503,7 +504,7 @@ int ab2_gar_destroy(ab2_gar_solver *s) {
     cudaFree(s->pg_local);
   if (s->pg_done)
     cudaFree(s->pg_done);
-  for (double *q : {s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev, s->cond, s->ls_tmp, s->fddp_slack, s->fddp_G0,
+  for (double *q : {s->own_stage_sym, s->own_stage, s->own_term, s->own_G0, s->own_g0, s->gains_tmp, s->kkt_tmp, s->theta_dev, s->cond, s->ls_tmp, s->fddp_slack, s->fddp_G0,
                     s->fddp_g0, s->fddp_vx})
     if (q)
       cudaFree(q);
@@ -793,9 +794,106 @@ int ab2_gar_get_problem(ab2_gar_solver *s, int what, double *dst, int memspace, 
   return AB2_OK;
 }
 
+// ---- symmetric blocks travel as lower triangles (ab2_gar_sweep_host_sym) ----
+// source offset, in the triangle-packed record, of element e of the full record [A|B|f|Q|S|R|q|r|C|D|d]
+static inline __host__ __device__ int sym_source(int e, int nx, int nu, int nc) {
+  const int off_q = nx * nx + nx * nu + nx, tq = nx * (nx + 1) / 2, tr = nu * (nu + 1) / 2;
+  if (e < off_q)
+    return e;
+  e -= off_q;
+  if (e < nx * nx) { // Q(i, j), column-major; the lower triangle column by column: column j holds rows j..nx-1
+    int i = e % nx, j = e / nx;
+    if (i < j) {
+      const int t = i;
+      i = j;
+      j = t;
+    }
+    return off_q + j * nx - j * (j - 1) / 2 + (i - j);
+  }
+  e -= nx * nx;
+  if (e < nx * nu)
+    return off_q + tq + e;
+  e -= nx * nu;
+  if (e < nu * nu) {
+    int i = e % nu, j = e / nu;
+    if (i < j) {
+      const int t = i;
+      i = j;
+      j = t;
+    }
+    return off_q + tq + nx * nu + j * nu - j * (j - 1) / 2 + (i - j);
+  }
+  e -= nu * nu;
+  return off_q + tq + nx * nu + tr + e; // q, r, C, D, d
+}
+namespace ab2 {
+// full records from triangle-packed ones: HBM -> HBM, a table look-up per element (built once per CTA)
+__global__ void __launch_bounds__(256) expand_sym_kernel(const double *__restrict__ src, double *__restrict__ dst, const long nrec,
+                                                         const int nx, const int nu, const int nc, const int srec_full,
+                                                         const int srec_pad, const int srec_sym) {
+  extern __shared__ int lut[];
+  for (int e = threadIdx.x; e < srec_pad; e += blockDim.x)
+    lut[e] = e < srec_full ? sym_source(e, nx, nu, nc) : -1;
+  __syncthreads();
+  const long total = nrec * srec_pad;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / srec_pad;
+    const int e = (int)(i - r * srec_pad), o = lut[e];
+    dst[i] = o >= 0 ? src[r * srec_sym + o] : 0.0;
+  }
+}
+} // namespace ab2
+
+size_t ab2_gar_stage_record_doubles_sym(int nx, int nu, int nc) {
+  if (nx < 1 || nu < 0 || nc < 0)
+    return 0;
+  return (size_t)nx * nx + (size_t)nx * nu + nx + (size_t)nx * (nx + 1) / 2 + (size_t)nx * nu + (size_t)nu * (nu + 1) / 2 + nx + nu +
+         (size_t)nc * nx + (size_t)nc * nu + nc;
+}
+
+int ab2_gar_pack_stage_sym(int nx, int nu, int nc, const double *stage, double *stage_sym, long nrec) {
+  if (!stage || !stage_sym || nrec < 0 || nx < 1 || nu < 0 || nc < 0)
+    return fail(AB2_ERR_INVALID, "bad argument");
+  const int full = nx * nx + nx * nu + nx + nx * nx + nx * nu + nu * nu + nx + nu + nc * nx + nc * nu + nc;
+  const size_t pad = ab2_gar_stage_record_doubles(nx, nu, nc), sym = ab2_gar_stage_record_doubles_sym(nx, nu, nc);
+  std::vector<int> dst_of(sym, 0); // one full-record element per packed slot (the lower-triangle one)
+  for (int e = full - 1; e >= 0; --e) {
+    const int off_q = nx * nx + nx * nu + nx;
+    int keep = 1;
+    int r = e - off_q;
+    if (r >= 0 && r < nx * nx)
+      keep = (r % nx) >= (r / nx);
+    r -= nx * nx + nx * nu;
+    if (r >= 0 && r < nu * nu)
+      keep = (r % nu) >= (r / nu);
+    if (keep)
+      dst_of[sym_source(e, nx, nu, nc)] = e;
+  }
+  for (long k = 0; k < nrec; ++k)
+    for (size_t o = 0; o < sym; ++o)
+      stage_sym[(size_t)k * sym + o] = stage[(size_t)k * pad + dst_of[o]];
+  return AB2_OK;
+}
+
+static int sweep_host_impl(ab2_gar_solver *s, const double *stage, const double *term, const double *G0,
+                           const double *g0, double mueq, int nchunks, const int *whats,
+                           double *const *dsts, int nwhat, void *stream, bool sym);
 int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *term, const double *G0,
                        const double *g0, double mueq, int nchunks, const int *whats,
                        double *const *dsts, int nwhat, void *stream) {
+  return sweep_host_impl(s, stage, term, G0, g0, mueq, nchunks, whats, dsts, nwhat, stream, false);
+}
+int ab2_gar_sweep_host_sym(ab2_gar_solver *s, const double *stage_sym, const double *term, const double *G0,
+                           const double *g0, double mueq, int nchunks, const int *whats,
+                           double *const *dsts, int nwhat, void *stream) {
+  if (s && (s->rec_nth > 0 || s->legs > 1 || s->dense))
+    return fail(AB2_ERR_UNSUPPORTED, "sweep_host_sym: plain (nth = 0) serial handles only");
+  return sweep_host_impl(s, stage_sym, term, G0, g0, mueq, nchunks, whats, dsts, nwhat, stream, true);
+}
+
+static int sweep_host_impl(ab2_gar_solver *s, const double *stage, const double *term, const double *G0,
+                           const double *g0, double mueq, int nchunks, const int *whats,
+                           double *const *dsts, int nwhat, void *stream, const bool sym) {
   if (!s || !stage || !term || (s->d.nc0 > 0 && (!G0 || !g0)) || nwhat < 0 || (nwhat > 0 && (!whats || !dsts)))
     return fail(AB2_ERR_INVALID, "bad argument");
   for (int i = 0; i < nwhat; ++i)
@@ -821,6 +919,9 @@ int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *ter
   int rc;
   if ((rc = own(s->own_stage, stage_total(s))) != AB2_OK || (rc = own(s->own_term, (size_t)B * s->trec)) != AB2_OK ||
       (rc = own(s->own_G0, (size_t)B * nc0 * nx)) != AB2_OK || (rc = own(s->own_g0, (size_t)B * nc0)) != AB2_OK)
+    return rc;
+  const size_t srec_sym = ab2_gar_stage_record_doubles_sym(nx, s->d.nu, s->d.nc);
+  if (sym && (rc = own(s->own_stage_sym, (size_t)B * N * srec_sym)) != AB2_OK)
     return rc;
   s->p.stage = s->own_stage;
   s->p.stage_head = 0;
@@ -856,8 +957,35 @@ int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *ter
                                  (size_t)nb * per_inst * sizeof(double), cudaMemcpyHostToDevice, st));
       return AB2_OK;
     };
-    if ((rc = up(s->own_stage, stage, (size_t)N * s->srec)) != AB2_OK || (rc = up(s->own_term, term, s->trec)) != AB2_OK ||
+    // the small uploads first: enqueued behind the expansion kernel they would sit in the copy engine's queue
+    // behind the NEXT slice's records and hold this slice's sweep back by a whole upload
+    if ((rc = up(s->own_term, term, s->trec)) != AB2_OK ||
         (rc = up(s->own_G0, G0, (size_t)nc0 * nx)) != AB2_OK || (rc = up(s->own_g0, g0, nc0)) != AB2_OK)
+      return rc;
+    if (sym) { // lower triangles over PCIe, full records rebuilt in HBM
+      if ((rc = up(s->own_stage_sym, stage, (size_t)N * srec_sym)) != AB2_OK)
+        return rc;
+      const long nrec = (long)nb * N;
+      if (nrec > 0) {
+        const int full = nx * nx + nx * s->d.nu + nx + nx * nx + nx * s->d.nu + s->d.nu * s->d.nu + nx + s->d.nu +
+                         s->d.nc * nx + s->d.nc * s->d.nu + s->d.nc;
+        long blocks = (nrec * (long)s->srec + 255) / 256;
+        if (blocks > 148 * 8)
+          blocks = 148 * 8;
+        // same shared-memory carve-out as the sweeps it runs beside (an SM is configured for one carve-out at a time)
+        static bool carve = false;
+        if (!carve) {
+          CUDA_TRY(cudaFuncSetAttribute(ab2::expand_sym_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        (int)cudaSharedmemCarveoutMaxShared));
+          carve = true;
+        }
+        ab2::expand_sym_kernel<<<(int)blocks, 256, s->srec * sizeof(int), st>>>(
+            s->own_stage_sym + (size_t)b0 * N * srec_sym, s->own_stage + (size_t)b0 * N * s->srec, nrec, nx, s->d.nu, s->d.nc,
+            full, (int)s->srec, (int)srec_sym);
+        CUDA_TRY(cudaGetLastError());
+        s->launches += 1;
+      }
+    } else if ((rc = up(s->own_stage, stage, (size_t)N * s->srec)) != AB2_OK)
       return rc;
     const ab2::SweepParams q = slice_params(s, b0, nb);
     if (int rc2 = run_kernels(s, q, 1, 1, st))
@@ -1375,6 +1503,12 @@ int ab2_gar_policy_allgather_wait(ab2_gar_solver *s, void *stream) {
   if (!s || !s->pg_peer_base[0] || s->pg_step == 0)
     return fail(AB2_ERR_STATE, "policy_allgather_wait before policy_allgather");
   CUDA_TRY(cudaSetDevice(s->d.device));
+  static bool carve = false; // (an SM holds one shared-memory carve-out at a time: ask for the sweeps' so that this
+  if (!carve) {              //  kernel can start while a sweep is resident)
+    CUDA_TRY(cudaFuncSetAttribute(ab2::policy_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
+    carve = true;
+  }
   ab2::policy_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(s->pg_ptrs, s->pg_world, s->pg_rank, s->pg_step);
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;

@@ -97,6 +97,10 @@ def lib():
         L.ab2_gar_sweep_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_double, C.c_int, C.POINTER(C.c_int),
                                          C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+        L.ab2_gar_sweep_host_sym.argtypes = L.ab2_gar_sweep_host.argtypes
+        L.ab2_gar_stage_record_doubles_sym.restype = C.c_size_t
+        L.ab2_gar_stage_record_doubles_sym.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ab2_gar_pack_stage_sym.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_long]
         L.ab2_gar_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ab2_gar_get_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_int, C.c_void_p]
@@ -241,6 +245,26 @@ class CudaRiccatiBatch:
         _check(lib().ab2_gar_sweep_host(self.h, _ptr(stage), _ptr(term), _ptr(G0), _ptr(g0),
                                         C.c_double(mueq), int(nchunks), whats, dsts, len(outputs),
                                         C.c_void_p(stream)))
+
+    def sweep_host_sym(self, stage_sym, term, G0, g0, mueq, outputs, nchunks=0, stream=0):
+        """``sweep_host`` with the symmetric blocks Q, R of every stage knot sent as lower triangles
+        (``ab2_gar_sweep_host_sym``; records made by ``pack_stage_sym``): fewer bytes over PCIe."""
+        whats = (C.c_int * len(outputs))(*outputs.keys())
+        dsts = (C.c_void_p * len(outputs))(*[_ptr(a).value for a in outputs.values()])
+        self._keep = (stage_sym, term, G0, g0, outputs)
+        _check(lib().ab2_gar_sweep_host_sym(self.h, _ptr(stage_sym), _ptr(term), _ptr(G0), _ptr(g0),
+                                            C.c_double(mueq), int(nchunks), whats, dsts, len(outputs),
+                                            C.c_void_p(stream)))
+
+    def pack_stage_sym(self, stage, out=None):
+        """Full stage records [batch][N][srec] (host) -> triangle-packed records (``ab2_gar_pack_stage_sym``)."""
+        d = self.dims
+        n = int(lib().ab2_gar_stage_record_doubles_sym(d.nx, d.nu, d.nc))
+        nrec = d.batch * d.horizon
+        if out is None:
+            out = np.empty(max(nrec * n, 1), dtype=np.float64)
+        _check(lib().ab2_gar_pack_stage_sym(d.nx, d.nu, d.nc, _ptr(stage), _ptr(out), C.c_long(nrec)))
+        return out
 
     # ---- results ------------------------------------------------------------
     def out_shape(self, what):

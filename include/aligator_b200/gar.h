@@ -221,6 +221,18 @@ int ab2_gar_get_problem(ab2_gar_solver *s, int what, double *dst, int memspace, 
 int ab2_gar_sweep_host(ab2_gar_solver *s, const double *stage, const double *term, const double *G0,
                        const double *g0, double mueq, int nchunks, const int *whats,
                        double *const *dsts, int nwhat, void *stream);
+/* The same with the symmetric blocks of every stage knot sent as LOWER TRIANGLES (what Eigen's
+ * triangularView<Lower> of LqrKnotTpl::Q / ::R walks, lqr-problem.hpp:53-57; the Riccati recursion only ever
+ * needs those): record [A | B | f | Qlow nx(nx+1)/2 | S | Rlow nu(nu+1)/2 | q | r | C | D | d], column j of a
+ * triangle holding rows j..n-1, no padding.  The host path is PCIe-bound, so the 16 % fewer bytes at
+ * config 2 are 16 % less time; the full records are rebuilt in HBM by one streaming kernel per slice.
+ * Plain serial handles only (nth = 0).  pack_stage_sym is the host-side helper that derives the packed
+ * records from full ones (an adapter packs its Eigen matrices straight into this layout instead). */
+size_t ab2_gar_stage_record_doubles_sym(int nx, int nu, int nc);
+int ab2_gar_pack_stage_sym(int nx, int nu, int nc, const double *stage, double *stage_sym, long nrec);
+int ab2_gar_sweep_host_sym(ab2_gar_solver *s, const double *stage_sym, const double *term, const double *G0,
+                           const double *g0, double mueq, int nchunks, const int *whats,
+                           double *const *dsts, int nwhat, void *stream);
 
 /* Replaces: getFeedforward(i)/getFeedback(i) (riccati-base.hpp:33-34), the public
  * `datas[i].vm` / `kkt0` members (proximal-riccati.hpp:40-43) and the caller-owned

@@ -453,6 +453,40 @@ def test_pipelined_host_sweep_equals_plain_calls(gar, shape, chunks):
     s.close()
 
 
+@pytest.mark.parametrize("shape,chunks", [((12, 6, 0, 0, 9, 11, 1e-8), 3), ((4, 2, 2, 2, 7, 9, 1e-3), 2),
+                                          ((9, 5, 3, 0, 5, 6, 1e-2), 0)])
+def test_host_sweep_with_triangle_packed_records(gar, shape, chunks):
+    """ab2_gar_sweep_host_sym: Q and R of every stage knot cross PCIe as lower triangles
+    (ab2_gar_pack_stage_sym) and are rebuilt in HBM -- bit for bit the results of the plain host sweep
+    (the generator's Q, R are exactly symmetric: wishart products)."""
+    import torch
+    nx, nu, nc, nct, N, B, mueq = shape
+    probs = gen.generate_batch(8, B, N, nx, nu, nc, nct)
+    for p in probs:  # exact symmetry, whatever the generator's arithmetic did
+        for k in p.stages:
+            k.Q[:] = 0.5 * (k.Q + k.Q.T)
+            k.R[:] = 0.5 * (k.R + k.R.T)
+    plain, packed = run_cuda(gar, probs, nx, nu, nc, nct, N, mueq)
+    s = gar.CudaRiccatiBatch(nx, nu, nc, nct, probs[0].nc0, N, B)
+    sym = s.pack_stage_sym(np.ascontiguousarray(packed[0]))
+    nsym = int(gar.lib().ab2_gar_stage_record_doubles_sym(nx, nu, nc))
+    assert sym.size == B * N * nsym and nsym < s.srec
+    pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (sym,) + tuple(packed[1:])]
+    whats = dict(fb=gar.OUT_FB, ff=gar.OUT_FF, xs=gar.OUT_XS, us=gar.OUT_US, lbdas=gar.OUT_LBDAS, Vxx=gar.OUT_VXX)
+    outs = {w: torch.full((max(int(np.prod(s.out_shape(w))), 1),), np.nan, dtype=torch.float64).pin_memory()
+            for w in whats.values()}
+    for _ in range(2):
+        s.sweep_host_sym(pin[0], pin[1], pin[2], pin[3], mueq, outs, nchunks=chunks)
+        s.synchronize()
+    for k, w in whats.items():
+        got = outs[w].numpy()[:int(np.prod(s.out_shape(w)))].reshape(s.out_shape(w))
+        if k == "Vxx":
+            got = got.transpose(0, 1, 3, 2)
+        assert np.array_equal(got, plain[k]), k
+    assert np.all(s.status() == 0)
+    s.close()
+
+
 def test_first_step_policy_kernel(gar):
     """ab2_gar_first_step_policy packs [K_0 | k_0] exactly as the host-side reference packing
     of knot 0 of OUT_FB / OUT_FF (aligator_b200.sharding.pack_first_step_policy)."""
