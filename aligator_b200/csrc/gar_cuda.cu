@@ -979,6 +979,9 @@ static int sweep_host_impl(ab2_gar_solver *s, const double *stage, const double 
                                         (int)cudaSharedmemCarveoutMaxShared));
           carve = true;
         }
+        if (s->srec * sizeof(int) > 48 * 1024) // (records beyond 12 288 doubles: opt in to the larger table)
+          CUDA_TRY(cudaFuncSetAttribute(ab2::expand_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(s->srec * sizeof(int))));
         ab2::expand_sym_kernel<<<(int)blocks, 256, s->srec * sizeof(int), st>>>(
             s->own_stage_sym + (size_t)b0 * N * srec_sym, s->own_stage + (size_t)b0 * N * s->srec, nrec, nx, s->d.nu, s->d.nc,
             full, (int)s->srec, (int)srec_sym);
