@@ -1469,7 +1469,17 @@ int ab2_gar_peer_gather_connect(ab2_gar_solver *s, const void *all_handles) {
     if (w != s->pg_rank) {
       cudaIpcMemHandle_t h;
       std::memcpy(&h, (const char *)all_handles + 64 * (size_t)w, sizeof(h));
-      CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+      const cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { // no peer access / IPC not permitted: leave the handle unconnected (callers fall back)
+        cudaGetLastError();
+        for (int v = 0; v < w; ++v) {
+          if (v != s->pg_rank && s->pg_peer_base[v])
+            cudaIpcCloseMemHandle(s->pg_peer_base[v]);
+          s->pg_peer_base[v] = nullptr;
+        }
+        return fail(AB2_ERR_CUDA, std::string("peer_gather_connect: cudaIpcOpenMemHandle(rank ") + std::to_string(w) +
+                                      "): " + cudaGetErrorString(e));
+      }
     }
     s->pg_peer_base[w] = base;
     s->pg_ptrs.buf[w] = (double *)base;

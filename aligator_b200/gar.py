@@ -378,12 +378,22 @@ class CudaRiccatiBatch:
         import torch
         L = lib()
         h = (C.c_ubyte * 64)()
-        _check(L.ab2_gar_peer_gather_init(self.h, int(world), int(rank), h))
-        mine = bytes(h)
+        # every rank takes part in both collectives whatever happens locally, and all ranks raise together:
+        # a rank that cannot map its peers (no IPC / no peer access) must not leave the others waiting
+        err = None
+        if L.ab2_gar_peer_gather_init(self.h, int(world), int(rank), h) != 0:
+            err = L.ab2_gar_last_error().decode()
         allh = [None] * world
-        dist.all_gather_object(allh, mine)
-        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(allh))
-        _check(L.ab2_gar_peer_gather_connect(self.h, blob))
+        dist.all_gather_object(allh, (err, bytes(h)))
+        if err is None and all(e is None for e, _ in allh):
+            blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(b for _, b in allh))
+            if L.ab2_gar_peer_gather_connect(self.h, blob) != 0:
+                err = L.ab2_gar_last_error().decode()
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        bad = [(r, e) for r, (e0, _) in enumerate(allh) for e in [e0 or errs[r]] if e]
+        if bad:
+            raise GarError("peer gather unavailable (rank %d: %s)" % bad[0])
         dist.barrier()
         torch.cuda.synchronize()
 

@@ -398,8 +398,12 @@ def main():
 
     from aligator_b200 import sharding
     peer = world > 1 and args.gather == "peer"
+    peer_note = None
     if peer:
-        solver.peer_gather_setup(dist, rank, world)
+        try:  # (collective-safe: every rank raises or none does)
+            solver.peer_gather_setup(dist, rank, world)
+        except gar.GarError as e:  # no CUDA IPC / peer access on this box: the library collective takes over
+            peer, peer_note = False, str(e)
     waited = [None]
 
     def step():
@@ -584,7 +588,7 @@ def main():
         sst = synth_batch_torch(torch, sb, sN, snx, snu, dev, 4321 + rank, snc)
         s3 = gar.CudaRiccatiBatch(snx, snu, snc, snct, snx, sN, sb, device=local, legs=args.strong_legs)
         s3.set_problem(*sst, memspace=gar.AB2_DEVICE, stream=stream)
-        speer = world > 1 and args.gather == "peer" and sb * world == sB
+        speer = peer and sb * world == sB
         if speer:
             s3.peer_gather_setup(dist, rank, world)
         sw = [None]
@@ -696,7 +700,8 @@ def main():
                              % ((stage.numel() * 8 + B * (N + 1) * 8 * ((NU + NC + NX) * (NX + 1) + NX * NX + NX)) / 1e9),
                        "kernel": solver.kernel_info(), "variant": args.variant, "numa": numa,
                        "exchange": ("fused pack + NVLink peer-memory all-gather of [K0|k0] (no NCCL on the data path)"
-                                    if peer else ("ncclAllGather of [K0|k0]" if world > 1 else "none (1 GPU)"))},
+                                    if peer else (("ncclAllGather of [K0|k0]" + (" (peer memory unavailable: %s)" % peer_note if peer_note else ""))
+                                                  if world > 1 else "none (1 GPU)"))},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e,
             "gpu_launches": launches, "parity": parity, "strong": strong, "e2e_device": e2e_device}
     print(json.dumps(line))

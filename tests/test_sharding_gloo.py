@@ -56,3 +56,32 @@ def test_policy_all_gather_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, 5, 3, 6, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def _peer_setup_worker(rank, world, port, ret):
+    """peer_gather_setup on a box where the peer buffers cannot be set up (here: no CUDA at all): every rank takes
+    part in the same collectives and EVERY rank raises GarError -- nobody is left waiting in an all-gather."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import aligator_b200.gar as gar
+    s = object.__new__(gar.CudaRiccatiBatch)  # no device: the handle cannot exist; the C entry point refuses a null one
+    s.h = None
+    try:
+        s.peer_gather_setup(dist, rank, world)
+        ret[rank] = "no error"
+    except gar.GarError as e:
+        ret[rank] = "GarError: " + str(e)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_gather_setup_fails_on_all_ranks_together():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_peer_setup_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0].startswith("GarError: peer gather unavailable") and ret[1].startswith("GarError: peer gather unavailable")
